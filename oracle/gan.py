@@ -1,0 +1,187 @@
+"""Oracle (test infrastructure): losses, penalties, TF-form Adam, EMA and one
+ModularGAN training cycle (disc_iters D-updates + 1 G-update, unrolled/TPU
+semantics) restated on PyTorch-CPU.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import nets
+from . import tf_ops as T
+
+
+# --------------------------------------------------------------------------- loss_lib
+
+def _check_pair(a, b):
+  if tuple(a) != tuple(b):
+    raise ValueError("Shape mismatch: %s vs %s." % (tuple(a), tuple(b)))
+  if len(a) != 2 or len(b) != 2:
+    raise ValueError("Rank: expected 2, got %s and %s" % (len(a), len(b)))
+
+
+def get_losses(fn, d_real, d_fake, d_real_logits, d_fake_logits):
+  """gans/loss_lib.py:53-154 -> (d_loss, d_loss_real, d_loss_fake, g_loss)."""
+  _check_pair(d_real_logits.shape, d_fake_logits.shape)
+  if fn == "non_saturating":      # :53-78
+    lr = T.sigmoid_ce(d_real_logits, True).mean()
+    lf = T.sigmoid_ce(d_fake_logits, False).mean()
+    return lr + lf, lr, lf, T.sigmoid_ce(d_fake_logits, True).mean()
+  if fn == "wasserstein":         # :81-101
+    lr = -d_real_logits.mean()
+    lf = d_fake_logits.mean()
+    return lr + lf, lr, lf, -lf
+  if fn == "least_squares":       # :104-124
+    lr = ((d_real - 1.0) ** 2).mean()
+    lf = (d_fake ** 2).mean()
+    return 0.5 * (lr + lf), lr, lf, 0.5 * ((d_fake - 1.0) ** 2).mean()
+  if fn == "hinge":               # :127-148
+    lr = torch.relu(1.0 - d_real_logits).mean()
+    lf = torch.relu(1.0 + d_fake_logits).mean()
+    return lr + lf, lr, lf, -d_fake_logits.mean()
+  raise ValueError(fn)
+
+
+# --------------------------------------------------------------------------- penalty_lib
+
+def wgangp_penalty(store, cfg, x, x_fake, y, is_training, alpha):
+  """gans/penalty_lib.py:59-82; ``alpha`` [B,1,1,1] is fed (SURVEY §5 RNG)."""
+  xi = (x + alpha * (x_fake - x)).detach().requires_grad_(True)
+  logits = nets.discriminator(store, cfg, xi, y, is_training)[1]
+  g = torch.autograd.grad(logits.sum(), xi, create_graph=True)[0]
+  slopes = torch.sqrt(0.0001 + (g * g).sum(dim=(1, 2, 3)))
+  return ((slopes - 1.0) ** 2).mean()
+
+
+def get_penalty_loss(fn, store, cfg, x, x_fake, y, is_training, alpha=None):
+  """gans/penalty_lib.py:105-108."""
+  if fn == "no_penalty":
+    return torch.zeros(())
+  if fn == "wgangp_penalty":
+    return wgangp_penalty(store, cfg, x, x_fake, y, is_training, alpha)
+  raise ValueError(fn)
+
+
+# --------------------------------------------------------------------------- optimizer
+
+class TFAdam(object):
+  """tf.train.AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+  theta -= lr_t*m/(sqrt(v)+eps), eps=1e-8 outside the corrected sqrt."""
+
+  def __init__(self, params, lr, beta1, beta2, eps=1e-8):
+    self.params = params            # OrderedDict name -> tensor
+    self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+    self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in params.items())
+    self.v = OrderedDict((k, torch.zeros_like(v)) for k, v in params.items())
+    self.t = 0
+
+  def step(self, grads):
+    self.t += 1
+    lr_t = self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+    lr_t = np.float32(lr_t)
+    with torch.no_grad():
+      for k, p in self.params.items():
+        g = grads[k]
+        self.m[k].mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+        self.v[k].mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        p.sub_(lr_t * self.m[k] / (self.v[k].sqrt() + self.eps))
+
+
+# --------------------------------------------------------------------------- ModularGAN cycle
+
+class GanOracle(object):
+  """gans/modular_gan.py restated (model_fn :512-604, create_loss :618-670)."""
+
+  def __init__(self, cfg, loss="non_saturating", penalty="no_penalty", lamba=1.0, disc_iters=1,
+               g_lr=2e-4, d_lr=None, beta1=0.5, beta2=0.999, conditional=False,
+               g_use_ema=False, ema_decay=0.9999, ema_start_step=40000, z_dim=128, seed=0):
+    self.cfg, self.loss, self.penalty = cfg, loss, penalty
+    self.lamba, self.disc_iters = lamba, disc_iters
+    self.g_lr, self.d_lr = g_lr, g_lr if d_lr is None else d_lr
+    self.beta1, self.beta2 = beta1, beta2
+    self.conditional = conditional
+    self.g_use_ema, self.ema_decay, self.ema_start_step = g_use_ema, ema_decay, ema_start_step
+    self.z_dim = z_dim
+    self.store = nets.VarStore(seed)
+    self.global_step = 0        # counts G steps  (modular_gan_test.py:175-177)
+    self.global_step_disc = 0   # counts D steps
+    self.d_opt = self.g_opt = None
+    self.ema = None
+
+  def one_hot(self, labels):
+    return torch.nn.functional.one_hot(torch.as_tensor(labels).long(),
+                                       self.cfg.num_classes).float()
+
+  def build(self, batch):
+    """Create all variables by one G and one D call (like TF graph construction)."""
+    h, w, c = self.cfg.image_shape
+    z = torch.zeros(batch, self.z_dim)
+    y = self.one_hot(np.zeros(batch, np.int64)) if self.conditional else None
+    with torch.no_grad():
+      x = nets.generator(self.store, self.cfg, z, y, True)
+      nets.discriminator(self.store, self.cfg, torch.cat([x, x]),
+                         None if y is None else torch.cat([y, y]), True)
+      # graph construction runs no ops in TF: undo the moving-average / u_var side effects
+      for k, v in self.store.vars.items():
+        if k.endswith("moving_mean"):
+          v.zero_()
+        elif k.endswith("moving_variance"):
+          v.fill_(1.0)
+    return self
+
+  def _ensure_opts(self):
+    if self.d_opt is None:
+      self.d_opt = TFAdam(self.store.trainable_under("discriminator"), self.d_lr, self.beta1, self.beta2)
+      self.g_opt = TFAdam(self.store.trainable_under("generator"), self.g_lr, self.beta1, self.beta2)
+      if self.g_use_ema:
+        self.ema = OrderedDict((k, v.detach().clone())
+                               for k, v in self.store.trainable_under("generator").items())
+
+  def create_loss(self, images, generated, y, sampled_y, alpha=None, for_d=True):
+    """modular_gan.py:618-670: D on concat([real, fake]) as ONE batch of 2B."""
+    all_images = torch.cat([images, generated], 0)
+    all_y = torch.cat([y, sampled_y], 0) if self.conditional else None
+    d_all, d_all_logits, _ = nets.discriminator(self.store, self.cfg, all_images, all_y, True)
+    b = images.shape[0]
+    d_loss, _, _, g_loss = get_losses(self.loss, d_all[:b], d_all[b:], d_all_logits[:b], d_all_logits[b:])
+    if not for_d:   # g_loss does not depend on the penalty sub-graph, TF never runs it
+      return None, g_loss
+    pen = get_penalty_loss(self.penalty, self.store, self.cfg, images, generated, y, True, alpha)
+    return d_loss + self.lamba * pen, g_loss
+
+  def cycle(self, images, z, labels=None, sampled_labels=None, alphas=None):
+    """One unrolled cycle.  images/z/...: lists of length disc_iters+1 (one per sub-step)."""
+    self._ensure_opts()
+    k = self.disc_iters
+    ys = [self.one_hot(l) for l in labels] if self.conditional else [None] * (k + 1)
+    sys_ = [self.one_hot(l) for l in sampled_labels] if self.conditional else [None] * (k + 1)
+    # _split_inputs_and_generate_samples :428-469 — all G forwards up front.
+    gens = []
+    for i in range(k + 1):
+      with torch.set_grad_enabled(i == k):   # only the G-step sample needs a backward graph
+        gens.append(nets.generator(self.store, self.cfg, torch.as_tensor(z[i]), sys_[i], True))
+    d_losses = []
+    for i in range(k):                                  # _train_discriminator :471-485
+      gen = gens[i].detach()
+      d_loss, _ = self.create_loss(torch.as_tensor(images[i]), gen, ys[i], sys_[i],
+                                   None if alphas is None else torch.as_tensor(alphas[i]))
+      params = self.store.trainable_under("discriminator")
+      grads = torch.autograd.grad(d_loss, list(params.values()), allow_unused=True)
+      self.d_opt.step({n: (g if g is not None else torch.zeros_like(p))
+                       for (n, p), g in zip(params.items(), grads)})
+      self.global_step_disc += 1
+      d_losses.append(float(d_loss))
+    # _train_generator :487-510 — new D forward with updated D, G grads only.
+    _, g_loss = self.create_loss(torch.as_tensor(images[k]), gens[k], ys[k], sys_[k],
+                                 None, for_d=False)
+    params = self.store.trainable_under("generator")
+    grads = torch.autograd.grad(g_loss, list(params.values()), allow_unused=True)
+    self.g_opt.step({n: (g if g is not None else torch.zeros_like(p))
+                     for (n, p), g in zip(params.items(), grads)})
+    if self.g_use_ema:                                  # :498-508
+      decay = self.ema_decay * float(self.global_step >= self.ema_start_step)
+      with torch.no_grad():
+        for n, p in params.items():
+          self.ema[n].sub_((self.ema[n] - p) * (1.0 - decay))
+    self.global_step += 1
+    return d_losses, float(g_loss)

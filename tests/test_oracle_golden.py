@@ -1,0 +1,192 @@
+"""Pin the CPU oracle against every golden the reference's own tests hold for the
+hot path.  Runs on CPU."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import gan, metrics, nets
+from oracle import tf_ops as T
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+V = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "resnet_cifar_variables.json")))
+
+
+def test_batch_norm_golden():
+  # architectures/arch_ops_test.py:29-61
+  x = torch.tensor(G["bn_input"]["x"], dtype=torch.float32)
+  assert list(x.shape) == [4, 2, 1, 3]
+  store, cfg = nets.VarStore(), nets.Cfg()
+  y = nets.batch_norm(store, cfg, x, True)
+  np.testing.assert_allclose(y.detach().numpy(), np.array(G["bn_expected"]["y"], np.float32),
+                             rtol=1e-6, atol=1e-6)
+
+
+def test_cross_replica_batch_norm_equals_single():
+  # architectures/arch_ops_tpu_test.py:112-133: 2-replica sync BN == the single-device golden
+  x = torch.tensor(G["bn_input"]["x"], dtype=torch.float32)
+  store, cfg = nets.VarStore(), nets.Cfg(bn_replicas=2)
+  y = nets.batch_norm(store, cfg, x, True)
+  np.testing.assert_allclose(y.detach().numpy(), np.array(G["bn_expected"]["y"], np.float32),
+                             rtol=1e-6, atol=1e-6)
+
+
+def test_cross_replica_mean_golden():
+  # tpu/tpu_ops_test.py:79-83
+  inp = np.array(G["cross_replica_mean"]["inputs"], np.float32)
+  out = T.cross_replica_mean([torch.from_numpy(inp[0]), torch.from_numpy(inp[1])])
+  np.testing.assert_allclose(out.numpy(), G["cross_replica_mean"]["expected"], atol=1e-6)
+
+
+def test_accumulated_moments_state_machine():
+  # architectures/arch_ops_test.py:63-132 driven through standardize_batch's accumulator path.
+  cfg = nets.Cfg(use_moving_averages=False, bn_eps=0.0)
+  store = nets.VarStore()
+
+  def feed(mean, var, training):
+    # a 2-sample batch with exactly the requested per-channel mean / biased variance
+    m, v = np.array(mean, np.float32), np.array(var, np.float32)
+    x = torch.from_numpy(np.stack([m - np.sqrt(v), m + np.sqrt(v)]).reshape(2, 1, 1, 2))
+    y = nets.standardize_batch(store, cfg, x, training)
+    # recover the (mean, var) the layer used from its output: y = (x-mean)/sqrt(var)
+    x0, x1 = x[0, 0, 0], x[1, 0, 0]
+    y0, y1 = y[0, 0, 0], y[1, 0, 0]
+    inv = (y1 - y0) / (x1 - x0)
+    used_mean = x0 - y0 / inv
+    return used_mean.numpy(), (1.0 / inv ** 2).numpy()
+
+  # training: batch moments pass through, accumulators untouched (:63-89)
+  for mean, var in G["accu_moments"]["feeds"][:2]:
+    m, v = feed(mean, var, True)
+    np.testing.assert_allclose(m, mean, rtol=1e-5)
+    np.testing.assert_allclose(v, var, rtol=1e-4)
+  assert float(store.vars["accu/accu_mean"].sum()) == 0.0
+  assert abs(float(store.vars["accu/accu_counter"])) < 1e-6
+  # eval with update_accus=1, then 0 (:91-132)
+  store.vars["accu/update_accus"].fill_(1.0)
+  feeds, outs = G["accu_moments"]["feeds"], G["accu_moments"]["eval_outputs"]
+  for i in range(2):
+    m, v = feed(feeds[i][0], feeds[i][1], False)
+    np.testing.assert_allclose(m, outs[i][0], rtol=1e-4)
+    np.testing.assert_allclose(v, outs[i][1], rtol=1e-4)
+  store.vars["accu/update_accus"].fill_(0.0)
+  m, v = feed(feeds[2][0], feeds[2][1], False)
+  np.testing.assert_allclose(m, outs[2][0], rtol=1e-4)
+  np.testing.assert_allclose(v, outs[2][1], rtol=1e-4)
+  aa = G["accu_moments"]["accu_after"]
+  np.testing.assert_allclose(store.vars["accu/accu_mean"].numpy(), aa["mean"], rtol=1e-5)
+  np.testing.assert_allclose(store.vars["accu/accu_variance"].numpy(), aa["variance"], rtol=1e-5)
+  np.testing.assert_allclose(float(store.vars["accu/accu_counter"]), aa["counter"], rtol=1e-6)
+
+
+def test_fid_golden():
+  # metrics/fid_score_test.py:31-40
+  real = np.ones((100, 2)); real[:50, 0] = 2
+  gen = np.ones((100, 2)) * 9; gen[50:, 0] = 2
+  assert abs(metrics.compute_fid_from_activations(real, gen) - G["fid"]["value"]) < G["fid"]["tol"]
+
+
+def _names(cfg, which, trainable):
+  store = nets.VarStore()
+  z = torch.zeros(8, 128)
+  with torch.no_grad():
+    if which == "g":
+      out = nets.generator(store, cfg, z, None, True)
+      assert list(out.shape) == [8, 32, 32, 3]
+    else:
+      nets.discriminator(store, cfg, torch.zeros(8, 32, 32, 3), None, True)
+  src = store.trainable if trainable else store.vars
+  return [[k, list(v.shape)] for k, v in src.items()]
+
+
+def test_resnet_cifar_variable_lists():
+  # architectures/resnet_norm_test.py:39-63, 78-106, 124-162, 326-361
+  assert _names(nets.Cfg(g_bn=None), "g", True) == V["g_default"]
+  assert _names(nets.Cfg(g_bn=None), "d", True) == V["d_default"]
+  assert _names(nets.Cfg(g_bn="batch_norm"), "g", True) == V["g_batch_norm"]
+  assert _names(nets.Cfg(g_bn=None, g_sn=True), "g", False) == V["g_spectral_norm_global"]
+
+
+def test_biggan128_parameter_counts():
+  # architectures/resnet_biggan_test.py:112-154
+  cfg = nets.Cfg(architecture="resnet_biggan_arch", image_shape=(128, 128, 3),
+                 g_bn="conditional_batch_norm", g_sn=True, d_sn=True, sn_singular="auto",
+                 hierarchical_z=True, embed_y=True, project_y=True, num_classes=1000,
+                 use_moving_averages=False)
+  store = nets.VarStore()
+  with torch.no_grad():
+    z = torch.zeros(2, 120)
+    y = torch.zeros(2, 1000); y[:, 1] = 1
+    x = nets.generator(store, cfg, z, y, True)
+    assert list(x.shape) == [2, 128, 128, 3]
+    assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0   # architectures_test.py:51-57
+    d, _, _ = nets.discriminator(store, cfg, x, y, True)
+    assert float(d.min()) >= 0.0 and float(d.max()) <= 1.0
+  ng = sum(v.numel() for k, v in store.trainable.items() if k.startswith("generator/"))
+  nd = sum(v.numel() for k, v in store.trainable.items() if k.startswith("discriminator/"))
+  assert ng == G["biggan128_params"]["generator"]
+  assert nd == G["biggan128_params"]["discriminator"]
+  # resnet_biggan_test.py: CBN input width 148, embed_y [1000,128], 1x1 shortcuts, no shortcut in D B6
+  assert list(store.vars["generator/B1/bn1/condition/gamma/kernel"].shape) == [148, 1536]
+  assert list(store.vars["generator/embed_y/kernel"].shape) == [1000, 128]
+  assert list(store.vars["generator/B1/up_conv_shortcut/kernel"].shape) == [1, 1, 1536, 1536]
+  assert not any(k.startswith("discriminator/B6/") and "shortcut" in k for k in store.vars)
+
+
+def test_step_counters_and_cycle_runs():
+  # gans/modular_gan_test.py:142-177: global_step_disc == global_step * disc_iters
+  cfg = nets.Cfg(d_sn=True, bn_decay=0.9, bn_eps=1e-5)
+  k = 2
+  o = gan.GanOracle(cfg, disc_iters=k).build(2)
+  rng = np.random.RandomState(0)
+  for _ in range(2):
+    imgs = [rng.rand(2, 32, 32, 3).astype(np.float32) for _ in range(k + 1)]
+    zs = [rng.uniform(-1, 1, (2, 128)).astype(np.float32) for _ in range(k + 1)]
+    dl, gl = o.cycle(imgs, zs)
+    assert len(dl) == k and np.isfinite(gl)
+  assert o.global_step == 2 and o.global_step_disc == o.global_step * k
+
+
+def test_wgangp_matches_finite_difference():
+  # penalty (gans/penalty_lib.py:59-82) has no golden: check the autograd double-backward
+  # against a central finite difference of the penalty wrt one D weight.
+  torch.manual_seed(0)
+  cfg = nets.Cfg(architecture="resnet5_arch", image_shape=(16, 16, 3), g_bn=None)
+  store = nets.VarStore(1)
+  x = torch.rand(2, 16, 16, 3).double()
+  xf = torch.rand(2, 16, 16, 3).double()
+  alpha = torch.rand(2, 1, 1, 1).double()
+  with torch.no_grad():
+    nets.discriminator(store, cfg, x.float(), None, True)
+  for k in list(store.vars):   # run this check in float64
+    v = store.vars[k].detach().double() * 5.0
+    v.requires_grad_(k in store.trainable)
+    store.vars[k] = v
+    if k in store.trainable:
+      store.trainable[k] = v
+  w = store.vars["discriminator/B1/same_conv1/kernel"]
+  p = gan.wgangp_penalty(store, cfg, x, xf, None, True, alpha)
+  gw = torch.autograd.grad(p, w)[0]
+  idx = (1, 1, 3, 5)
+  eps = 1e-5
+  with torch.no_grad():
+    w[idx] += eps
+  pp = float(gan.wgangp_penalty(store, cfg, x, xf, None, True, alpha))
+  with torch.no_grad():
+    w[idx] -= 2 * eps
+  pm = float(gan.wgangp_penalty(store, cfg, x, xf, None, True, alpha))
+  fd = (pp - pm) / (2 * eps)
+  assert abs(fd - float(gw[idx])) <= 1e-5 * max(1.0, abs(fd)), (fd, float(gw[idx]))
+
+
+def test_conv_transpose_is_adjoint_of_conv():
+  # deconv2d semantics (arch_ops.py:588-589): <conv(x,w), y> == <x, conv_transpose(y,w)>
+  rng = np.random.RandomState(0)
+  for k, s, n in [(4, 2, 8), (3, 1, 6), (5, 2, 8), (5, 2, 7)]:
+    x = torch.from_numpy(rng.randn(2, n, n, 3)).double()
+    w = torch.from_numpy(rng.randn(k, k, 3, 5)).double()     # conv: 3 -> 5
+    y = torch.from_numpy(rng.randn(2, -(-n // s), -(-n // s), 5)).double()
+    lhs = (T.conv2d_same(x, w, s) * y).sum()
+    rhs = (x * T.conv2d_transpose_same(y, w, (n, n), s)).sum()
+    assert abs(float(lhs - rhs)) < 1e-9 * max(1.0, abs(float(lhs)))
