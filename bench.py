@@ -1,0 +1,305 @@
+"""bench.py — images/sec of the G+D training cycle (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload resnet_cifar10]
+
+A "step" is one ModularGAN cycle of `resnet_cifar10.gin` at batch 256 per GPU: disc_iters=5 D-updates +
+1 G-update on fresh synthetic images/z (unrolled semantics, reference gans/modular_gan.py:218-223), i.e.
+256*6 images consumed per GPU per step.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: arch, image_shape, per-GPU batch, disc_iters, extra
+    "resnet_cifar10": dict(arch="resnet_cifar_arch", image=(32, 32, 3), batch=256, k=5, loss="non_saturating",
+                           penalty="no_penalty", lamba=1.0, d_sn=True, g_sn=False, g_lr=2e-4, beta1=0.5, beta2=0.999,
+                           gflop_per_slot_image=39.05),   # BASELINE.md §3 (useful FLOPs per batch-slot image per cycle)
+}
+
+
+def peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+            "source": "measured"}
+  return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                    "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      pass
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1]))
+      except Exception:
+        continue
+      for nm, v in zip(names, r[3:7]):
+        if v.lower().startswith("active"):
+          reasons.add(nm)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_engine(wl, seed=0):
+  from compare_gan_b200 import datasets, gin_lite as gin
+  from compare_gan_b200.gans import modular_gan
+  gin.clear_config()
+  gin.parse_config("\n".join([
+      "G.batch_norm_fn = @batch_norm", "G.spectral_norm = %s" % wl["g_sn"], "D.spectral_norm = %s" % wl["d_sn"],
+      "standardize_batch.decay = 0.9", "standardize_batch.epsilon = 1e-5",
+      "loss.fn = @%s" % wl["loss"], "penalty.fn = @%s" % wl["penalty"],
+      "ModularGAN.g_lr = %r" % wl["g_lr"], "ModularGAN.g_optimizer_fn = @tf.train.AdamOptimizer",
+      "tf.train.AdamOptimizer.beta1 = %r" % wl["beta1"], "tf.train.AdamOptimizer.beta2 = %r" % wl["beta2"]]))
+  ds = datasets.ImageDatasetV2("synthetic", wl["image"][0], wl["image"][2], None, 10000)
+  params = {"architecture": wl["arch"], "z_dim": 128, "lambda": wl["lamba"], "disc_iters": wl["k"], "seed": seed}
+  eng = modular_gan.ModularGAN(dataset=ds, parameters=params, model_dir="/tmp/cgan_bench")
+  eng.build(wl["batch"])
+  return eng, ds
+
+
+def time_dominant_kernel(wl, iters=20):
+  """Roofline evidence for the dominant kernel: the 3x3 256->256 conv of G's B3 block at 32x32, batch = bench batch
+  (1208 MF/img), timed alone with CUDA events on the launching stream; its 268 MB input and
+  268 MB output exceed the 126 MB L2, so every launch streams from HBM."""
+  import torch
+  from compare_gan_b200 import kernels as K
+  b = wl["batch"]
+  x = K.from_numpy(np.random.RandomState(0).randn(b, 32, 32, 256).astype(np.float32))
+  w = K.from_numpy((np.random.RandomState(1).randn(3, 3, 256, 256) * 0.02).astype(np.float32))
+  bias = K.zeros(256)
+  for _ in range(3):
+    K.conv2d(x, w, bias)
+  torch.cuda.synchronize()
+  st = torch.cuda.current_stream()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(st)
+  for _ in range(iters):
+    K.conv2d(x, w, bias)
+  e1.record(st)
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / iters
+  flops = 2.0 * b * 32 * 32 * 256 * 256 * 9
+  return {"kernel": "gather_gemm_kernel<FWD> conv3x3 256->256 @32x32 B=%d" % b, "ms": ms, "tflops": flops / ms / 1e9,
+          "flops_per_launch": flops}
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  from compare_gan_b200 import kernels as K
+  from compare_gan_b200 import runner_lib
+  K.init(local)
+  wl = WORKLOADS[args.workload]
+  eng, ds = build_engine(wl, seed=0)
+  k, b = wl["k"], wl["batch"]
+  rng = np.random.RandomState(1000 + rank)
+
+  # pinned host staging buffers for the e2e arm
+  def pinned_cycle():
+    imgs, zs, _, _, alphas = runner_lib.sample_cycle_inputs(eng, ds, b, rng)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    return [pin(a) for a in imgs], [pin(a) for a in zs], None, None, [pin(a) for a in alphas]
+  host = [pinned_cycle() for _ in range(2)]
+  h2d_bytes = sum(t.numel() * 4 for part in (host[0][0], host[0][1], host[0][4]) for t in part)
+
+  n0 = K.lib().launch_count()
+  eng.set_inputs(*host[0])
+  eng.run_cycle()
+  torch.cuda.synchronize()
+  launches_per_cycle = K.lib().launch_count() - n0
+  graph = True
+  try:
+    eng.capture(warmup=2)
+  except Exception as e:      # e.g. NCCL not capturable in this build: run the cycle eagerly
+    graph = False
+    sys.stderr.write("[bench] CUDA-graph capture unavailable (%s); running eagerly\n" % str(e)[:200])
+    eng._graph = None
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(steps, e2e):
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for i in range(steps):
+      if e2e:
+        eng.set_inputs(*host[i % 2])          # H2D from pinned memory inside the timed region
+      eng.run_cycle()
+      if e2e:
+        eng.read_losses()                     # D2H read of the step's result
+    e1.record(st)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device="cuda")
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms
+
+  eng.set_inputs(*host[0])
+  timed(max(args.warmup, 3), False)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  ms_dev = timed(args.steps, False)
+  ms_e2e = timed(args.steps, True)
+  clocks = sampler.stop() if rank == 0 else None
+  d_losses, g_loss = eng.read_losses()
+  images_per_step = b * (k + 1) * world
+  value = images_per_step * args.steps / (ms_dev / 1e3)
+  e2e_value = images_per_step * args.steps / (ms_e2e / 1e3)
+
+  out = None
+  if rank == 0:
+    pk = peaks()
+    dom = time_dominant_kernel(wl)
+    cyc_tflop = wl["gflop_per_slot_image"] * b / 1e3          # useful TFLOP per cycle per GPU
+    cpu = cpu_baseline_leg(args, sample_cycles=2)
+    out = {
+        "metric": "images/sec G+D step (resnet_cifar10)", "value": value, "unit": "images/sec", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "resnet_cifar10.gin: resnet_cifar_arch 32x32x3, batch %d per GPU, disc_iters %d, "
+                               "non_saturating, spectral_norm on D, BN in G, Adam(2e-4,0.5,0.999); "
+                               "step = 5 D-updates + 1 G-update on %d images" % (b, k, b * (k + 1)),
+                   "global_batch": b * world, "parallelism": "dp%d" % world, "cuda_graph": graph,
+                   "l2": "activations per cycle (GBs) exceed the 126 MB L2: inputs larger than L2",
+                   "math_mode": "fp32 SIMT contraction (math_mode 0)"},
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4 * (k + 1), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_cycle * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": dom["tflops"] / pk["bf16_tflops"], "traffic": None,
+                     "kernel": dom["kernel"], "kernel_ms": dom["ms"],
+                     "peak_kind": "%s dense bf16 cuBLAS burst (MEASURED_PEAKS.json); this kernel computes in fp32 on "
+                                  "CUDA cores, so the fraction is of the tensor-core roofline it is meant to reach" % pk["source"],
+                     "step_useful_tflops_per_gpu": cyc_tflop / (ms_dev / args.steps / 1e3),
+                     "step_frac": cyc_tflop / (ms_dev / args.steps / 1e3) / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])},
+        "cpu_baseline": cpu,
+        "losses": {"d": d_losses, "g": g_loss},
+    }
+    print(json.dumps(out))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return out
+
+
+def cpu_baseline_leg(args, sample_cycles=2, batch=64):
+  """The CPU restatement of the reference (TF cannot run here) on config C1: resnet_cifar, B=64, full cycle."""
+  import torch
+  from oracle import gan as ogan, nets as onets
+  wl = WORKLOADS[args.workload]
+  cfg = onets.Cfg(architecture=wl["arch"], image_shape=wl["image"], g_bn="batch_norm", d_sn=wl["d_sn"], g_sn=wl["g_sn"],
+                  bn_decay=0.9, bn_eps=1e-5)
+  o = ogan.GanOracle(cfg, loss=wl["loss"], penalty=wl["penalty"], lamba=wl["lamba"], disc_iters=wl["k"],
+                     g_lr=wl["g_lr"], beta1=wl["beta1"], beta2=wl["beta2"]).build(2)
+  rng = np.random.RandomState(547)
+  k = wl["k"]
+
+  def one():
+    imgs = [rng.rand(batch, *wl["image"]).astype(np.float32) for _ in range(k + 1)]
+    zs = [rng.uniform(-1, 1, (batch, 128)).astype(np.float32) for _ in range(k + 1)]
+    o.cycle(imgs, zs)
+  one()   # warm-up
+  t0 = time.time()
+  for _ in range(sample_cycles):
+    one()
+  dt = (time.time() - t0) / sample_cycles
+  return {"value": batch * (k + 1) / dt, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+          "sample": "%d full cycles (5 D + 1 G) of resnet_cifar10 at batch %d per sub-step on the host cores, "
+                    "PyTorch-CPU fp32 oracle (CPU restatement of the reference; TF unavailable)" % (sample_cycles, batch),
+          "seconds_per_cycle": dt, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU path (its restatement; TF cannot be installed here) on host cores."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import torch
+  wl = WORKLOADS[args.workload]
+  k = wl["k"]
+  batch = 64
+  steps = max(1, min(args.steps, 3))
+  t0 = time.time()
+  cpu = cpu_baseline_leg(args, sample_cycles=steps, batch=batch)
+  out = {"impl": "reference", "metric": "images/sec G+D step (resnet_cifar10)", "value": cpu["value"],
+         "unit": "images/sec", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 1,
+         "ms_per_step": cpu["seconds_per_cycle"] * 1e3, "higher_is_better": True, "scaling": "weak",
+         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+         "config": {"workload": "resnet_cifar10.gin cycle (5 D-updates + 1 G-update); each step is a bounded sample: "
+                                "batch %d per sub-step instead of 256" % batch, "parallelism": "cpu"},
+         "cpu_baseline": cpu,
+         "e2e": {"value": cpu["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+         "wall_s": time.time() - t0}
+  print(json.dumps(out))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours")
+  ap.add_argument("--workload", default="resnet_cifar10")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,94 @@
+// Shared helpers for the sm_100a kernels behind include/cgan_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cgan_b200.h"
+
+struct cgan_ctx {
+  int device;
+  cudaStream_t stream;
+  void* ws;
+  size_t ws_bytes;
+  int math_mode;
+  int64_t launches;
+  int num_sms;
+  char err[512];
+};
+
+static inline int cgan_fail(cgan_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "") {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+  return code;
+}
+
+#define CGAN_REQUIRE(ctx, cond, msg)                                              \
+  do {                                                                            \
+    if (!(cond)) return cgan_fail((ctx), CGAN_ERR_ARG, "%s: %s", __func__, msg);  \
+  } while (0)
+
+#define CGAN_CUDA(ctx, call)                                                                        \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) return cgan_fail((ctx), CGAN_ERR_CUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
+  } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors without synchronising
+#define CGAN_LAUNCHED(ctx)                                                                          \
+  do {                                                                                              \
+    (ctx)->launches++;                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                                           \
+    if (e__ != cudaSuccess) return cgan_fail((ctx), CGAN_ERR_CUDA, "%s: launch: %s", __func__, cudaGetErrorString(e__)); \
+  } while (0)
+
+// Workspace owned by the context; grows on demand outside stream capture only.
+static inline int cgan_ws(cgan_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->ws_bytes) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &st);
+    if (st != cudaStreamCaptureStatusNone)
+      return cgan_fail(ctx, CGAN_ERR_WORKSPACE, "%s: workspace would grow during stream capture (warm up first)%s", "cgan_ws");
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    want = (want + 255) / 256 * 256;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->ws) e = cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: %s", "cgan_ws", cudaGetErrorString(e));
+    ctx->ws_bytes = want;
+  }
+  *out = ctx->ws;
+  return CGAN_OK;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in all threads. `sh` must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) sh[0] = r;
+  }
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+// internal (C++ linkage) entry points shared between translation units
+int cgan_conv2d_fwd_simt(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const float* bias, float* y);
+int cgan_conv2d_dgrad_simt(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, float* dx);

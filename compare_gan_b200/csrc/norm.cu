@@ -1,0 +1,405 @@
+// Batch-norm family (moments / apply / backward, conditional and cross-replica aware) and the
+// spectral-norm power iteration.  All HBM-bound rows x channels work over NHWC activations:
+// channels are the fastest dimension, so a warp reads 128 contiguous bytes of one row and the
+// per-channel sums are reduced over row lanes in shared memory, then over chunks in a second,
+// fixed-order (deterministic) pass.
+//
+// Replaces: standardize_batch (arch_ops.py:194-319), batch_norm (:327-367), conditional_batch_norm
+// (:423-445), cross_replica_moments (tpu/tpu_ops.py:94-125), spectral_norm (arch_ops.py:453-535).
+#include "common.cuh"
+
+namespace {
+
+constexpr int CR_X = 32, CR_Y = 8;   // column-reduce block: 32 channels x 8 row lanes
+
+struct MomentsF {
+  const float* x;
+  __device__ __forceinline__ void operator()(long long r, int c, int C, long long, float* v) const {
+    float t = x[r * C + c];
+    v[0] = t;
+    v[1] = t * t;
+  }
+};
+struct SumF {
+  const float* x;
+  __device__ __forceinline__ void operator()(long long r, int c, int C, long long, float* v) const {
+    v[0] = x[r * C + c];
+  }
+};
+struct WeightedSumF {   // sum_r a[r] * w[r,c]  (W^T a)
+  const float* w;
+  const float* a;
+  __device__ __forceinline__ void operator()(long long r, int c, int C, long long, float* v) const {
+    v[0] = w[r * C + c] * a[r];
+  }
+};
+struct BnBwdF {         // v0 = sum dy*xhat, v1 = sum dy
+  const float* dy;
+  const float* x;
+  const float* mean_var;
+  float eps;
+  __device__ __forceinline__ void operator()(long long r, int c, int C, long long, float* v) const {
+    float inv = 1.0f / sqrtf(mean_var[C + c] + eps);
+    float xh = (x[r * C + c] - mean_var[c]) * inv;
+    float g = dy[r * C + c];
+    v[0] = g * xh;
+    v[1] = g;
+  }
+};
+
+// partial[((g*chunks + chunk)*NV + v)*C + c]
+template <class F, int NV>
+__global__ void colreduce_kernel(F f, float* __restrict__ partial, long long rows_per_group, int C,
+                                 long long rows_per_chunk, int chunks) {
+  __shared__ float sh[NV][CR_Y][CR_X + 1];
+  const int c = blockIdx.x * CR_X + threadIdx.x;
+  const int chunk = blockIdx.y, g = blockIdx.z;
+  float acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+  if (c < C) {
+    long long r0 = (long long)chunk * rows_per_chunk;
+    long long r1 = min(rows_per_group, r0 + rows_per_chunk);
+    long long base = (long long)g * rows_per_group;
+    for (long long r = r0 + threadIdx.y; r < r1; r += CR_Y) {
+      float v[NV];
+      f(base + r, c, C, r, v);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sh[v][threadIdx.y][threadIdx.x] = acc[v];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < CR_Y; ++y) s += sh[v][y][threadIdx.x];
+      partial[(((long long)g * chunks + chunk) * NV + v) * C + c] = s;
+    }
+  }
+}
+
+// out_v[g*C + c] = scale * sum_chunk partial
+template <int NV>
+__global__ void colreduce_final_kernel(const float* __restrict__ partial, int groups, int chunks, int C, float scale,
+                                       float* out0, float* out1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)groups * C) return;
+  int g = (int)(i / C), c = (int)(i % C);
+  float* outs[2] = {out0, out1};
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (!outs[v]) continue;
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partial[(((long long)g * chunks + k) * NV + v) * C + c];
+    outs[v][i] = s * scale;
+  }
+}
+
+template <class F, int NV>
+int colreduce(cgan_ctx* ctx, F f, int groups, long long rows_per_group, int C, float scale, float* out0, float* out1) {
+  int cblocks = cdiv(C, CR_X);
+  long long want = (4ll * ctx->num_sms + (long long)cblocks * groups - 1) / ((long long)cblocks * groups);
+  long long maxchunks = (rows_per_group + 4 * CR_Y - 1) / (4 * CR_Y);
+  long long chunks = want < 1 ? 1 : want;
+  if (chunks > maxchunks) chunks = maxchunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  long long rpc = (rows_per_group + chunks - 1) / chunks;
+  rpc = (rpc + CR_Y - 1) / CR_Y * CR_Y;
+  chunks = (rows_per_group + rpc - 1) / rpc;
+  if (chunks < 1) chunks = 1;
+  if (groups > 65535) return cgan_fail(ctx, CGAN_ERR_ARG, "%s: too many groups%s", "colreduce");
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, (size_t)groups * chunks * NV * C * sizeof(float), &ws);
+  if (rc) return rc;
+  float* partial = reinterpret_cast<float*>(ws);
+  dim3 grid(cblocks, (unsigned)chunks, groups), block(CR_X, CR_Y);
+  colreduce_kernel<F, NV><<<grid, block, 0, ctx->stream>>>(f, partial, rows_per_group, C, rpc, (int)chunks);
+  CGAN_LAUNCHED(ctx);
+  long long tot = (long long)groups * C;
+  colreduce_final_kernel<NV><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(partial, groups, (int)chunks, C, scale, out0, out1);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+__global__ void bn_finalize_kernel(float* mean_var, const float* stats, int C, float* mm, float* mv, float decay) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean = stats[c], msq = stats[C + c];
+  float var = msq - mean * mean;
+  mean_var[c] = mean;
+  mean_var[C + c] = var;
+  if (mm) mm[c] -= (mm[c] - mean) * (1.0f - decay);
+  if (mv) mv[c] -= (mv[c] - var) * (1.0f - decay);
+}
+
+__global__ void bn_accumulate_kernel(float* mean_var, const float* batch, int C, float* am, float* av, float* ac,
+                                     const float* upd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool update = (*upd == 1.0f);
+  float counter = *ac + (update ? 1.0f : 0.0f);
+  if (c < C) {
+    float m = am[c], v = av[c];
+    if (update) {
+      m += batch[c];
+      v += batch[C + c];
+      am[c] = m;
+      av[c] = v;
+    }
+    mean_var[c] = m / counter;
+    mean_var[C + c] = v / counter;
+  }
+  __syncthreads();
+  // every thread has read *ac above; a single thread publishes the new counter (one block only)
+  if (update && blockIdx.x == 0 && threadIdx.x == 0) *ac = counter;
+}
+
+__global__ void bn_apply_kernel(float* __restrict__ y, const float* __restrict__ x, long long total, int C,
+                                long long rows_per_sample, const float* __restrict__ mean_var, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int cond, int act) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    long long pidx = cond ? (r / rows_per_sample) * C + c : c;
+    float inv = 1.0f / sqrtf(mean_var[C + c] + eps);
+    float v = (x[i] - mean_var[c]) * inv;
+    if (gamma) v *= gamma[pidx];
+    if (beta) v += beta[pidx];
+    if (act == 1) v = fmaxf(v, 0.f);
+    y[i] = v;
+  }
+}
+
+// sums[c] = sum_g gamma(g,c)*B(g,c); sums[C+c] = sum_g gamma(g,c)*A(g,c);  A = sum dy*xhat, B = sum dy (per group)
+__global__ void bn_bwd_sums_kernel(float* sums, const float* A, const float* Bv, const float* gamma, int groups, int C,
+                                   int cond) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    float gm = gamma ? (cond ? gamma[(long long)g * C + c] : gamma[c]) : 1.0f;
+    s1 += gm * Bv[(long long)g * C + c];
+    s2 += gm * A[(long long)g * C + c];
+  }
+  sums[c] = s1;
+  sums[C + c] = s2;
+}
+
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ x,
+                                    long long total, int C, long long rows_per_sample,
+                                    const float* __restrict__ mean_var, float eps, const float* __restrict__ gamma,
+                                    int cond, const float* __restrict__ sums, float inv_count) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    float inv = 1.0f / sqrtf(mean_var[C + c] + eps);
+    float xh = (x[i] - mean_var[c]) * inv;
+    float g = gamma ? gamma[cond ? (r / rows_per_sample) * C + c : c] : 1.0f;
+    float dxh = dy[i] * g;
+    dx[i] = inv * (dxh - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+  }
+}
+
+// one warp per row: out[r] = sum_c w[r,c]*b[c]
+__global__ void gemv_rows_kernel(float* __restrict__ out, const float* __restrict__ w, const float* __restrict__ b,
+                                 int rows, int cols) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* row = w + (long long)warp * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += row[c] * b[c];
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = s;
+}
+
+// out = t * rsqrt(max(sum t^2, eps)); optionally sigma = dot(out, t).  Single block.
+__global__ void l2_normalize_kernel(float* out, const float* t, int n, float eps, float* sigma) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += t[i] * t[i];
+  s = block_sum(s, sh);
+  float scale = 1.0f / sqrtf(fmaxf(s, eps));
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float o = t[i] * scale;
+    out[i] = o;
+    d += o * t[i];
+  }
+  if (sigma) {
+    d = block_sum(d, sh);
+    if (threadIdx.x == 0) *sigma = d;
+  }
+}
+
+__global__ void sn_bwd_kernel(float* __restrict__ dw, const float* __restrict__ dwbar, int rows, int cols, int left,
+                              const float* __restrict__ u, const float* __restrict__ v, const float* sigma,
+                              const float* dotp) {
+  long long total = (long long)rows * cols;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  float inv_s = 1.0f / *sigma, dp = *dotp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int r = (int)(i / cols), c = (int)(i % cols);
+    float outer = left ? u[r] * v[c] : v[r] * u[c];
+    dw[i] = (dwbar[i] - dp * outer) * inv_s;
+  }
+}
+
+inline int ew_grid(cgan_ctx* ctx, long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)ctx->num_sms * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int cgan_colsum(cgan_ctx* ctx, float* out, const float* x, int groups, int64_t rows_per_group, int c) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, out && x && groups > 0 && rows_per_group > 0 && c > 0, "bad argument");
+  return colreduce<SumF, 1>(ctx, SumF{x}, groups, rows_per_group, c, 1.0f, out, nullptr);
+}
+
+int cgan_bn_moments(cgan_ctx* ctx, float* stats2c, const float* x, int64_t rows, int c) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, stats2c && x && rows > 0 && c > 0, "bad argument");
+  return colreduce<MomentsF, 2>(ctx, MomentsF{x}, 1, rows, c, 1.0f / (float)rows, stats2c, stats2c + c);
+}
+
+int cgan_bn_finalize(cgan_ctx* ctx, float* mean_var2c, const float* stats2c, int c, float* moving_mean,
+                     float* moving_var, float decay) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, mean_var2c && stats2c && c > 0, "bad argument");
+  bn_finalize_kernel<<<cdiv(c, 256), 256, 0, ctx->stream>>>(mean_var2c, stats2c, c, moving_mean, moving_var, decay);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_bn_accumulate(cgan_ctx* ctx, float* mean_var2c, const float* batch, int c, float* accu_mean, float* accu_var,
+                       float* accu_counter, const float* update_accus_dev) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, mean_var2c && batch && accu_mean && accu_var && accu_counter && update_accus_dev, "null pointer");
+  CGAN_REQUIRE(ctx, c > 0 && c <= 1024, "channels must be in (0,1024] (single block)");
+  bn_accumulate_kernel<<<1, 1024, 0, ctx->stream>>>(mean_var2c, batch, c, accu_mean, accu_var, accu_counter,
+                                                     update_accus_dev);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_bn_apply(cgan_ctx* ctx, float* y, const float* x, int64_t rows, int c, int64_t rows_per_sample,
+                  const float* mean_var2c, float eps, const float* gamma, const float* beta, int cond, int act) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, y && x && mean_var2c && rows > 0 && c > 0, "bad argument");
+  CGAN_REQUIRE(ctx, !cond || (rows_per_sample > 0 && rows % rows_per_sample == 0), "rows_per_sample must divide rows");
+  long long total = (long long)rows * c;
+  bn_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(y, x, total, c, rows_per_sample > 0 ? rows_per_sample : 1,
+                                                                mean_var2c, eps, gamma, beta, cond, act);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_bn_bwd_reduce(cgan_ctx* ctx, float* sums2c, float* dgamma, float* dbeta, const float* dy, const float* x,
+                       int64_t rows, int c, int64_t rows_per_sample, const float* mean_var2c, float eps,
+                       const float* gamma, int cond) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, sums2c && dy && x && mean_var2c && rows > 0 && c > 0, "bad argument");
+  CGAN_REQUIRE(ctx, !cond || (rows_per_sample > 0 && rows % rows_per_sample == 0), "rows_per_sample must divide rows");
+  int groups = cond ? (int)(rows / rows_per_sample) : 1;
+  long long rpg = cond ? rows_per_sample : rows;
+  // per-group A = sum dy*xhat, B = sum dy; kept in caller-visible dgamma/dbeta or in workspace tail
+  float *A = dgamma, *Bv = dbeta;
+  void* ws = nullptr;
+  if (!A || !Bv) {
+    // scratch behind the colreduce partials: reserve generously first so the pointer stays valid
+    size_t need = (size_t)groups * c * 2 * sizeof(float);
+    int rc = cgan_ws(ctx, need + (size_t)64 * 1024 * 1024, &ws);
+    if (rc) return rc;
+    float* tail = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ctx->ws_bytes - need);
+    if (!A) A = tail;
+    if (!Bv) Bv = tail + (size_t)groups * c;
+  }
+  int rc = colreduce<BnBwdF, 2>(ctx, BnBwdF{dy, x, mean_var2c, eps}, groups, rpg, c, 1.0f, A, Bv);
+  if (rc) return rc;
+  bn_bwd_sums_kernel<<<cdiv(c, 256), 256, 0, ctx->stream>>>(sums2c, A, Bv, gamma, groups, c, cond);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_bn_bwd_apply(cgan_ctx* ctx, float* dx, const float* dy, const float* x, int64_t rows, int c,
+                      int64_t rows_per_sample, const float* mean_var2c, float eps, const float* gamma, int cond,
+                      const float* sums2c, float inv_count) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, dx && dy && x && mean_var2c && sums2c && rows > 0 && c > 0, "bad argument");
+  long long total = (long long)rows * c;
+  bn_bwd_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(
+      dx, dy, x, total, c, rows_per_sample > 0 ? rows_per_sample : 1, mean_var2c, eps, gamma, cond, sums2c, inv_count);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+// internal: out[c] = sum_r w[r,c]*a[r]
+static int gemv_cols(cgan_ctx* ctx, float* out, const float* w, const float* a, int rows, int cols) {
+  return colreduce<WeightedSumF, 1>(ctx, WeightedSumF{w, a}, 1, rows, cols, 1.0f, out, nullptr);
+}
+static int gemv_rows(cgan_ctx* ctx, float* out, const float* w, const float* b, int rows, int cols) {
+  gemv_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, ctx->stream>>>(out, w, b, rows, cols);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_scale_by_dev(cgan_ctx*, float*, const float*, const float*, float, int, int64_t);
+
+int cgan_spectral_norm(cgan_ctx* ctx, const float* w, int rows, int cols, int left, float eps, float* u, float* v,
+                       float* sigma, float* wbar) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, w && u && v && sigma && rows > 0 && cols > 0, "bad argument");
+  // scratch vector t (max(rows, cols)) lives in the workspace tail, clear of the colreduce partials
+  size_t tbytes = (size_t)(rows > cols ? rows : cols) * sizeof(float);
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, tbytes + (size_t)64 * 1024 * 1024, &ws);
+  if (rc) return rc;
+  float* t = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ctx->ws_bytes - ((tbytes + 255) / 256) * 256);
+  if (left) {
+    // v = normalize(W^T u); u' = normalize(W v); sigma = u'^T W v       (arch_ops.py:505-509, 525)
+    rc = gemv_cols(ctx, t, w, u, rows, cols);
+    if (rc) return rc;
+    l2_normalize_kernel<<<1, 1024, 0, ctx->stream>>>(v, t, cols, eps, nullptr);
+    CGAN_LAUNCHED(ctx);
+    rc = gemv_rows(ctx, t, w, v, rows, cols);
+    if (rc) return rc;
+    l2_normalize_kernel<<<1, 1024, 0, ctx->stream>>>(u, t, rows, eps, sigma);
+    CGAN_LAUNCHED(ctx);
+  } else {
+    // v = normalize(u W^T); u' = normalize(v W); sigma = v W u'^T       (arch_ops.py:511-513, 527)
+    rc = gemv_rows(ctx, t, w, u, rows, cols);
+    if (rc) return rc;
+    l2_normalize_kernel<<<1, 1024, 0, ctx->stream>>>(v, t, rows, eps, nullptr);
+    CGAN_LAUNCHED(ctx);
+    rc = gemv_cols(ctx, t, w, v, rows, cols);
+    if (rc) return rc;
+    l2_normalize_kernel<<<1, 1024, 0, ctx->stream>>>(u, t, cols, eps, sigma);
+    CGAN_LAUNCHED(ctx);
+  }
+  if (wbar) return cgan_scale_by_dev(ctx, wbar, w, sigma, 1.0f, 1, (int64_t)rows * cols);
+  return CGAN_OK;
+}
+
+int cgan_spectral_norm_bwd(cgan_ctx* ctx, float* dw, const float* dwbar, const float* wbar, int rows, int cols,
+                           int left, const float* u, const float* v, const float* sigma) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, dw && dwbar && wbar && u && v && sigma && rows > 0 && cols > 0, "bad argument");
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, (size_t)64 * 1024 * 1024, &ws);
+  if (rc) return rc;
+  float* dotp = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ctx->ws_bytes - 256);
+  rc = cgan_dot(ctx, dotp, dwbar, wbar, (int64_t)rows * cols);
+  if (rc) return rc;
+  long long total = (long long)rows * cols;
+  sn_bwd_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dw, dwbar, rows, cols, left, u, v, sigma, dotp);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}

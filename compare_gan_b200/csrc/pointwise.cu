@@ -1,0 +1,537 @@
+// Context management plus the HBM-bound pointwise / pooling / loss / optimizer kernels.
+// All are grid-stride loops over NHWC float32 with the channel index fastest (coalesced), sized to
+// a multiple of the SM count.
+//
+// Replaces: tf.nn.relu / lrelu (arch_ops.py:595-597) / sigmoid / tanh, tf.nn.pool AVG
+// (resnet_ops.py:131-133), max_pooling2d (arch_ops.py:741,750), reduce_mean/sum over [1,2]
+// (resnet_cifar.py:156, resnet_biggan.py:405), tf.nn.softmax (arch_ops.py:745), the losses
+// (gans/loss_lib.py:53-148), the WGAN-GP slope penalty (gans/penalty_lib.py:78-81) and
+// tf.train.AdamOptimizer + ExponentialMovingAverage (gans/modular_gan.py:498-508).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------- context
+int cgan_version(void) { return 1; }
+
+int cgan_ctx_create(cgan_ctx** out, int device) {
+  if (!out) return CGAN_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return CGAN_ERR_CUDA;
+  cgan_ctx* c = new cgan_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return CGAN_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CGAN_ERR_CUDA; }
+  c->num_sms = prop.multiProcessorCount;
+  c->stream = 0;
+  *out = c;
+  return CGAN_OK;
+}
+
+int cgan_ctx_destroy(cgan_ctx* ctx) {
+  if (!ctx) return CGAN_ERR_ARG;
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return CGAN_OK;
+}
+
+int cgan_ctx_set_stream(cgan_ctx* ctx, void* s) {
+  if (!ctx) return CGAN_ERR_ARG;
+  ctx->stream = reinterpret_cast<cudaStream_t>(s);
+  return CGAN_OK;
+}
+
+int cgan_ctx_reserve_workspace(cgan_ctx* ctx, size_t bytes) {
+  if (!ctx) return CGAN_ERR_ARG;
+  void* p;
+  return cgan_ws(ctx, bytes, &p);
+}
+
+int cgan_ctx_set_math_mode(cgan_ctx* ctx, int mode) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (fp32 SIMT) or 1 (tcgen05 tf32)");
+  ctx->math_mode = mode;
+  return CGAN_OK;
+}
+
+const char* cgan_last_error(cgan_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+int64_t cgan_launch_count(cgan_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+namespace {
+
+inline int ew_grid(cgan_ctx* ctx, long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)ctx->num_sms * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define EW_LOOP(i, n)                                                                  \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, s__ = (long long)gridDim.x * blockDim.x; \
+       i < (n); i += s__)
+
+__global__ void fill_kernel(float* d, float v, long long n) { EW_LOOP(i, n) d[i] = v; }
+__global__ void copy_kernel(float* __restrict__ d, const float* __restrict__ s, long long n) { EW_LOOP(i, n) d[i] = s[i]; }
+__global__ void copy2d_kernel(float* __restrict__ d, int dld, int doff, const float* __restrict__ s, int sld, int soff,
+                              long long rows, int cols) {
+  long long n = rows * cols;
+  EW_LOOP(i, n) {
+    long long r = i / cols;
+    int j = (int)(i % cols);
+    d[r * dld + doff + j] = s[r * sld + soff + j];
+  }
+}
+__global__ void axpby_kernel(float* __restrict__ y, float a, const float* __restrict__ x, float b,
+                             const float* __restrict__ y0, float c, long long n) {
+  EW_LOOP(i, n) {
+    float v = a * x[i] + c;
+    if (y0) v += b * y0[i];
+    y[i] = v;
+  }
+}
+__global__ void scale_by_dev_kernel(float* __restrict__ y, const float* __restrict__ x, const float* s, float mul, int inv,
+                                    long long n) {
+  float f = inv ? mul / *s : mul * *s;
+  // division by sigma is done per element to match "w / norm_value" (arch_ops.py:531) bit for bit
+  if (inv && mul == 1.0f) {
+    float sv = *s;
+    EW_LOOP(i, n) y[i] = x[i] / sv;
+  } else {
+    EW_LOOP(i, n) y[i] = x[i] * f;
+  }
+}
+__global__ void dot_partial_kernel(float* part, const float* __restrict__ a, const float* __restrict__ b, long long n) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  EW_LOOP(i, n) s += a[i] * b[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void sum_final_kernel(float* out, const float* part, int n, float scale) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) *out = s * scale;
+}
+__global__ void interpolate_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ xf,
+                                   const float* __restrict__ alpha, long long per, long long n) {
+  EW_LOOP(i, n) {
+    float a = alpha[i / per];
+    y[i] = x[i] + a * (xf[i] - x[i]);
+  }
+}
+__global__ void one_hot_kernel(float* out, const int32_t* labels, int n, int classes) {
+  long long tot = (long long)n * classes;
+  EW_LOOP(i, tot) {
+    int r = (int)(i / classes), c = (int)(i % classes);
+    out[i] = (labels[r] == c) ? 1.0f : 0.0f;
+  }
+}
+__global__ void bias_add_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ b,
+                                long long n, int c) {
+  EW_LOOP(i, n) y[i] = x[i] + b[i % c];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void act_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int kind, float leak, long long n) {
+  EW_LOOP(i, n) {
+    float v = x[i];
+    if (kind == CGAN_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (kind == CGAN_ACT_LRELU) v = fmaxf(v, leak * v);
+    else if (kind == CGAN_ACT_SIGMOID) v = sigmoidf_(v);
+    else v = (tanhf(v) + 1.0f) * 0.5f;
+    y[i] = v;
+  }
+}
+__global__ void act_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ ref,
+                               int kind, float leak, long long n) {
+  EW_LOOP(i, n) {
+    float g = dy[i], r = ref[i];
+    if (kind == CGAN_ACT_RELU) g = r > 0.f ? g : 0.f;
+    else if (kind == CGAN_ACT_LRELU) g = (r > leak * r) ? g : ((r < leak * r) ? leak * g : 0.5f * (1.0f + leak) * g);
+    else if (kind == CGAN_ACT_SIGMOID) g = g * r * (1.0f - r);
+    else { float t = 2.0f * r - 1.0f; g = g * 0.5f * (1.0f - t * t); }   // y=(tanh+1)/2 -> tanh = 2y-1
+    dx[i] = g;
+  }
+}
+__global__ void add_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, long long n) {
+  EW_LOOP(i, n) y[i] = a[i] + b[i];
+}
+
+__global__ void avgpool2_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int h, int w, int c) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * oh * ow * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    const float* p = x + (((b * h + 2 * oy) * w) + 2 * ox) * c + ch;
+    y[i] = (p[0] + p[c] + p[(long long)w * c] + p[(long long)w * c + c]) * 0.25f;
+  }
+}
+__global__ void avgpool2_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, int n, int h, int w, int c) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * h * w * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int xx = (int)(t % w); t /= w;
+    int yy = (int)(t % h);
+    long long b = t / h;
+    dx[i] = 0.25f * dy[(((b * oh + yy / 2) * ow) + xx / 2) * c + ch];
+  }
+}
+__global__ void maxpool2_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int h, int w, int c) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * oh * ow * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    const float* p = x + (((b * h + 2 * oy) * w) + 2 * ox) * c + ch;
+    y[i] = fmaxf(fmaxf(p[0], p[c]), fmaxf(p[(long long)w * c], p[(long long)w * c + c]));
+  }
+}
+__global__ void maxpool2_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ x,
+                                    int n, int h, int w, int c) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * oh * ow * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    long long base = (((b * h + 2 * oy) * w) + 2 * ox) * c + ch;
+    long long offs[4] = {0, c, (long long)w * c, (long long)w * c + c};
+    int best = 0;
+    float bv = x[base];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      float v = x[base + offs[k]];
+      if (v > bv) { bv = v; best = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[base + offs[k]] = (k == best) ? dy[i] : 0.f;
+  }
+}
+// y[n,c] = scale * sum_hw x[n,hw,c]: one thread per (n,c) strides over hw; consecutive threads -> consecutive c
+__global__ void globalpool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int hw, int c, float scale) {
+  long long tot = (long long)n * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long b = i / c;
+    const float* p = x + b * hw * c + ch;
+    float s = 0.f;
+    for (int k = 0; k < hw; ++k) s += p[(long long)k * c];
+    y[i] = s * scale;
+  }
+}
+__global__ void globalpool_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, int n, int hw, int c, float scale) {
+  long long tot = (long long)n * hw * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long b = i / ((long long)hw * c);
+    dx[i] = scale * dy[b * c + ch];
+  }
+}
+// one block per row
+__global__ void softmax_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int cols) {
+  __shared__ float sh[32];
+  const float* xr = x + (long long)blockIdx.x * cols;
+  float* yr = y + (long long)blockIdx.x * cols;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) m = fmaxf(m, xr[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = sh[0];
+  for (int k = 1; k < (blockDim.x >> 5); ++k) m = fmaxf(m, sh[k]);
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    float e = expf(xr[j] - m);
+    yr[j] = e;
+    s += e;
+  }
+  s = block_sum(s, sh);
+  float inv = 1.0f / s;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) yr[j] *= inv;
+}
+__global__ void softmax_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ y, int cols) {
+  __shared__ float sh[32];
+  long long off = (long long)blockIdx.x * cols;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) s += dy[off + j] * y[off + j];
+  s = block_sum(s, sh);
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) dx[off + j] = y[off + j] * (dy[off + j] - s);
+}
+__global__ void rowdot_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, long long rows, int cols) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float s = 0.f;
+  for (int j = lane; j < cols; j += 32) s += a[warp * cols + j] * b[warp * cols + j];
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = s;
+}
+__global__ void rowscale_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ s, long long n, int cols) {
+  EW_LOOP(i, n) y[i] = a[i] * s[i / cols];
+}
+
+// ---- losses: single block, b <= a few thousand logits
+__device__ __forceinline__ float sce(float x, float z) { return fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x))); }
+
+__global__ void gan_loss_kernel(int kind, const float* __restrict__ lr, const float* __restrict__ lf, int b, float* out4,
+                                float* dl, int which) {
+  __shared__ float sh[32];
+  float sr = 0.f, sf = 0.f, sg = 0.f;
+  float invb = 1.0f / (float)b;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    float r = lr[i], f = lf[i];
+    float dr = 0.f, df = 0.f;   // gradients wrt the real / fake logit of the requested loss
+    if (kind == CGAN_LOSS_NON_SATURATING) {
+      sr += sce(r, 1.f); sf += sce(f, 0.f); sg += sce(f, 1.f);
+      float pr = sigmoidf_(r), pf = sigmoidf_(f);
+      if (which == 0) { dr = (pr - 1.f) * invb; df = pf * invb; } else { df = (pf - 1.f) * invb; }
+    } else if (kind == CGAN_LOSS_HINGE) {
+      sr += fmaxf(1.f - r, 0.f); sf += fmaxf(1.f + f, 0.f); sg += -f;
+      if (which == 0) { dr = (1.f - r > 0.f) ? -invb : 0.f; df = (1.f + f > 0.f) ? invb : 0.f; } else { df = -invb; }
+    } else if (kind == CGAN_LOSS_WASSERSTEIN) {
+      sr += -r; sf += f; sg += -f;
+      if (which == 0) { dr = -invb; df = invb; } else { df = -invb; }
+    } else {  // least squares on probabilities d = sigmoid(logit)
+      float pr = sigmoidf_(r), pf = sigmoidf_(f);
+      sr += (pr - 1.f) * (pr - 1.f); sf += pf * pf; sg += 0.5f * (pf - 1.f) * (pf - 1.f);
+      if (which == 0) { dr = 0.5f * 2.f * (pr - 1.f) * pr * (1.f - pr) * invb; df = 0.5f * 2.f * pf * pf * (1.f - pf) * invb; }
+      else { df = (pf - 1.f) * pf * (1.f - pf) * invb; }
+    }
+    if (dl) { dl[i] = dr; dl[b + i] = df; }
+  }
+  sr = block_sum(sr, sh);
+  sf = block_sum(sf, sh);
+  sg = block_sum(sg, sh);
+  if (threadIdx.x == 0) {
+    float a = sr * invb, c = sf * invb, g = sg * invb;
+    float d = a + c;
+    if (kind == CGAN_LOSS_LEAST_SQUARES) d = 0.5f * (a + c);
+    out4[0] = d; out4[1] = a; out4[2] = c; out4[3] = g;
+  }
+}
+
+// one block per sample: slope_n = sqrt(1e-4 + sum g^2)
+__global__ void gp_slopes_kernel(float* slopes, const float* __restrict__ g, long long per) {
+  __shared__ float sh[32];
+  const float* p = g + (long long)blockIdx.x * per;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) s += p[i] * p[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) slopes[blockIdx.x] = sqrtf(0.0001f + s);
+}
+__global__ void gp_penalty_kernel(float* pen, const float* slopes, int n) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float d = slopes[i] - 1.0f; s += d * d; }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) *pen = s / (float)n;
+}
+__global__ void gp_grad_kernel(float* __restrict__ dg, const float* __restrict__ g, const float* __restrict__ slopes,
+                               long long per, long long tot, float coef) {
+  EW_LOOP(i, tot) {
+    float s = slopes[i / per];
+    dg[i] = coef * (s - 1.0f) / s * g[i];
+  }
+}
+
+__global__ void step_inc_kernel(int32_t* step) { *step += 1; }
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float gscale, const int32_t* step,
+                            float* __restrict__ ema, float ema_decay, int32_t ema_start) {
+  int t = *step;   // already incremented
+  // lr_t in double then rounded once, as the host-side TF kernel does
+  double lr_t_d = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+  float lr_t = (float)lr_t_d;
+  float d = ((t - 1) >= ema_start) ? ema_decay : 0.0f;
+  EW_LOOP(i, n) {
+    float gi = g[i] * gscale;
+    float mi = m[i] * b1 + (1.0f - b1) * gi;
+    float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    if (ema) { float e = ema[i]; ema[i] = e - (e - pi) * (1.0f - d); }
+  }
+}
+
+}  // namespace
+
+#define NONNULL(ctx) do { if (!(ctx)) return CGAN_ERR_ARG; } while (0)
+
+int cgan_fill(cgan_ctx* ctx, float* d, float v, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, n >= 0 && (d || n == 0), "bad argument");
+  if (n == 0) return CGAN_OK;
+  fill_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(d, v, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_copy(cgan_ctx* ctx, float* d, const float* s, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, n >= 0 && ((d && s) || n == 0), "bad argument");
+  if (n == 0) return CGAN_OK;
+  copy_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(d, s, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_copy2d(cgan_ctx* ctx, float* d, int dld, int doff, const float* s, int sld, int soff, int64_t rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, d && s && rows >= 0 && cols >= 0 && doff >= 0 && soff >= 0, "bad argument");
+  CGAN_REQUIRE(ctx, doff + cols <= dld && soff + cols <= sld, "column window exceeds leading dimension");
+  if (rows * cols == 0) return CGAN_OK;
+  copy2d_kernel<<<ew_grid(ctx, rows * cols), 256, 0, ctx->stream>>>(d, dld, doff, s, sld, soff, rows, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_axpby(cgan_ctx* ctx, float* y, float a, const float* x, float b, const float* y0, float c, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n >= 0, "bad argument");
+  if (n == 0) return CGAN_OK;
+  axpby_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, a, x, b, y0, c, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_scale_by_dev(cgan_ctx* ctx, float* y, const float* x, const float* s, float mul, int inverse, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && s && n >= 0, "bad argument");
+  if (n == 0) return CGAN_OK;
+  scale_by_dev_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, x, s, mul, inverse, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_dot(cgan_ctx* ctx, float* out, const float* a, const float* b, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && a && b && n > 0, "bad argument");
+  int blocks = ew_grid(ctx, n);
+  if (blocks > 1024) blocks = 1024;
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, 1024 * sizeof(float), &ws);
+  if (rc) return rc;
+  float* part = reinterpret_cast<float*>(ws);
+  dot_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(part, a, b, n);
+  CGAN_LAUNCHED(ctx);
+  sum_final_kernel<<<1, 256, 0, ctx->stream>>>(out, part, blocks, 1.0f);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_interpolate(cgan_ctx* ctx, float* y, const float* x, const float* xf, const float* alpha, int n, int64_t per) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && xf && alpha && n > 0 && per > 0, "bad argument");
+  long long tot = (long long)n * per;
+  interpolate_kernel<<<ew_grid(ctx, tot), 256, 0, ctx->stream>>>(y, x, xf, alpha, per, tot);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_one_hot(cgan_ctx* ctx, float* out, const int32_t* labels, int n, int classes) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && labels && n > 0 && classes > 0, "bad argument");
+  one_hot_kernel<<<ew_grid(ctx, (long long)n * classes), 256, 0, ctx->stream>>>(out, labels, n, classes);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_bias_add(cgan_ctx* ctx, float* y, const float* x, const float* bias, int64_t rows, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && bias && rows > 0 && c > 0, "bad argument");
+  bias_add_kernel<<<ew_grid(ctx, rows * c), 256, 0, ctx->stream>>>(y, x, bias, rows * c, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_act_fwd(cgan_ctx* ctx, float* y, const float* x, int kind, float leak, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
+  if (n == 0) return CGAN_OK;
+  act_fwd_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, x, kind, leak, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_act_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* ref, int kind, float leak, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && ref && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
+  if (n == 0) return CGAN_OK;
+  act_bwd_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(dx, dy, ref, kind, leak, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && a && b && n >= 0, "bad argument");
+  if (n == 0) return CGAN_OK;
+  add_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, a, b, n);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+#define POOL_ARGS_OK(ctx) CGAN_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "need even h,w")
+int cgan_avgpool2_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x, "null pointer"); POOL_ARGS_OK(ctx);
+  avgpool2_fwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(y, x, n, h, w, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_avgpool2_bwd(cgan_ctx* ctx, float* dx, const float* dy, int n, int h, int w, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy, "null pointer"); POOL_ARGS_OK(ctx);
+  avgpool2_bwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c), 256, 0, ctx->stream>>>(dx, dy, n, h, w, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_maxpool2_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x, "null pointer"); POOL_ARGS_OK(ctx);
+  maxpool2_fwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(y, x, n, h, w, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_maxpool2_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* x, int n, int h, int w, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && x, "null pointer"); POOL_ARGS_OK(ctx);
+  maxpool2_bwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(dx, dy, x, n, h, w, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_globalpool_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int hw, int c, float scale) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n > 0 && hw > 0 && c > 0, "bad argument");
+  globalpool_fwd_kernel<<<ew_grid(ctx, (long long)n * c), 256, 0, ctx->stream>>>(y, x, n, hw, c, scale);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_globalpool_bwd(cgan_ctx* ctx, float* dx, const float* dy, int n, int hw, int c, float scale) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && n > 0 && hw > 0 && c > 0, "bad argument");
+  globalpool_bwd_kernel<<<ew_grid(ctx, (long long)n * hw * c), 256, 0, ctx->stream>>>(dx, dy, n, hw, c, scale);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_softmax_fwd(cgan_ctx* ctx, float* y, const float* x, int64_t rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && rows > 0 && cols > 0 && rows < (1ll << 31), "bad argument");
+  softmax_fwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(y, x, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_softmax_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* y, int64_t rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && y && rows > 0 && cols > 0 && rows < (1ll << 31), "bad argument");
+  softmax_bwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(dx, dy, y, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_rowdot(cgan_ctx* ctx, float* out, const float* a, const float* b, int64_t rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && a && b && rows > 0 && cols > 0, "bad argument");
+  rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, ctx->stream>>>(out, a, b, rows, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_rowscale(cgan_ctx* ctx, float* y, const float* a, const float* s, int64_t rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && a && s && rows > 0 && cols > 0, "bad argument");
+  rowscale_kernel<<<ew_grid(ctx, rows * cols), 256, 0, ctx->stream>>>(y, a, s, rows * cols, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_gan_loss(cgan_ctx* ctx, int kind, const float* lr, const float* lf, int b, float* out4, float* dl, int which) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, lr && lf && out4 && b > 0 && kind >= 0 && kind <= 3 && (which == 0 || which == 1), "bad argument");
+  gan_loss_kernel<<<1, 256, 0, ctx->stream>>>(kind, lr, lf, b, out4, dl, which);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_gp_penalty(cgan_ctx* ctx, float* pen, float* dg, const float* g, int n, int64_t per, float weight) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, pen && g && n > 0 && per > 0, "bad argument");
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, (size_t)n * sizeof(float), &ws);
+  if (rc) return rc;
+  float* slopes = reinterpret_cast<float*>(ws);
+  gp_slopes_kernel<<<n, 256, 0, ctx->stream>>>(slopes, g, per);
+  CGAN_LAUNCHED(ctx);
+  gp_penalty_kernel<<<1, 256, 0, ctx->stream>>>(pen, slopes, n);
+  CGAN_LAUNCHED(ctx);
+  if (dg) {
+    long long tot = (long long)n * per;
+    gp_grad_kernel<<<ew_grid(ctx, tot), 256, 0, ctx->stream>>>(dg, g, slopes, per, tot, 2.0f * weight / (float)n);
+    CGAN_LAUNCHED(ctx);
+  }
+  return CGAN_OK;
+}
+int cgan_adam_step(cgan_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                   float eps, float gscale, int32_t* step, float* ema, float ema_decay, int32_t ema_start) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, p && g && m && v && step && n > 0, "bad argument");
+  step_inc_kernel<<<1, 1, 0, ctx->stream>>>(step);
+  CGAN_LAUNCHED(ctx);
+  adam_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step, ema, ema_decay, ema_start);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}

@@ -1,0 +1,308 @@
+"""ModularGAN: the training step (reference gans/modular_gan.py:56-670) on one B200 per process.
+
+What TF did with a static graph + TPUEstimator is done here with:
+  * an eager "cycle" (disc_iters D-updates + 1 G-update, the unrolled/TPU semantics of
+    model_fn :512-604) written against the taped C-ABI ops, and
+  * CUDA-graph capture of that whole cycle (streams + graphs instead of a tracing compiler), so the
+    per-step host cost is one graph launch; all state (weights, Adam moments, BN moving averages,
+    spectral-norm u vectors, step counters, EMA shadows) lives in HBM and is updated in place.
+Data parallelism: one process per GPU, gradients of a flat per-network buffer are all-reduced
+with NCCL (CrossShardOptimizer, :606-616) and BN moments are all-reduced inside standardize_batch.
+"""
+import numpy as np
+import torch
+
+from .. import gin_lite as gin
+from .. import kernels as K
+from .. import tape
+from .. import variables as V
+from ..architectures import resnet5, resnet_biggan, resnet_cifar, sndcgan
+from ..tpu import tpu_ops
+from . import consts, loss_lib, penalty_lib
+from .abstract_gan import AbstractGAN
+
+
+class AdamOptimizer(object):
+  """tf.train.AdamOptimizer hyper-parameters; the update itself is cgan_adam_step (TF form:
+  lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps outside the corrected sqrt)."""
+
+  def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
+
+
+gin.external_configurable(AdamOptimizer, "tf.train.AdamOptimizer")
+
+
+class _FlatAdam(object):
+  def __init__(self, opt, flat):
+    self.opt, self.flat = opt, flat
+    n = flat["total"]
+    dev = flat["param"].t.device
+    self.m = tape.DT(torch.zeros(n, dtype=torch.float32, device=dev))
+    self.v = tape.DT(torch.zeros(n, dtype=torch.float32, device=dev))
+    self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+
+  def apply(self, grad_scale, ema=None, ema_decay=0.0, ema_start=0):
+    o, f = self.opt, self.flat
+    K._call("adam_step", f["param"].ptr, f["grad"].ptr, self.m.ptr, self.v.ptr, f["total"], float(o.learning_rate),
+            float(o.beta1), float(o.beta2), float(o.epsilon), float(grad_scale), self.step.data_ptr(),
+            None if ema is None else ema.ptr, float(ema_decay), int(ema_start))
+
+
+@gin.configurable(blacklist=["dataset", "parameters", "model_dir"])
+class ModularGAN(AbstractGAN):
+  """Gin-configurable GAN (reference gans/modular_gan.py:56-165 constructor contract)."""
+
+  def __init__(self, dataset, parameters, model_dir, deprecated_split_disc_calls=False,
+               experimental_joint_gen_for_disc=False, experimental_force_graph_unroll=False, g_use_ema=False,
+               ema_decay=0.9999, ema_start_step=40000, g_optimizer_fn=AdamOptimizer, d_optimizer_fn=None,
+               g_lr=0.0002, d_lr=None, conditional=False, fit_label_distribution=False):
+    super(ModularGAN, self).__init__(dataset=dataset, parameters=parameters, model_dir=model_dir)
+    if deprecated_split_disc_calls or fit_label_distribution:
+      raise NotImplementedError("deprecated_split_disc_calls / fit_label_distribution are outside the hot path")
+    self._experimental_joint_gen_for_disc = experimental_joint_gen_for_disc
+    self._g_use_ema = g_use_ema
+    self._ema_decay = ema_decay
+    self._ema_start_step = ema_start_step
+    self._g_optimizer_fn = g_optimizer_fn
+    self._d_optimizer_fn = d_optimizer_fn if d_optimizer_fn is not None else g_optimizer_fn
+    self._g_lr = g_lr
+    self._d_lr = g_lr if d_lr is None else d_lr
+    if conditional and not self._dataset.num_classes:
+      raise ValueError("Option 'conditional' selected but dataset {} does not have labels".format(
+          self._dataset.name))
+    self._conditional = conditional
+    self._architecture = parameters["architecture"]
+    self._z_dim = parameters["z_dim"]
+    self._lambda = parameters["lambda"]
+    self._disc_iters = parameters.get("disc_iters", 1)
+    self.d_loss = None
+    self.g_loss = None
+    self.penalty_loss = None
+    self._discriminator = None
+    self._generator = None
+    self.store = V.VariableStore(seed=parameters.get("seed", 0))
+    self._graph = None
+    self._built_batch = None
+
+  # ---- architecture registry (reference :169-213) ---------------------------------------------
+  @property
+  def conditional(self):
+    return self._conditional
+
+  @property
+  def generator(self):
+    if self._generator is None:
+      module = {consts.RESNET5_ARCH: resnet5, consts.RESNET_BIGGAN_ARCH: resnet_biggan,
+                consts.RESNET_CIFAR_ARCH: resnet_cifar, consts.SNDCGAN_ARCH: sndcgan}.get(self._architecture)
+      if module is None:
+        raise NotImplementedError("Architecture {} not implemented.".format(self._architecture))
+      self._generator = module.Generator(image_shape=self._dataset.image_shape)
+    return self._generator
+
+  @property
+  def discriminator(self):
+    if self._discriminator is None:
+      module = {consts.RESNET5_ARCH: resnet5, consts.RESNET_BIGGAN_ARCH: resnet_biggan,
+                consts.RESNET_CIFAR_ARCH: resnet_cifar, consts.SNDCGAN_ARCH: sndcgan}.get(self._architecture)
+      if module is None:
+        raise NotImplementedError("Architecture {} not implemented.".format(self._architecture))
+      self._discriminator = module.Discriminator()
+    return self._discriminator
+
+  def _get_one_hot_labels(self, labels):
+    """reference :359-363."""
+    if not self.conditional:
+      raise ValueError("_get_one_hot_labels() called but GAN is not conditional.")
+    return K.one_hot(labels, self._dataset.num_classes)
+
+  # ---- loss (reference create_loss :618-670) ------------------------------------------------------
+  def create_loss(self, features, labels, params=None, is_training=True, for_discriminator=True):
+    """Sets self.d_loss / self.g_loss.  features: dict with "images", "generated" (+"sampled_labels", "alpha").
+    As in TF, the penalty sub-graph only runs when d_loss is the fetched tensor."""
+    images = features["images"]
+    generated = features["generated"]
+    if self.conditional:
+      y = self._get_one_hot_labels(labels)
+      sampled_y = self._get_one_hot_labels(features["sampled_labels"])
+      all_y = K.concat_rows(y, sampled_y)
+    else:
+      y = sampled_y = all_y = None
+    all_images = K.concat_rows(images, generated)
+    d_all, d_all_logits, _ = self.discriminator(all_images, y=all_y, is_training=is_training)
+    b = images.shape[0]
+    d_real, d_fake = K.slice_rows(d_all, 0, b), K.slice_rows(d_all, b, 2 * b)
+    d_real_logits, d_fake_logits = K.slice_rows(d_all_logits, 0, b), K.slice_rows(d_all_logits, b, 2 * b)
+    self.d_loss, _, _, self.g_loss = loss_lib.get_losses(
+        d_real=d_real, d_fake=d_fake, d_real_logits=d_real_logits, d_fake_logits=d_fake_logits)
+    if for_discriminator:
+      penalty_loss = penalty_lib.get_penalty_loss(
+          x=images, x_fake=generated, y=y, is_training=is_training, discriminator=self.discriminator,
+          alpha=features.get("alpha"))
+      self.penalty_loss = penalty_loss
+      if penalty_loss.node is not None:
+        self.d_loss = K.add(self.d_loss, K.affine(penalty_loss, self._lambda))
+
+  # ---- build -----------------------------------------------------------------------------------------
+  def build(self, batch_size):
+    """Creates all variables (one dry G/D call, like TF graph construction), packs them into flat buffers,
+    creates optimizer state and the static input buffers for `batch_size` per sub-step."""
+    K.lib()
+    K.sync_stream()
+    k = self._disc_iters
+    h, w, c = self._dataset.image_shape
+    dev = K._RT["device"]
+    b = batch_size
+    self.inputs = []
+    for _ in range(k + 1):
+      f = {"images": tape.DT(torch.zeros(b, h, w, c, device=dev)), "z": tape.DT(torch.zeros(b, self._z_dim, device=dev))}
+      if self.conditional:
+        f["labels"] = tape.DT(torch.zeros(b, dtype=torch.int32, device=dev))
+        f["sampled_labels"] = tape.DT(torch.zeros(b, dtype=torch.int32, device=dev))
+      f["alpha"] = tape.DT(torch.zeros(b, 1, 1, 1, device=dev))
+      self.inputs.append(f)
+    self.losses = tape.DT(torch.zeros(k + 1, device=dev))
+    with V.use(self.store), tape.no_record():
+      f = self.inputs[0]
+      sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
+      gen = self.generator(f["z"], y=sy, is_training=True)
+      all_y = K.concat_rows(sy, sy) if self.conditional else None
+      self.discriminator(K.concat_rows(f["images"], gen), y=all_y, is_training=True)
+    self.flat_g = self.store.pack("generator")
+    self.flat_d = self.store.pack("discriminator")
+    self.store.reset_to_init()          # graph construction runs no ops: undo BN/u_var side effects
+    self.g_opt = _FlatAdam(self._g_optimizer_fn(self._g_lr), self.flat_g)
+    self.d_opt = _FlatAdam(self._d_optimizer_fn(self._d_lr), self.flat_d)
+    self.ema = None
+    if self._g_use_ema:
+      self.ema = tape.DT(self.flat_g["param"].t.clone())
+    self._built_batch = b
+    torch.cuda.synchronize()
+    return self
+
+  # ---- one cycle (reference model_fn :512-604, unrolled) -------------------------------------------------
+  def _apply_grads(self, prefix, flat, grads, names):
+    K.fill_(flat["grad"], 0.0)
+    for name, g in zip(names, grads):
+      if g is not None:
+        K.copy_(self.store.grad_view(prefix, name), g)
+    world = tpu_ops.num_replicas()
+    if world > 1:
+      tpu_ops.cross_replica_sum_(flat["grad"])
+    return 1.0 / world
+
+  def _cycle(self):
+    k = self._disc_iters
+    with V.use(self.store):
+      # _split_inputs_and_generate_samples (:428-469): all G forwards first; only the last one is differentiated
+      gens = []
+      for i in range(k + 1):
+        f = self.inputs[i]
+        sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
+        with tape.record(i == k):
+          gens.append(self.generator(f["z"], y=sy, is_training=True))
+      d_params = self.store.trainable_under("discriminator")
+      g_params = self.store.trainable_under("generator")
+      ones = K.fill_(K.empty(1), 1.0)
+      for i in range(k):                                # _train_discriminator (:471-485)
+        f = dict(self.inputs[i])
+        f["generated"] = tape.DT(gens[i].t)             # tf.stop_gradient
+        self.create_loss(f, f.get("labels"), for_discriminator=True)
+        grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add)
+        scale = self._apply_grads("discriminator", self.flat_d, grads, list(d_params.keys()))
+        self.d_opt.apply(scale)
+        K._call("copy", self.losses.ptr + 4 * i, self.d_loss.ptr, 1)
+        self.d_loss = self.g_loss = None
+      f = dict(self.inputs[k])                          # _train_generator (:487-510)
+      f["generated"] = gens[k]
+      self.create_loss(f, f.get("labels"), for_discriminator=False)
+      grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add)
+      scale = self._apply_grads("generator", self.flat_g, grads, list(g_params.keys()))
+      self.g_opt.apply(scale, self.ema, self._ema_decay, self._ema_start_step)
+      K._call("copy", self.losses.ptr + 4 * k, self.g_loss.ptr, 1)
+      self.d_loss = self.g_loss = None
+
+  # ---- public step API -------------------------------------------------------------------------------------
+  def set_inputs(self, images, z, labels=None, sampled_labels=None, alphas=None, non_blocking=True):
+    """Host -> device copy of one cycle's inputs (lists of length disc_iters+1 of numpy / pinned torch arrays)."""
+    def put(dst, src):
+      if src is None:
+        return
+      t = src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src))
+      dst.t.copy_(t.view(dst.t.shape) if t.numel() == dst.t.numel() else t, non_blocking=non_blocking)
+    for i, f in enumerate(self.inputs):
+      put(f["images"], images[i])
+      put(f["z"], z[i])
+      if self.conditional:
+        put(f["labels"], labels[i])
+        put(f["sampled_labels"], sampled_labels[i])
+      if alphas is not None:
+        put(f["alpha"], alphas[i])
+
+  def run_cycle(self):
+    """Executes one cycle on the current inputs (graph replay when captured).  Asynchronous."""
+    if self._graph is not None:
+      self._graph.replay()
+    else:
+      K.sync_stream()
+      self._cycle()
+
+  def capture(self, warmup=3):
+    """Capture the cycle into a CUDA graph.  State mutated by the warm-up/capture passes is restored."""
+    snap = self.snapshot()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      K.sync_stream()
+      for _ in range(warmup):
+        self._cycle()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      K.sync_stream()
+      self._cycle()
+    K.sync_stream()
+    torch.cuda.synchronize()
+    self._graph = g
+    self.restore(snap)
+    return g
+
+  def read_losses(self):
+    """(d_losses list, g_loss) of the last cycle — a device->host read (synchronises)."""
+    a = self.losses.t.cpu().numpy()
+    return [float(x) for x in a[:-1]], float(a[-1])
+
+  @property
+  def global_step(self):
+    return int(self.g_opt.step.item())
+
+  @property
+  def global_step_disc(self):
+    return int(self.d_opt.step.item())
+
+  # ---- state I/O (checkpoint key space = reference variable names) ------------------------------------------
+  def snapshot(self):
+    s = {"vars": {k: v.t.clone() for k, v in self.store.vars.items()},
+         "g": (self.g_opt.m.t.clone(), self.g_opt.v.t.clone(), self.g_opt.step.clone()),
+         "d": (self.d_opt.m.t.clone(), self.d_opt.v.t.clone(), self.d_opt.step.clone()),
+         "ema": None if self.ema is None else self.ema.t.clone(), "losses": self.losses.t.clone()}
+    return s
+
+  def restore(self, s):
+    for k, v in self.store.vars.items():
+      v.t.copy_(s["vars"][k])
+    for opt, key in ((self.g_opt, "g"), (self.d_opt, "d")):
+      opt.m.t.copy_(s[key][0]); opt.v.t.copy_(s[key][1]); opt.step.copy_(s[key][2])
+    if self.ema is not None:
+      self.ema.t.copy_(s["ema"])
+    self.losses.t.copy_(s["losses"])
+    torch.cuda.synchronize()
+
+  def state_numpy(self):
+    return self.store.state_numpy()
+
+  def load_numpy(self, state):
+    self.store.load_numpy(state)
+    if self.ema is not None:
+      self.ema.t.copy_(self.flat_g["param"].t)

@@ -1,0 +1,34 @@
+"""Gradient penalties (reference gans/penalty_lib.py:28-108)."""
+import torch
+
+from .. import gin_lite as gin
+from .. import kernels as K
+from .. import tape
+from .. import utils
+
+
+@gin.configurable
+def no_penalty():
+  """reference penalty_lib.py:28-30."""
+  return K.zeros(1)
+
+
+@gin.configurable(whitelist=[])
+def wgangp_penalty(discriminator, x, x_fake, y, is_training, alpha=None):
+  """WGAN gradient penalty (reference penalty_lib.py:59-82).  `alpha` [B,1,1,1] may be fed (parity tests,
+  bench); otherwise it is drawn U[0,1) on the device."""
+  if alpha is None:
+    alpha = tape.DT(torch.rand(x.shape[0], 1, 1, 1, device=x.t.device, dtype=torch.float32))
+  interpolates = K.interpolate(x, x_fake, alpha)
+  interpolates.req = True                      # differentiate the logits wrt this leaf
+  with tape.record(True):
+    logits = discriminator(interpolates, y=y, is_training=is_training, reuse=True)[1]
+    ones = K.fill_(K.empty(*logits.shape), 1.0)
+    (gradients,) = tape.backward([(logits, ones)], [interpolates], K.add, create_graph=True)
+    return K.gp_penalty(gradients)
+
+
+@gin.configurable("penalty", whitelist=["fn"])
+def get_penalty_loss(fn=no_penalty, **kwargs):
+  """Returns the penalty loss (reference penalty_lib.py:105-108)."""
+  return utils.call_with_accepted_args(fn, **kwargs)

@@ -1,0 +1,583 @@
+"""Taped device ops: each function launches sm_100a kernels through the C-ABI (include/cgan_b200.h)
+and records its vector-Jacobian product on the tape (tape.py).  The vjps are written with the same
+ops, so second-order differentiation (WGAN-GP, gans/penalty_lib.py:59-82) works by construction.
+
+These are the B200 stand-ins for the TF library calls the reference's ops library makes
+(arch_ops.py / resnet_ops.py / loss_lib.py / penalty_lib.py); file:line citations sit on each op.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .tape import DT, attach, no_record
+
+_RT = {"lib": None, "device": None}
+
+ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH01 = 1, 2, 3, 4
+LOSSES = {"non_saturating": 0, "hinge": 1, "wasserstein": 2, "least_squares": 3}
+
+
+def init(device=0):
+  """Bind this process to one GPU (one process per GPU) and load the C-ABI library."""
+  if not torch.cuda.is_available():
+    raise _lib.CganError("compare_gan_b200 needs a CUDA device: the product path has no CPU fallback")
+  torch.cuda.set_device(device)
+  _RT["lib"] = _lib.get_lib(device)
+  _RT["device"] = torch.device("cuda", device)
+  sync_stream()
+  return _RT["lib"]
+
+
+def lib():
+  if _RT["lib"] is None:
+    init(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+  return _RT["lib"]
+
+
+def sync_stream():
+  """Point the library at torch's current stream (call after switching streams / entering capture)."""
+  _RT["lib"].set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def empty(*shape):
+  return DT(torch.empty(shape, dtype=torch.float32, device=_RT["device"]))
+
+
+def from_numpy(a, req=False):
+  import numpy as np
+  a = np.asarray(a)
+  t = torch.from_numpy(np.ascontiguousarray(a).reshape(a.shape)).to(_RT["device"])
+  return DT(t.contiguous(), req)
+
+
+def _call(name, *args):
+  _RT["lib"].call(name, *args)
+
+
+# ------------------------------------------------------------------------------------ basic helpers
+
+def fill_(x, value):
+  _call("fill", x.ptr, float(value), x.numel)
+  return x
+
+
+def zeros(*shape):
+  return fill_(empty(*shape), 0.0)
+
+
+def copy_(dst, src):
+  assert dst.numel == src.numel
+  _call("copy", dst.ptr, src.ptr, dst.numel)
+  return dst
+
+
+def reshape(x, *shape):
+  """tf.reshape: zero-copy view, taped."""
+  y = DT(x.t.view(*shape))
+  xs = x.shape
+  return attach("reshape", y, [x], lambda g, needs: [reshape(g, *xs)])
+
+
+def add(a, b):
+  assert a.shape == b.shape, (a.shape, b.shape)
+  y = empty(*a.shape)
+  _call("add", y.ptr, a.ptr, b.ptr, y.numel)
+  return attach("add", y, [a, b], lambda g, needs: [g if needs[0] else None, g if needs[1] else None])
+
+
+def affine(x, a, c=0.0):
+  """y = a*x + c  (sndcgan.py:108 `x*2-1`; loss weights)."""
+  y = empty(*x.shape)
+  _call("axpby", y.ptr, float(a), x.ptr, 0.0, None, float(c), y.numel)
+  return attach("affine", y, [x], lambda g, needs: [affine(g, a)])
+
+
+def axpy_(y, a, x):
+  """y += a*x in place (gradient accumulation into flat buffers; untaped)."""
+  _call("axpby", y.ptr, float(a), x.ptr, 1.0, y.ptr, 0.0, y.numel)
+  return y
+
+
+def concat_rows(a, b):
+  """tf.concat([a, b], axis=0) (modular_gan.py:657)."""
+  assert a.shape[1:] == b.shape[1:]
+  y = empty(a.shape[0] + b.shape[0], *a.shape[1:])
+  na = a.numel
+  _call("copy", y.ptr, a.ptr, na)
+  _call("copy", y.ptr + 4 * na, b.ptr, b.numel)
+  ra = a.shape[0]
+
+  def vjp(g, needs):
+    return [slice_rows(g, 0, ra) if needs[0] else None, slice_rows(g, ra, g.shape[0]) if needs[1] else None]
+  return attach("concat_rows", y, [a, b], vjp)
+
+
+def slice_rows(x, lo, hi):
+  """x[lo:hi] as a zero-copy view (tf.split on axis 0, modular_gan.py:660-661)."""
+  y = DT(x.t[lo:hi])
+  n0 = x.shape[0]
+
+  def vjp(g, needs):
+    full = zeros(*((n0,) + g.shape[1:]))
+    per = g.numel // max(1, g.shape[0])
+    _call("copy", full.ptr + 4 * lo * per, g.ptr, g.numel)
+    return [full]
+  return attach("slice_rows", y, [x], vjp)
+
+
+def concat_cols(a, b):
+  """tf.concat([a, b], axis=1) for rank-2 tensors (resnet_biggan.py:254)."""
+  n, ca, cb = a.shape[0], a.shape[1], b.shape[1]
+  y = empty(n, ca + cb)
+  _call("copy2d", y.ptr, ca + cb, 0, a.ptr, ca, 0, n, ca)
+  _call("copy2d", y.ptr, ca + cb, ca, b.ptr, cb, 0, n, cb)
+
+  def vjp(g, needs):
+    return [slice_cols(g, 0, ca) if needs[0] else None, slice_cols(g, ca, ca + cb) if needs[1] else None]
+  return attach("concat_cols", y, [a, b], vjp)
+
+
+def slice_cols(x, lo, hi):
+  """x[:, lo:hi] (tf.split on axis 1, resnet_biggan.py:251-252)."""
+  n, c = x.shape
+  y = empty(n, hi - lo)
+  _call("copy2d", y.ptr, hi - lo, 0, x.ptr, c, lo, n, hi - lo)
+
+  def vjp(g, needs):
+    full = zeros(n, c)
+    _call("copy2d", full.ptr, c, lo, g.ptr, hi - lo, 0, n, hi - lo)
+    return [full]
+  return attach("slice_cols", y, [x], vjp)
+
+
+# ------------------------------------------------------------------------------------ contractions
+
+def same_pad(n, k, s):
+  """TF SAME: out=ceil(n/s), pad_before = max((out-1)*s+k-n, 0)//2."""
+  out = -(-n // s)
+  total = max((out - 1) * s + k - n, 0)
+  return out, total // 2
+
+
+def conv_desc(n, h, w, cin, cout, kh, kw, stride, upsample):
+  vh, vw = (2 * h, 2 * w) if upsample else (h, w)
+  oh, pt = same_pad(vh, kh, stride)
+  ow, pl = same_pad(vw, kw, stride)
+  return _lib.ConvDesc(n, h, w, cin, cout, kh, kw, stride, 1 if upsample else 0, oh, ow, pt, pl)
+
+
+def _conv_fwd_raw(d, x, w, bias):
+  y = empty(d.n, d.oh, d.ow, d.cout)
+  _call("conv2d_fwd", ctypes.byref(d), x.ptr, w.ptr, None if bias is None else bias.ptr, y.ptr)
+  return y
+
+
+def conv2d(x, w, bias=None, stride=1, upsample=False):
+  """tf.nn.conv2d(..., "SAME") + bias (arch_ops.py:568-572); `upsample` fuses resnet_ops.unpool
+  (resnet_ops.py:35-56, 122-123) without materialising the zeros.  w is HWIO."""
+  n, h, ww, cin = x.shape
+  kh, kw, wcin, cout = w.shape
+  if wcin != cin:
+    raise ValueError("conv2d: kernel expects %d input channels, got %d" % (wcin, cin))
+  d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, upsample)
+  y = _conv_fwd_raw(d, x, w, bias)
+
+  def vjp(g, needs):
+    return [conv2d_dgrad(d, g, w) if needs[0] else None,
+            conv2d_wgrad(d, x, g) if needs[1] else None,
+            colsum(reshape(g, -1, cout)) if (bias is not None and needs[2]) else None]
+  return attach("conv2d", y, [x, w, bias], vjp)
+
+
+def conv2d_dgrad(d, dy, w):
+  """Input gradient of conv2d == tf.nn.conv2d_transpose (arch_ops.py:588-589)."""
+  dx = empty(d.n, d.h, d.w, d.cin)
+  _call("conv2d_dgrad", ctypes.byref(d), dy.ptr, w.ptr, dx.ptr)
+
+  def vjp(g, needs):   # linear in dy and in w
+    return [_taped_fwd(d, g, w) if needs[0] else None,
+            conv2d_wgrad(d, g, dy) if needs[1] else None]
+  return attach("conv2d_dgrad", dx, [dy, w], vjp)
+
+
+def _taped_fwd(d, x, w):
+  y = _conv_fwd_raw(d, x, w, None)
+
+  def vjp(g, needs):
+    return [conv2d_dgrad(d, g, w) if needs[0] else None, conv2d_wgrad(d, x, g) if needs[1] else None]
+  return attach("conv2d", y, [x, w], vjp)
+
+
+def conv2d_wgrad(d, x, dy):
+  """Filter gradient (TF Conv2DBackpropFilter); deterministic split-K."""
+  dw = empty(d.kh, d.kw, d.cin, d.cout)
+  _call("conv2d_wgrad", ctypes.byref(d), x.ptr, dy.ptr, dw.ptr)
+
+  def vjp(g, needs):
+    raise NotImplementedError("third-order differentiation through conv2d_wgrad is not needed on this path")
+  return attach("conv2d_wgrad", dw, [x, dy], vjp)
+
+
+def deconv2d(x, w, bias, out_hw, stride):
+  """tf.nn.conv2d_transpose + bias (arch_ops.py:579-592).  w is [kh,kw,cout,cin(=x channels)]: as an HWIO conv
+  kernel it maps the deconv OUTPUT (cout channels) to x, so deconv(x) is that conv's input gradient."""
+  n, h, ww, cin = x.shape
+  kh, kw, cout, wcin = w.shape
+  if wcin != cin:
+    raise ValueError("deconv2d: kernel expects %d input channels, got %d" % (wcin, cin))
+  oh, ow = out_hw
+  d = conv_desc(n, oh, ow, cout, cin, kh, kw, stride, False)
+  if (d.oh, d.ow) != (h, ww):
+    raise ValueError("deconv2d: output shape %s incompatible with input %s" % ((oh, ow), (h, ww)))
+  y = conv2d_dgrad(d, x, w)
+  return bias_add(y, bias) if bias is not None else y
+
+
+def matmul(a, b, ta=False, tb=False):
+  """tf.matmul (arch_ops.py:548)."""
+  m = a.shape[1] if ta else a.shape[0]
+  k = a.shape[0] if ta else a.shape[1]
+  kb = b.shape[1] if tb else b.shape[0]
+  n = b.shape[0] if tb else b.shape[1]
+  if k != kb:
+    raise ValueError("matmul: inner dimensions differ: %d vs %d" % (k, kb))
+  c = empty(m, n)
+  _call("gemm", int(ta), int(tb), m, n, k, 1.0, a.ptr, a.shape[1], b.ptr, b.shape[1], 0.0, c.ptr, n)
+
+  def vjp(g, needs):
+    ga = gb = None
+    if needs[0]:
+      ga = matmul(b, g, tb, True) if ta else matmul(g, b, False, not tb)
+    if needs[1]:
+      gb = matmul(g, a, True, ta) if tb else matmul(a, g, not ta, False)
+    return [ga, gb]
+  return attach("matmul", c, [a, b], vjp)
+
+
+def bmm(a, b, ta=False, tb=False):
+  """Batched tf.matmul on rank-3 tensors (arch_ops.py:744, 753)."""
+  bsz = a.shape[0]
+  m = a.shape[2] if ta else a.shape[1]
+  k = a.shape[1] if ta else a.shape[2]
+  n = b.shape[1] if tb else b.shape[2]
+  c = empty(bsz, m, n)
+  _call("gemm_batched", int(ta), int(tb), m, n, k, 1.0, a.ptr, a.shape[2], a.shape[1] * a.shape[2],
+        b.ptr, b.shape[2], b.shape[1] * b.shape[2], 0.0, c.ptr, n, m * n, bsz)
+
+  def vjp(g, needs):
+    ga = gb = None
+    if needs[0]:
+      ga = bmm(b, g, tb, True) if ta else bmm(g, b, False, not tb)
+    if needs[1]:
+      gb = bmm(g, a, True, ta) if tb else bmm(a, g, not ta, False)
+    return [ga, gb]
+  return attach("bmm", c, [a, b], vjp)
+
+
+def colsum(x2, groups=1):
+  """Per-channel sum over rows (bias / beta gradients)."""
+  rows, c = x2.shape
+  out = empty(c) if groups == 1 else empty(groups, c)
+  _call("colsum", out.ptr, x2.ptr, groups, rows // groups, c)
+  return out   # leaf of the backward pass: never differentiated again
+
+
+def bias_add(x, bias):
+  c = x.shape[-1]
+  y = empty(*x.shape)
+  _call("bias_add", y.ptr, x.ptr, bias.ptr, x.numel // c, c)
+
+  def vjp(g, needs):
+    return [g if needs[0] else None, colsum(reshape(g, -1, c)) if needs[1] else None]
+  return attach("bias_add", y, [x, bias], vjp)
+
+
+# ------------------------------------------------------------------------------------ pointwise / pooling
+
+def act(x, kind, leak=0.0):
+  y = empty(*x.shape)
+  _call("act_fwd", y.ptr, x.ptr, kind, float(leak), y.numel)
+  ref = x if kind in (ACT_RELU, ACT_LRELU) else y
+  return attach("act%d" % kind, y, [x], lambda g, needs: [act_bwd(g, ref, kind, leak)])
+
+
+def act_bwd(g, ref, kind, leak=0.0):
+  dx = empty(*g.shape)
+  _call("act_bwd", dx.ptr, g.ptr, ref.ptr, kind, float(leak), dx.numel)
+
+  def vjp(gg, needs):
+    if kind not in (ACT_RELU, ACT_LRELU):
+      raise NotImplementedError("second derivative only needed for piecewise-linear activations")
+    return [act_bwd(gg, ref, kind, leak)]   # the mask is constant almost everywhere: no gradient to `ref`
+  return attach("act_bwd%d" % kind, dx, [g], vjp)
+
+
+def relu(x):
+  return act(x, ACT_RELU)
+
+
+def lrelu(x, leak=0.2):
+  return act(x, ACT_LRELU, leak)
+
+
+def sigmoid(x):
+  return act(x, ACT_SIGMOID)
+
+
+def tanh01(x):
+  """(tanh(x)+1)/2 (sndcgan.py:74-78, resnet_biggan.py:301)."""
+  return act(x, ACT_TANH01)
+
+
+def avgpool2(x):
+  """tf.nn.pool AVG 2x2 s2 (resnet_ops.py:131-133)."""
+  n, h, w, c = x.shape
+  y = empty(n, h // 2, w // 2, c)
+  _call("avgpool2_fwd", y.ptr, x.ptr, n, h, w, c)
+  return attach("avgpool2", y, [x], lambda g, needs: [avgpool2_bwd(g, h, w)])
+
+
+def avgpool2_bwd(g, h, w):
+  n, _, _, c = g.shape
+  dx = empty(n, h, w, c)
+  _call("avgpool2_bwd", dx.ptr, g.ptr, n, h, w, c)
+  return attach("avgpool2_bwd", dx, [g], lambda gg, needs: [avgpool2(gg)])
+
+
+def maxpool2(x):
+  """tf.layers.max_pooling2d(2, 2) (arch_ops.py:741, 750)."""
+  n, h, w, c = x.shape
+  y = empty(n, h // 2, w // 2, c)
+  _call("maxpool2_fwd", y.ptr, x.ptr, n, h, w, c)
+
+  def vjp(g, needs):
+    dx = empty(n, h, w, c)
+    _call("maxpool2_bwd", dx.ptr, g.ptr, x.ptr, n, h, w, c)
+    return [dx]
+  return attach("maxpool2", y, [x], vjp)
+
+
+def globalpool(x, mean):
+  """tf.reduce_mean / reduce_sum over axes [1,2] (resnet_cifar.py:156, resnet_biggan.py:405)."""
+  n, h, w, c = x.shape
+  scale = 1.0 / (h * w) if mean else 1.0
+  y = empty(n, c)
+  _call("globalpool_fwd", y.ptr, x.ptr, n, h * w, c, scale)
+  return attach("globalpool", y, [x], lambda g, needs: [globalpool_bwd(g, h, w, scale)])
+
+
+def globalpool_bwd(g, h, w, scale):
+  n, c = g.shape
+  dx = empty(n, h, w, c)
+  _call("globalpool_bwd", dx.ptr, g.ptr, n, h * w, c, scale)
+
+  def vjp(gg, needs):
+    y = empty(n, c)
+    _call("globalpool_fwd", y.ptr, gg.ptr, n, h * w, c, scale)
+    return [attach("globalpool", y, [gg], lambda g3, needs3: [globalpool_bwd(g3, h, w, scale)])]
+  return attach("globalpool_bwd", dx, [g], vjp)
+
+
+def softmax(x):
+  """tf.nn.softmax over the last axis (arch_ops.py:745)."""
+  cols = x.shape[-1]
+  rows = x.numel // cols
+  y = empty(*x.shape)
+  _call("softmax_fwd", y.ptr, x.ptr, rows, cols)
+
+  def vjp(g, needs):
+    dx = empty(*x.shape)
+    _call("softmax_bwd", dx.ptr, g.ptr, y.ptr, rows, cols)
+    return [dx]
+  return attach("softmax", y, [x], vjp)
+
+
+def rowdot(a, b):
+  """sum(a*b, axis=1, keepdims=True) (resnet_biggan.py:423)."""
+  rows, cols = a.shape
+  y = empty(rows, 1)
+  _call("rowdot", y.ptr, a.ptr, b.ptr, rows, cols)
+  return attach("rowdot", y, [a, b],
+                lambda g, needs: [rowscale(b, g) if needs[0] else None, rowscale(a, g) if needs[1] else None])
+
+
+def rowscale(a, s):
+  rows, cols = a.shape
+  y = empty(rows, cols)
+  _call("rowscale", y.ptr, a.ptr, s.ptr, rows, cols)
+  return attach("rowscale", y, [a, s],
+                lambda g, needs: [rowscale(g, s) if needs[0] else None, rowdot(g, a) if needs[1] else None])
+
+
+def scale_by_param(x, s):
+  """x * s with s a scalar parameter on device (non_local_block sigma, arch_ops.py:755-758)."""
+  y = empty(*x.shape)
+  _call("scale_by_dev", y.ptr, x.ptr, s.ptr, 1.0, 0, y.numel)
+
+  def vjp(g, needs):
+    gx = gs = None
+    if needs[0]:
+      gx = empty(*x.shape)
+      _call("scale_by_dev", gx.ptr, g.ptr, s.ptr, 1.0, 0, gx.numel)
+    if needs[1]:
+      gs = empty(*s.shape)
+      _call("dot", gs.ptr, g.ptr, x.ptr, x.numel)
+    return [gx, gs]
+  return attach("scale_by_param", y, [x, s], vjp)
+
+
+def one_hot(labels_i32, classes):
+  """tf.one_hot (modular_gan.py:359-363); labels: int32 device tensor wrapped in a DT."""
+  n = labels_i32.t.shape[0]
+  y = empty(n, classes)
+  _call("one_hot", y.ptr, labels_i32.ptr, n, classes)
+  return y
+
+
+def interpolate(x, xf, alpha):
+  """x + alpha*(x_fake - x), alpha [B,1,1,1] (penalty_lib.py:74-75).  Result is a fresh leaf."""
+  y = empty(*x.shape)
+  _call("interpolate", y.ptr, x.ptr, xf.ptr, alpha.ptr, x.shape[0], x.numel // x.shape[0])
+  return y
+
+
+# ------------------------------------------------------------------------------------ batch norm
+
+class BNState(object):
+  """Per-layer buffers: moving averages or accumulators (arch_ops.py:66-191) and scratch."""
+  __slots__ = ("moving_mean", "moving_var", "accu_mean", "accu_var", "accu_counter", "update_accus")
+
+  def __init__(self):
+    self.moving_mean = self.moving_var = None
+    self.accu_mean = self.accu_var = self.accu_counter = self.update_accus = None
+
+
+def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_after=False, allreduce=None, world=1):
+  """Training-mode standardize_batch (+ gamma/beta) (arch_ops.py:194-319, 353-366, 435-444).
+
+  gamma/beta: [C] DTs, or [N,C] when cond (conditional BN); either may be None.
+  allreduce(stats_dt) sums a [2C] buffer over replicas (cross-replica moments, tpu_ops.py:94-125).
+  """
+  c = x.shape[-1]
+  rows = x.numel // c
+  rps = rows // x.shape[0]
+  stats = empty(2 * c)
+  _call("bn_moments", stats.ptr, x.ptr, rows, c)
+  if allreduce is not None and world > 1:
+    allreduce(stats)
+    _call("axpby", stats.ptr, 1.0 / world, stats.ptr, 0.0, None, 0.0, 2 * c)
+  mv = empty(2 * c)
+  mm = state.moving_mean if state is not None else None
+  mvv = state.moving_var if state is not None else None
+  _call("bn_finalize", mv.ptr, stats.ptr, c, None if mm is None else mm.ptr, None if mvv is None else mvv.ptr,
+        float(decay))
+  y = empty(*x.shape)
+  _call("bn_apply", y.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr,
+        None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
+
+  def vjp(g, needs):
+    if relu_after:
+      g = act_bwd(g, y, ACT_RELU)     # y>0 <=> pre-activation>0
+    sums = empty(2 * c)
+    dgamma = dbeta = None
+    if gamma is not None and needs[1]:
+      dgamma = empty(*gamma.shape)
+    if beta is not None and needs[2]:
+      dbeta = empty(*beta.shape)
+    with no_record():
+      _call("bn_bwd_reduce", sums.ptr, None if dgamma is None else dgamma.ptr, None if dbeta is None else dbeta.ptr,
+            g.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr, int(cond))
+      count = rows
+      if allreduce is not None and world > 1:
+        allreduce(sums)
+        count = rows * world
+      dx = None
+      if needs[0]:
+        dx = empty(*x.shape)
+        _call("bn_bwd_apply", dx.ptr, g.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps),
+              None if gamma is None else gamma.ptr, int(cond), sums.ptr, 1.0 / count)
+    return [dx, dgamma, dbeta]
+  return attach("bn_train", y, [x, gamma, beta], vjp)
+
+
+def bn_infer(x, gamma, beta, eps, state, use_moving_averages, cond=False, relu_after=False):
+  """Inference-mode standardize_batch: moving averages (arch_ops.py:66-119) or accumulators (:122-191)."""
+  c = x.shape[-1]
+  rows = x.numel // c
+  rps = rows // x.shape[0]
+  if use_moving_averages:
+    mv = empty(2 * c)
+    _call("copy", mv.ptr, state.moving_mean.ptr, c)
+    _call("copy", mv.ptr + 4 * c, state.moving_var.ptr, c)
+  else:
+    stats = empty(2 * c)
+    _call("bn_moments", stats.ptr, x.ptr, rows, c)
+    batch = empty(2 * c)
+    _call("bn_finalize", batch.ptr, stats.ptr, c, None, None, 0.0)
+    mv = empty(2 * c)
+    _call("bn_accumulate", mv.ptr, batch.ptr, c, state.accu_mean.ptr, state.accu_var.ptr, state.accu_counter.ptr,
+          state.update_accus.ptr)
+  y = empty(*x.shape)
+  _call("bn_apply", y.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr,
+        None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
+  return y
+
+
+# ------------------------------------------------------------------------------------ spectral norm
+
+def spectral_normalize(w, u, left, eps=1e-12):
+  """arch_ops.py:453-535: one power iteration, `u` (persistent state) updated in place, returns w/sigma."""
+  rows = w.numel // w.shape[-1]
+  cols = w.shape[-1]
+  v = empty(cols if left else rows)
+  sigma = empty(1)
+  wbar = empty(*w.shape)
+  _call("spectral_norm", w.ptr, rows, cols, int(left), float(eps), u.ptr, v.ptr, sigma.ptr, wbar.ptr)
+  # the backward needs u AFTER this call's update; later calls overwrite u_var, so keep a copy
+  u_used = empty(*u.shape)
+  _call("copy", u_used.ptr, u.ptr, u.numel)
+
+  def vjp(g, needs):
+    dw = empty(*w.shape)
+    _call("spectral_norm_bwd", dw.ptr, g.ptr, wbar.ptr, rows, cols, int(left), u_used.ptr, v.ptr, sigma.ptr)
+    return [dw]
+  return attach("spectral_norm", wbar, [w], vjp)
+
+
+# ------------------------------------------------------------------------------------ losses / penalties
+
+def _scale_by(x, g):
+  """x * g[0] with g a one-element device tensor (chain rule through a scalar loss)."""
+  y = empty(*x.shape)
+  _call("scale_by_dev", y.ptr, x.ptr, g.ptr, 1.0, 0, y.numel)
+  return y
+
+
+def gan_losses(kind, d_real_logits, d_fake_logits):
+  """gans/loss_lib.py:53-148 in one fused kernel.  Returns (d_loss, d_loss_real, d_loss_fake, g_loss) as
+  one-element device tensors; d_loss and g_loss are differentiable wrt both logit tensors."""
+  b = d_real_logits.shape[0]
+  out4 = empty(4)
+  dl_d = empty(2 * b, 1)
+  dl_g = empty(2 * b, 1)
+  _call("gan_loss", LOSSES[kind], d_real_logits.ptr, d_fake_logits.ptr, b, out4.ptr, dl_d.ptr, 0)
+  _call("gan_loss", LOSSES[kind], d_real_logits.ptr, d_fake_logits.ptr, b, out4.ptr, dl_g.ptr, 1)
+
+  def make(idx, dl):
+    loss = DT(out4.t[idx:idx + 1])
+
+    def vjp(g, needs):
+      s = _scale_by(dl, g)
+      return [DT(s.t[:b]) if needs[0] else None, DT(s.t[b:]) if needs[1] else None]
+    return attach("gan_loss", loss, [d_real_logits, d_fake_logits], vjp)
+  return make(0, dl_d), DT(out4.t[1:2]), DT(out4.t[2:3]), make(3, dl_g)
+
+
+def gp_penalty(g):
+  """gans/penalty_lib.py:78-81 on g = d logits / d x_hat: mean((sqrt(1e-4 + sum g^2) - 1)^2)."""
+  n = g.shape[0]
+  pen = empty(1)
+  dg = empty(*g.shape)
+  _call("gp_penalty", pen.ptr, dg.ptr, g.ptr, n, g.numel // n, 1.0)
+  return attach("gp_penalty", pen, [g], lambda gg, needs: [_scale_by(dg, gg)])

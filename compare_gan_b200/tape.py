@@ -1,0 +1,143 @@
+"""Host-side tape for reverse-mode differentiation over the C-ABI kernels.
+
+TensorFlow's graph autodiff (tf.gradients, used by optimizer.minimize at
+gans/modular_gan.py:478-497 and by the gradient penalties at gans/penalty_lib.py:78) is
+replaced by a small tape: every op in `kernels.py` launches sm_100a kernels through the C-ABI
+and records a vector-Jacobian closure that is itself written in terms of those ops, so the
+WGAN-GP second backward needs no special casing.  PyTorch is used for device memory only
+(`torch.empty`); no torch op, no torch.autograd, on this path.  The Python overhead disappears
+when the whole cycle is captured into a CUDA graph (gans/modular_gan.py of this package).
+"""
+import contextlib
+
+import torch
+
+
+class DT(object):
+  """Device tensor: float32 (or int32 labels), C-contiguous; 4-D tensors are NHWC."""
+  __slots__ = ("t", "node", "req")
+
+  def __init__(self, t, req=False):
+    assert t.is_contiguous()
+    self.t = t
+    self.node = None
+    self.req = req
+
+  @property
+  def shape(self):
+    return tuple(self.t.shape)
+
+  @property
+  def ptr(self):
+    return self.t.data_ptr()
+
+  @property
+  def numel(self):
+    return self.t.numel()
+
+  def view(self, *shape):
+    """Zero-copy reshape WITHOUT a tape link (use kernels.reshape inside differentiated code)."""
+    return DT(self.t.view(*shape))
+
+  def cpu(self):
+    return self.t.detach().cpu().numpy()
+
+
+class Node(object):
+  __slots__ = ("name", "inputs", "vjp", "out")
+
+  def __init__(self, name, inputs, vjp, out):
+    self.name, self.inputs, self.vjp, self.out = name, inputs, vjp, out
+
+
+_RECORD = [True]
+
+
+@contextlib.contextmanager
+def no_record():
+  _RECORD.append(False)
+  try:
+    yield
+  finally:
+    _RECORD.pop()
+
+
+@contextlib.contextmanager
+def record(flag=True):
+  _RECORD.append(flag)
+  try:
+    yield
+  finally:
+    _RECORD.pop()
+
+
+def recording():
+  return _RECORD[-1]
+
+
+def attach(name, out, inputs, vjp):
+  """Record `out = op(inputs)`; vjp(gout, needs) -> list of grads (None where not needed)."""
+  if _RECORD[-1] and any(i is not None and i.req for i in inputs):
+    out.req = True
+    out.node = Node(name, inputs, vjp, out)
+  return out
+
+
+def _topo(roots):
+  order, seen = [], set()
+  stack = [(r, False) for r in roots if r.node is not None]
+  while stack:
+    t, done = stack.pop()
+    if done:
+      order.append(t.node)
+      continue
+    if id(t) in seen:
+      continue
+    seen.add(id(t))
+    stack.append((t, True))
+    for i in t.node.inputs:
+      if i is not None and i.node is not None and id(i) not in seen:
+        stack.append((i, False))
+  return order   # inputs before consumers
+
+
+def backward(roots, wrt, add_fn, create_graph=False):
+  """roots: list of (DT, seed) with seed a DT or None (meaning d(root)/d(root)=1 for scalar-loss ops).
+  Returns the list of gradients for `wrt` (None where unreachable)."""
+  order = _topo([r for r, _ in roots])
+  dep = set(id(w) for w in wrt)
+  for node in order:
+    if any(i is not None and id(i) in dep for i in node.inputs):
+      dep.add(id(node.out))
+  grads = {}
+  keep = set(id(w) for w in wrt)
+  for r, seed in roots:
+    if id(r) in dep:
+      grads[id(r)] = ("seed", seed) if id(r) not in grads else grads[id(r)]
+  with record(create_graph):
+    for node in reversed(order):
+      oid = id(node.out)
+      if oid not in grads or oid not in dep:
+        continue
+      g = grads[oid]
+      if isinstance(g, tuple):
+        g = g[1]
+      needs = [i is not None and id(i) in dep for i in node.inputs]
+      if not any(needs):
+        continue
+      gins = node.vjp(g, needs)
+      for i, gi in zip(node.inputs, gins):
+        if gi is None or i is None or id(i) not in dep:
+          continue
+        if id(i) in grads:
+          prev = grads[id(i)]
+          grads[id(i)] = add_fn(prev, gi)
+        else:
+          grads[id(i)] = gi
+      if oid not in keep:
+        del grads[oid]
+  out = []
+  for w in wrt:
+    g = grads.get(id(w))
+    out.append(None if g is None or isinstance(g, tuple) else g)
+  return out

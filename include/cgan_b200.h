@@ -1,0 +1,175 @@
+/* cgan_b200.h — C-ABI of the B200 (sm_100a) GAN-step / FID engine.
+ *
+ * The reference (google/compare_gan) has no FFI: its seam is the Python ops library
+ * (compare_gan/architectures/arch_ops.py, resnet_ops.py, gans/loss_lib.py, gans/penalty_lib.py,
+ * tf.train.AdamOptimizer, tfgan FID).  Each entry point below replaces the TF library kernel(s)
+ * behind one of those call sites; the citation after each declaration is the reference
+ * file:line it stands in for (paths relative to /root/reference/compare_gan/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *  - activations float32 NHWC; conv kernels HWIO [kh,kw,cin,cout]; linear kernels [in,out]
+ *    (arch_ops.py:543-546, 563-565, 583-585).
+ *  - every call is asynchronous on the context's stream (cgan_ctx_set_stream); no call
+ *    synchronises or allocates after warm-up (workspace grows on first use only).
+ *  - return 0 on success, non-zero error code otherwise; message via cgan_last_error().
+ *    Nothing throws across the ABI.  A context is not thread-safe.
+ */
+#ifndef CGAN_B200_H_
+#define CGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgan_ctx cgan_ctx;
+
+enum { CGAN_OK = 0, CGAN_ERR_ARG = 1, CGAN_ERR_CUDA = 2, CGAN_ERR_WORKSPACE = 3, CGAN_ERR_UNSUPPORTED = 4 };
+
+/* ---- context ------------------------------------------------------------------------- */
+int cgan_version(void);
+int cgan_ctx_create(cgan_ctx** out, int device);
+int cgan_ctx_destroy(cgan_ctx* ctx);
+int cgan_ctx_set_stream(cgan_ctx* ctx, void* cuda_stream);          /* cudaStream_t */
+int cgan_ctx_reserve_workspace(cgan_ctx* ctx, size_t bytes);        /* pre-size (never during capture) */
+/* 0: exact fp32 SIMT contraction; 1: tcgen05 kind::tf32 tensor-core path where the shape allows. */
+int cgan_ctx_set_math_mode(cgan_ctx* ctx, int mode);
+const char* cgan_last_error(cgan_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t cgan_launch_count(cgan_ctx* ctx);
+
+/* ---- utilities ------------------------------------------------------------------------ */
+int cgan_fill(cgan_ctx*, float* dst, float value, int64_t n);
+int cgan_copy(cgan_ctx*, float* dst, const float* src, int64_t n);
+/* dst[r, dst_off + j] = src[r, src_off + j], j < cols  (tf.concat / tf.split on axis 1) */
+int cgan_copy2d(cgan_ctx*, float* dst, int dst_ld, int dst_off, const float* src, int src_ld, int src_off,
+                int64_t rows, int cols);
+/* y = a*x + b*y0 + c   (y0 nullable) — x*2-1 (sndcgan.py:108), (tanh+1)/2, grad accumulation */
+int cgan_axpby(cgan_ctx*, float* y, float a, const float* x, float b, const float* y0, float c, int64_t n);
+/* y[i] = x[i] * (*scalar_dev) * mul  — non_local_block sigma (arch_ops.py:758), 1/sigma scaling */
+int cgan_scale_by_dev(cgan_ctx*, float* y, const float* x, const float* scalar_dev, float mul, int inverse, int64_t n);
+/* out[0] = sum_i a[i]*b[i]  (deterministic two-stage) — d sigma of non_local_block, SN backward */
+int cgan_dot(cgan_ctx*, float* out_dev, const float* a, const float* b, int64_t n);
+/* y[n,:] = x[n,:] + alpha[n]*(xf[n,:]-x[n,:]) — WGAN-GP interpolates (gans/penalty_lib.py:74-75) */
+int cgan_interpolate(cgan_ctx*, float* y, const float* x, const float* xf, const float* alpha, int n, int64_t per);
+/* one-hot rows: out[n, labels[n]] = 1 (gans/modular_gan.py:359-363) */
+int cgan_one_hot(cgan_ctx*, float* out, const int32_t* labels, int n, int classes);
+
+/* ---- contractions ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t n, h, w, cin;      /* real input tensor [n,h,w,cin] */
+  int32_t cout, kh, kw, stride;
+  int32_t upsample;          /* 1: input is zero-inserted 2x first (resnet_ops.py:35-56, :122-123), never materialised */
+  int32_t oh, ow;            /* output spatial size */
+  int32_t pad_t, pad_l;      /* TF SAME: before = total/2 */
+} cgan_conv_desc;
+
+/* y = conv(x, w) + bias   — tf.nn.conv2d(..., "SAME") + bias_add, arch_ops.py:568-572;
+ * with desc.upsample: conv(unpool(x)), resnet_ops.py:122-130. */
+int cgan_conv2d_fwd(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const float* bias, float* y);
+/* dx = d/dx of the above (TF Conv2DBackpropInput); this is also tf.nn.conv2d_transpose, arch_ops.py:588-589. */
+int cgan_conv2d_dgrad(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w_hwio, float* dx);
+/* dw = d/dw (TF Conv2DBackpropFilter); deterministic split-K. */
+int cgan_conv2d_wgrad(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* dy, float* dw);
+/* C = alpha*op(A)*op(B) + beta*C, row-major, op = transpose when flag set — tf.matmul in
+ * linear (arch_ops.py:548), projection head (resnet_biggan.py:419-423), attention (arch_ops.py:744,753). */
+int cgan_gemm(cgan_ctx*, int trans_a, int trans_b, int m, int n, int k, float alpha, const float* a, int lda,
+              const float* b, int ldb, float beta, float* c, int ldc);
+int cgan_gemm_batched(cgan_ctx*, int trans_a, int trans_b, int m, int n, int k, float alpha, const float* a, int lda,
+                      int64_t stride_a, const float* b, int ldb, int64_t stride_b, float beta, float* c, int ldc,
+                      int64_t stride_c, int batch);
+
+/* ---- rows x channels reductions / bias -------------------------------------------------- */
+/* y[r,c] = x[r,c] + bias[c]   (linear bias, arch_ops.py:549-555) */
+int cgan_bias_add(cgan_ctx*, float* y, const float* x, const float* bias, int64_t rows, int c);
+/* out[g,c] = sum over the rows of group g of x[r,c]; rows = groups*rows_per_group (bias / beta gradients) */
+int cgan_colsum(cgan_ctx*, float* out, const float* x, int groups, int64_t rows_per_group, int c);
+
+/* ---- batch norm (arch_ops.py:194-319, 327-367, 423-445; tpu/tpu_ops.py:94-125) ------------ */
+/* local moments: mean[c] = sum x / rows, meansq[c] = sum x^2 / rows  (fp32; stats[0:c]=mean, stats[c:2c]=meansq).
+ * Cross-replica BN all-reduces this [2c] buffer and divides by the replica count (tpu_ops.py:110-125). */
+int cgan_bn_moments(cgan_ctx*, float* stats2c, const float* x, int64_t rows, int c);
+/* var = meansq - mean^2 (arch_ops.py:289-297 / tpu_ops.py:125); optional moving-average update
+ * m <- m - (m - batch)*(1-decay) (arch_ops.py:100-117); moving_* nullable. */
+int cgan_bn_finalize(cgan_ctx*, float* mean_var2c, const float* stats2c, int c, float* moving_mean, float* moving_var,
+                     float decay);
+/* accumulator inference path (arch_ops.py:122-191): if *update_accus_dev==1 accumulate; write accu/counter to mean_var2c */
+int cgan_bn_accumulate(cgan_ctx*, float* mean_var2c, const float* batch_mean_var2c, int c, float* accu_mean,
+                       float* accu_var, float* accu_counter, const float* update_accus_dev);
+/* y = (x-mean)*rsqrt(var+eps)*gamma + beta; gamma/beta: [c] (cond=0) or [samples,c] (cond=1, one row per sample of
+ * rows_per_sample rows); either nullable; act: 0 none, 1 relu. */
+int cgan_bn_apply(cgan_ctx*, float* y, const float* x, int64_t rows, int c, int64_t rows_per_sample,
+                  const float* mean_var2c, float eps, const float* gamma, const float* beta, int cond, int act);
+/* backward of training-mode BN.  Step 1 (reduce): sums2c[0:c] = sum dxhat, sums2c[c:2c] = sum dxhat*xhat over LOCAL rows
+ * (all-reduced by the caller under cross-replica BN); dgamma/dbeta: [c] or [samples,c] (nullable). */
+int cgan_bn_bwd_reduce(cgan_ctx*, float* sums2c, float* dgamma, float* dbeta, const float* dy, const float* x,
+                       int64_t rows, int c, int64_t rows_per_sample, const float* mean_var2c, float eps,
+                       const float* gamma, int cond);
+/* Step 2: dx = inv*(dxhat - sums[0]/count - xhat*sums[1]/count), count = GLOBAL rows. */
+int cgan_bn_bwd_apply(cgan_ctx*, float* dx, const float* dy, const float* x, int64_t rows, int c, int64_t rows_per_sample,
+                      const float* mean_var2c, float eps, const float* gamma, int cond, const float* sums2c,
+                      float inv_count);
+
+/* ---- spectral norm (arch_ops.py:453-535) -------------------------------------------------- */
+/* One power iteration on w[rows,cols]; left=1: u[rows], v[cols] (arch_ops.py:505-509,525); left=0: u[cols], v[rows]
+ * (:511-513,527).  u is updated in place (:516); v and sigma are outputs; wbar = w / sigma (nullable). */
+int cgan_spectral_norm(cgan_ctx*, const float* w, int rows, int cols, int left, float eps, float* u_inout, float* v_out,
+                       float* sigma_out, float* wbar_out);
+/* dw = (dwbar - <dwbar, wbar> * outer) / sigma, outer = u v^T (left) or v u^T (right); u,v constants (:521-522). */
+int cgan_spectral_norm_bwd(cgan_ctx*, float* dw, const float* dwbar, const float* wbar, int rows, int cols, int left,
+                           const float* u, const float* v, const float* sigma);
+
+/* ---- pointwise / pooling ------------------------------------------------------------------- */
+enum { CGAN_ACT_RELU = 1, CGAN_ACT_LRELU = 2, CGAN_ACT_SIGMOID = 3, CGAN_ACT_TANH01 = 4 /* (tanh(x)+1)/2 */ };
+int cgan_act_fwd(cgan_ctx*, float* y, const float* x, int kind, float leak, int64_t n);
+/* dx = dy * act'(.) ; `ref` is x for relu/lrelu and y for sigmoid/tanh01 */
+int cgan_act_bwd(cgan_ctx*, float* dx, const float* dy, const float* ref, int kind, float leak, int64_t n);
+int cgan_add(cgan_ctx*, float* y, const float* a, const float* b, int64_t n);
+/* 2x2 stride-2 average pool (resnet_ops.py:131-133) and its adjoint */
+int cgan_avgpool2_fwd(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c);
+int cgan_avgpool2_bwd(cgan_ctx*, float* dx, const float* dy, int n, int h, int w, int c);
+/* 2x2 stride-2 max pool (arch_ops.py:741,750) and backward (first-max wins, as TF MaxPoolGrad) */
+int cgan_maxpool2_fwd(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c);
+int cgan_maxpool2_bwd(cgan_ctx*, float* dx, const float* dy, const float* x, int n, int h, int w, int c);
+/* global pool over h*w: out[n,c] = scale * sum_hw x (mean: resnet_cifar.py:156; sum: resnet_biggan.py:405) */
+int cgan_globalpool_fwd(cgan_ctx*, float* y, const float* x, int n, int hw, int c, float scale);
+int cgan_globalpool_bwd(cgan_ctx*, float* dx, const float* dy, int n, int hw, int c, float scale);
+/* row softmax (tf.nn.softmax, arch_ops.py:745) and its backward */
+int cgan_softmax_fwd(cgan_ctx*, float* y, const float* x, int64_t rows, int cols);
+int cgan_softmax_bwd(cgan_ctx*, float* dx, const float* dy, const float* y, int64_t rows, int cols);
+/* out[r] = sum_j a[r,j]*b[r,j]  (projection discriminator, resnet_biggan.py:423) */
+int cgan_rowdot(cgan_ctx*, float* out, const float* a, const float* b, int64_t rows, int cols);
+/* y[r,j] = a[r,j] * s[r] */
+int cgan_rowscale(cgan_ctx*, float* y, const float* a, const float* s, int64_t rows, int cols);
+
+/* ---- losses and penalties ------------------------------------------------------------------ */
+enum { CGAN_LOSS_NON_SATURATING = 0, CGAN_LOSS_HINGE = 1, CGAN_LOSS_WASSERSTEIN = 2, CGAN_LOSS_LEAST_SQUARES = 3 };
+/* gans/loss_lib.py:53-148.  out4 = {d_loss, d_loss_real, d_loss_fake, g_loss}.  dlogits[2b] (nullable) receives
+ * d(d_loss)/dlogit (which=0) or d(g_loss)/dlogit (which=1) for the [real; fake] logit vector. */
+int cgan_gan_loss(cgan_ctx*, int kind, const float* logits_real, const float* logits_fake, int b, float* out4,
+                  float* dlogits, int which);
+/* gans/penalty_lib.py:78-81: slopes = sqrt(1e-4 + sum_hwc g^2); penalty = mean((slopes-1)^2);
+ * dg (nullable) = d(weight*penalty)/dg. */
+int cgan_gp_penalty(cgan_ctx*, float* penalty_out, float* dg, const float* g, int n, int64_t per, float weight);
+
+/* ---- optimizer (tf.train.AdamOptimizer + tf.train.ExponentialMovingAverage, gans/modular_gan.py:498-508) ---- */
+/* One fused multi-tensor step over a flat parameter buffer.  *step_dev (int32, device) is incremented first; then
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updated; p -= lr_t*m/(sqrt(v)+eps).  If ema != NULL:
+ * ema <- ema - (ema-p)*(1-d), d = ema_decay*[ (t-1) >= ema_start_step ]. grad_scale multiplies g first (1/world). */
+int cgan_adam_step(cgan_ctx*, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float grad_scale, int32_t* step_dev, float* ema, float ema_decay, int32_t ema_start_step);
+
+/* ---- FID statistics (tfgan frechet_classifier_distance_from_activations, metrics/fid_score.py:49-51) ---- */
+/* sum[d] += sum_n act[n,d]; sumxxT[d,d] += act^T act, accumulated in float64 on device. */
+int cgan_cov_accumulate(cgan_ctx*, const float* act, int n, int d, double* sum, double* sumxxT);
+/* bilinear resize NHWC [n,h,w,c] -> [n,oh,ow,c] (tf.image.resize_bilinear, align_corners=False) then (x*255-128)/128
+ * when `inception_scale` (eval_utils.py:157-175). */
+int cgan_resize_bilinear(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c, int oh, int ow, int inception_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CGAN_B200_H_ */

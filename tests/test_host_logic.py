@@ -1,0 +1,109 @@
+"""CPU tests of the host-side logic that needs no GPU: gin-compatible config surface, TF SAME padding
+arithmetic, dataset surface, metric math against the oracle and the reference's golden FID."""
+import numpy as np
+import pytest
+
+from compare_gan_b200 import datasets
+from compare_gan_b200 import gin_lite as gin
+from compare_gan_b200 import kernels as K
+from compare_gan_b200.metrics import fid_score, inception_score, kid_score
+from oracle import metrics as ometrics
+from oracle import tf_ops as T
+
+REF_CONFIGS = "/root/reference/example_configs"
+
+
+def test_same_padding_matches_oracle():
+  for n in range(1, 20):
+    for k in (1, 3, 4, 5):
+      for s in (1, 2):
+        out, before, _ = T._same_pads(n, k, s)
+        assert K.same_pad(n, k, s) == (out, before)
+
+
+def test_gin_bindings_scopes_and_refs():
+  gin.clear_config()
+
+  @gin.configurable("hp_test_fn", module="tmod")
+  def f(a, b=2, c=gin.REQUIRED):
+    return a, b, c
+  with pytest.raises(ValueError):
+    f(1)
+  gin.parse_config("hp_test_fn.c = 7\nscope1/hp_test_fn.b = 5\nX = 3\nhp_test_fn.b = %X")
+  assert f(1) == (1, 3, 7)
+  with gin.config_scope("scope1"):
+    assert f(1) == (1, 5, 7)
+  assert f(1, b=9) == (1, 9, 7)
+  with pytest.raises(ValueError):
+    gin.parse_config("hp_test_fn.nope = 1")
+  gin.clear_config()
+
+
+def test_example_config_parses_and_binds():
+  import os
+  from compare_gan_b200.gans import modular_gan  # noqa: F401
+  from compare_gan_b200 import runner_lib  # noqa: F401
+  gin.clear_config()
+  # a literal copy of the bindings of example_configs/resnet_cifar10.gin (the file itself lives in the read-only
+  # reference tree, which is absent on the GPU box)
+  text = """
+dataset.name = "cifar10"
+options.architecture = "resnet_cifar_arch"
+options.batch_size = 64
+options.gan_class = @ModularGAN
+options.lamba = 1
+options.training_steps = 40000
+options.z_dim = 128
+G.batch_norm_fn = @batch_norm
+standardize_batch.decay = 0.9
+standardize_batch.epsilon = 1e-5
+options.disc_iters = 5
+D.spectral_norm = True
+loss.fn = @non_saturating
+penalty.fn = @no_penalty
+ModularGAN.g_lr = 0.0002
+ModularGAN.g_optimizer_fn = @tf.train.AdamOptimizer
+tf.train.AdamOptimizer.beta1 = 0.5
+tf.train.AdamOptimizer.beta2 = 0.999
+"""
+  gin.parse_config(text)
+  opts = runner_lib.get_options_dict()
+  assert opts["architecture"] == "resnet_cifar_arch" and opts["disc_iters"] == 5 and opts["lambda"] == 1
+  assert opts["gan_class"] is modular_gan.ModularGAN
+  assert gin.query_parameter("standardize_batch.decay") == 0.9
+  if os.path.isdir(REF_CONFIGS):   # in the build container: every shipped config must parse unmodified
+    for fn in sorted(os.listdir(REF_CONFIGS)):
+      if fn.endswith(".gin") and "dcgan" not in fn:
+        gin.clear_config()
+        gin.parse_config(open(os.path.join(REF_CONFIGS, fn)).read())
+        assert runner_lib.get_options_dict()["gan_class"] is modular_gan.ModularGAN
+  gin.clear_config()
+
+
+def test_dataset_surface():
+  ds = datasets.get_dataset("cifar10")
+  assert ds.image_shape == (32, 32, 3) and ds.num_classes == 10 and ds.eval_test_samples == 10000
+  x = ds.sample_images(4)
+  assert x.shape == (4, 32, 32, 3) and x.dtype == np.float32 and 0 <= x.min() and x.max() < 1
+  assert datasets.get_dataset("imagenet_128").eval_test_samples == 50000
+  with pytest.raises(ValueError):
+    datasets.get_dataset("nope")
+
+
+def test_fid_golden_and_streaming_moments():
+  real = np.ones((100, 2)); real[:50, 0] = 2
+  gen = np.ones((100, 2)) * 9; gen[50:, 0] = 2
+  assert abs(fid_score.compute_fid_from_activations(gen, real) - 89.091) < 1e-4   # fid_score_test.py:31-40
+  rng = np.random.RandomState(0)
+  a = rng.randn(500, 12) * 2 + 1
+  mu, sigma = fid_score.moments_from_sums(a.sum(0), a.T @ a, 500)
+  np.testing.assert_allclose(mu, a.mean(0), rtol=1e-12)
+  np.testing.assert_allclose(sigma, np.cov(a, rowvar=False), rtol=1e-9, atol=1e-12)
+
+
+def test_is_and_kid_match_oracle():
+  rng = np.random.RandomState(1)
+  logits = rng.randn(200, 30)
+  assert abs(inception_score.classifier_score_from_logits(logits) - ometrics.inception_score_from_logits(logits)) < 1e-12
+  a, b = rng.randn(2100, 16), rng.randn(2500, 16) + 0.3
+  assert abs(kid_score.kid(a, b, gram=lambda x, y: x @ y.T) - ometrics.kid(a, b)) < 1e-12

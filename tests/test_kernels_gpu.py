@@ -1,0 +1,363 @@
+"""Per-op parity: every C-ABI kernel family against the CPU oracle on the same seeded inputs.
+Tolerances: fp32 SIMT path 2e-5 rel-L2 (reduction order only); stated per test otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gan as ogan
+from oracle import metrics as ometrics
+from oracle import tf_ops as T
+from tests.gpu_util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def K():
+  from compare_gan_b200 import kernels
+  kernels.init(0)
+  return kernels
+
+
+def dev(K, a, req=False):
+  return K.from_numpy(np.asarray(a, np.float32), req=req)
+
+
+def tape_grads(K, out, seed, wrt):
+  from compare_gan_b200 import tape
+  return tape.backward([(out, dev(K, seed))], wrt, K.add)
+
+
+CONV_CASES = [
+    # n, h, cin, cout, k, stride, upsample
+    (2, 8, 3, 16, 3, 1, False),
+    (2, 8, 16, 32, 3, 1, False),
+    (3, 4, 8, 8, 3, 1, True),
+    (2, 8, 16, 24, 4, 2, False),
+    (2, 8, 16, 16, 1, 1, False),
+    (2, 4, 8, 8, 1, 1, True),
+    (2, 9, 5, 7, 5, 2, False),
+    (2, 8, 32, 3, 3, 1, False),
+    (2, 16, 40, 136, 3, 1, False),
+    (1, 6, 8, 200, 3, 1, False),
+]
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,stride,up", CONV_CASES)
+def test_conv2d_fwd_dgrad_wgrad(K, n, h, cin, cout, k, stride, up):
+  rng = np.random.RandomState(hash((n, h, cin, cout, k, stride, up)) % 2**31)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) * 0.1).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt = torch.from_numpy(x).requires_grad_(True)
+  wt = torch.from_numpy(w).requires_grad_(True)
+  bt = torch.from_numpy(b).requires_grad_(True)
+  ref = T.conv2d_same(T.unpool(xt) if up else xt, wt, stride) + bt
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
+  y = K.conv2d(xd, wd, bd, stride=stride, upsample=up)
+  assert_close(y.cpu(), ref.detach().numpy(), TOL, "conv fwd")
+  gx, gw, gb = tape_grads(K, y, gy, [xd, wd, bd])
+  assert_close(gx.cpu(), xt.grad.numpy(), TOL, "conv dgrad")
+  assert_close(gw.cpu(), wt.grad.numpy(), TOL, "conv wgrad")
+  assert_close(gb.cpu(), bt.grad.numpy(), TOL, "conv bias grad")
+
+
+@pytest.mark.parametrize("k,stride,h", [(4, 2, 4), (3, 1, 6), (5, 2, 5)])
+def test_deconv2d(K, k, stride, h):
+  rng = np.random.RandomState(k * 10 + stride)
+  n, cin, cout = 2, 16, 8
+  oh = h * stride
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cout, cin) * 0.1).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt, wt = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(w).requires_grad_(True)
+  ref = T.conv2d_transpose_same(xt, wt, (oh, oh), stride) + torch.from_numpy(b)
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
+  y = K.deconv2d(xd, wd, bd, (oh, oh), stride)
+  assert_close(y.cpu(), ref.detach().numpy(), TOL, "deconv fwd")
+  gx, gw, gb = tape_grads(K, y, gy, [xd, wd, bd])
+  assert_close(gx.cpu(), xt.grad.numpy(), TOL, "deconv dx")
+  assert_close(gw.cpu(), wt.grad.numpy(), TOL, "deconv dw")
+  assert_close(gb.cpu(), gy.sum((0, 1, 2)), TOL, "deconv db")
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(5, 7, 3), (64, 130, 20), (256, 4096, 128), (33, 1, 257)])
+def test_matmul(K, ta, tb, m, n, k):
+  rng = np.random.RandomState(m + n + k)
+  a = rng.randn(*((k, m) if ta else (m, k))).astype(np.float32)
+  b = rng.randn(*((n, k) if tb else (k, n))).astype(np.float32)
+  at, bt = torch.from_numpy(a).requires_grad_(True), torch.from_numpy(b).requires_grad_(True)
+  ref = (at.t() if ta else at) @ (bt.t() if tb else bt)
+  gy = rng.randn(m, n).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  ad, bd = dev(K, a, True), dev(K, b, True)
+  c = K.matmul(ad, bd, ta, tb)
+  assert_close(c.cpu(), ref.detach().numpy(), TOL, "matmul")
+  ga, gb = tape_grads(K, c, gy, [ad, bd])
+  assert_close(ga.cpu(), at.grad.numpy(), TOL, "matmul dA")
+  assert_close(gb.cpu(), bt.grad.numpy(), TOL, "matmul dB")
+
+
+def test_bmm_attention_shapes(K):
+  rng = np.random.RandomState(0)
+  theta = rng.randn(3, 64, 6).astype(np.float32)
+  phi = rng.randn(3, 16, 6).astype(np.float32)
+  tt, pt = torch.from_numpy(theta).requires_grad_(True), torch.from_numpy(phi).requires_grad_(True)
+  ref = torch.softmax(tt @ pt.transpose(1, 2), -1)
+  gy = rng.randn(3, 64, 16).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  td, pd = dev(K, theta, True), dev(K, phi, True)
+  out = K.softmax(K.bmm(td, pd, False, True))
+  assert_close(out.cpu(), ref.detach().numpy(), TOL, "bmm+softmax")
+  gt, gp = tape_grads(K, out, gy, [td, pd])
+  assert_close(gt.cpu(), tt.grad.numpy(), 1e-4, "d theta")
+  assert_close(gp.cpu(), pt.grad.numpy(), 1e-4, "d phi")
+
+
+@pytest.mark.parametrize("shape,cond", [((4, 8, 8, 16), False), ((6, 4, 4, 40), True), ((16, 70), False),
+                                        ((3, 16, 16, 3), False)])
+def test_bn_train(K, shape, cond):
+  rng = np.random.RandomState(len(shape) + shape[-1])
+  c, n = shape[-1], shape[0]
+  x = (rng.randn(*shape) * 2 + 1).astype(np.float32)
+  gshape = (n, c) if cond else (c,)
+  gamma = (1 + 0.1 * rng.randn(*gshape)).astype(np.float32)
+  beta = (0.1 * rng.randn(*gshape)).astype(np.float32)
+  eps = 1e-5
+  xt = torch.from_numpy(x).requires_grad_(True)
+  gt, bt = torch.from_numpy(gamma).requires_grad_(True), torch.from_numpy(beta).requires_grad_(True)
+  x4 = xt.reshape(-1, 1, 1, c) if len(shape) == 2 else xt
+  mean, var = T.batch_moments(x4)
+  yn = T.normalize(x4, mean, var, eps).reshape(shape)
+  if cond:
+    ref = yn * gt.reshape(n, 1, 1, c) + bt.reshape(n, 1, 1, c)
+  else:
+    ref = yn * gt + bt
+  gy = rng.randn(*shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  st = K.BNState()
+  st.moving_mean, st.moving_var = dev(K, np.zeros(c)), dev(K, np.ones(c))
+  xd, gd, bd = dev(K, x, True), dev(K, gamma, True), dev(K, beta, True)
+  y = K.bn_train(xd, gd, bd, eps, st, decay=0.9, cond=cond)
+  assert_close(y.cpu(), ref.detach().numpy(), 1e-5, "bn fwd")
+  assert_close(st.moving_mean.cpu(), 0.1 * mean.detach().numpy(), 1e-5, "moving mean")
+  assert_close(st.moving_var.cpu(), 0.9 + 0.1 * var.detach().numpy(), 1e-5, "moving var")
+  gx, gg, gb = tape_grads(K, y, gy, [xd, gd, bd])
+  assert_close(gx.cpu(), xt.grad.numpy(), 5e-5, "bn dx")
+  assert_close(gg.cpu(), gt.grad.numpy(), 5e-5, "bn dgamma")
+  assert_close(gb.cpu(), bt.grad.numpy(), 5e-5, "bn dbeta")
+
+
+def test_bn_golden_tensor(K):
+  # reference architectures/arch_ops_test.py:29-61 through the CUDA kernels
+  import json, os
+  G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+  x = np.array(G["bn_input"]["x"], np.float32)
+  y = K.bn_train(dev(K, x), dev(K, np.ones(3)), dev(K, np.zeros(3)), 1e-3)
+  np.testing.assert_allclose(y.cpu(), np.array(G["bn_expected"]["y"], np.float32), rtol=1e-5, atol=1e-5)
+
+
+def test_bn_infer_accumulators(K):
+  # accumulator state machine (reference arch_ops_test.py:91-132) on the device kernels
+  st = K.BNState()
+  st.accu_mean, st.accu_var = dev(K, np.zeros(2)), dev(K, np.zeros(2))
+  st.accu_counter, st.update_accus = dev(K, np.array(1e-12)), dev(K, np.array(1.0))
+
+  def feed(mean, var):
+    m, v = np.array(mean, np.float32), np.array(var, np.float32)
+    x = np.stack([m - np.sqrt(v), m + np.sqrt(v)]).reshape(2, 1, 1, 2).astype(np.float32)
+    y = K.bn_infer(dev(K, x), None, None, 0.0, st, use_moving_averages=False).cpu()
+    inv = (y[1, 0, 0] - y[0, 0, 0]) / (x[1, 0, 0] - x[0, 0, 0])
+    return x[0, 0, 0] - y[0, 0, 0] / inv, 1.0 / inv ** 2
+  m, v = feed([1., 2.], [3., 4.])
+  np.testing.assert_allclose(m, [1., 2.], rtol=1e-4); np.testing.assert_allclose(v, [3., 4.], rtol=1e-4)
+  m, v = feed([5., 6.], [7., 8.])
+  np.testing.assert_allclose(m, [3., 4.], rtol=1e-4); np.testing.assert_allclose(v, [5., 6.], rtol=1e-4)
+  K.fill_(st.update_accus, 0.0)
+  m, v = feed([2., 2.], [3., 3.])
+  np.testing.assert_allclose(m, [3., 4.], rtol=1e-4); np.testing.assert_allclose(v, [5., 6.], rtol=1e-4)
+  np.testing.assert_allclose(st.accu_mean.cpu(), [6., 8.], rtol=1e-5)
+  np.testing.assert_allclose(st.accu_var.cpu(), [10., 12.], rtol=1e-5)
+  np.testing.assert_allclose(float(st.accu_counter.cpu()), 2.0, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,left", [((3, 3, 8, 16), True), ((3, 3, 16, 8), False), ((128, 4096), True),
+                                        ((1024, 1), True), ((20, 64), False)])
+def test_spectral_norm(K, shape, left):
+  rng = np.random.RandomState(shape[-1])
+  w = (rng.randn(*shape) * 0.05).astype(np.float32)
+  rows, cols = int(np.prod(shape[:-1])), shape[-1]
+  u0 = rng.randn(*((rows, 1) if left else (1, cols))).astype(np.float32)
+  wt = torch.from_numpy(w).requires_grad_(True)
+  sigma, u_new, v = T.spectral_sigma(wt.reshape(rows, cols), torch.from_numpy(u0), "left" if left else "right")
+  ref = wt / sigma
+  gy = rng.randn(*shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  wd, ud = dev(K, w, True), dev(K, u0)
+  wbar = K.spectral_normalize(wd, ud, left)
+  assert_close(wbar.cpu(), ref.detach().numpy(), 2e-5, "wbar")
+  assert_close(ud.cpu(), u_new.numpy(), 2e-5, "u update")
+  (gw,) = tape_grads(K, wbar, gy, [wd])
+  assert_close(gw.cpu(), wt.grad.numpy(), 1e-4, "sn backward")
+
+
+def test_pointwise_and_pools(K):
+  rng = np.random.RandomState(1)
+  x = rng.randn(3, 8, 8, 12).astype(np.float32)
+  gy = rng.randn(3, 8, 8, 12).astype(np.float32)
+  for name, fn, ref_fn in [("relu", K.relu, torch.relu), ("lrelu", lambda t: K.lrelu(t, 0.1), lambda t: T.lrelu(t, 0.1)),
+                           ("sigmoid", K.sigmoid, torch.sigmoid), ("tanh01", K.tanh01, lambda t: (torch.tanh(t) + 1) / 2),
+                           ("affine", lambda t: K.affine(t, 2.0, -1.0), lambda t: t * 2.0 - 1.0)]:
+    xt = torch.from_numpy(x).requires_grad_(True)
+    ref = ref_fn(xt)
+    ref.backward(torch.from_numpy(gy))
+    xd = dev(K, x, True)
+    y = fn(xd)
+    assert_close(y.cpu(), ref.detach().numpy(), 1e-6, name)
+    (gx,) = tape_grads(K, y, gy, [xd])
+    assert_close(gx.cpu(), xt.grad.numpy(), 1e-5, name + " grad")
+  for name, fn, ref_fn in [("avgpool", K.avgpool2, T.avg_pool2), ("maxpool", K.maxpool2, T.max_pool2),
+                           ("gmean", lambda t: K.globalpool(t, True), lambda t: t.mean((1, 2))),
+                           ("gsum", lambda t: K.globalpool(t, False), lambda t: t.sum((1, 2)))]:
+    xt = torch.from_numpy(x).requires_grad_(True)
+    ref = ref_fn(xt)
+    g2 = rng.randn(*ref.shape).astype(np.float32)
+    ref.backward(torch.from_numpy(g2))
+    xd = dev(K, x, True)
+    y = fn(xd)
+    assert_close(y.cpu(), ref.detach().numpy(), 1e-5, name)
+    (gx,) = tape_grads(K, y, g2, [xd])
+    assert_close(gx.cpu(), xt.grad.numpy(), 1e-5, name + " grad")
+
+
+def test_concat_slice_onehot_rowdot(K):
+  rng = np.random.RandomState(2)
+  a, b = rng.randn(4, 6).astype(np.float32), rng.randn(4, 3).astype(np.float32)
+  ad, bd = dev(K, a, True), dev(K, b, True)
+  cc = K.concat_cols(ad, bd)
+  assert_close(cc.cpu(), np.concatenate([a, b], 1), 0, "concat_cols")
+  g = rng.randn(4, 9).astype(np.float32)
+  ga, gb = tape_grads(K, cc, g, [ad, bd])
+  assert_close(ga.cpu(), g[:, :6], 0, "concat grad a"); assert_close(gb.cpu(), g[:, 6:], 0, "concat grad b")
+  s = K.slice_cols(ad, 2, 5)
+  assert_close(s.cpu(), a[:, 2:5], 0, "slice_cols")
+  (gs,) = tape_grads(K, s, g[:, :3], [ad])
+  full = np.zeros_like(a); full[:, 2:5] = g[:, :3]
+  assert_close(gs.cpu(), full, 0, "slice grad")
+  labels = np.array([1, 0, 3, 2], np.int32)
+  from compare_gan_b200.tape import DT
+  oh = K.one_hot(DT(torch.from_numpy(labels).cuda()), 5)
+  assert_close(oh.cpu(), np.eye(5, dtype=np.float32)[labels], 0, "one_hot")
+  c = rng.randn(4, 6).astype(np.float32)
+  cd = dev(K, c, True)
+  rd = K.rowdot(ad, cd)
+  assert_close(rd.cpu(), (a * c).sum(1, keepdims=True), 1e-6, "rowdot")
+  gr = rng.randn(4, 1).astype(np.float32)
+  g1, g2 = tape_grads(K, rd, gr, [ad, cd])
+  assert_close(g1.cpu(), c * gr, 1e-6, "rowdot da"); assert_close(g2.cpu(), a * gr, 1e-6, "rowdot db")
+  r0 = K.concat_rows(ad, cd)
+  assert_close(r0.cpu(), np.concatenate([a, c], 0), 0, "concat_rows")
+  x4 = rng.randn(3, 2, 2, 5).astype(np.float32)
+  sg = dev(K, np.array(0.7, np.float32), True)
+  xd = dev(K, x4, True)
+  y = K.scale_by_param(xd, sg)
+  assert_close(y.cpu(), x4 * 0.7, 1e-6, "scale_by_param")
+  gy = rng.randn(3, 2, 2, 5).astype(np.float32)
+  gx, gsig = tape_grads(K, y, gy, [xd, sg])
+  assert_close(gx.cpu(), gy * 0.7, 1e-6, "scale dx")
+  assert_close(gsig.cpu(), np.array((gy * x4).sum(), np.float32), 1e-5, "scale dsigma")
+
+
+@pytest.mark.parametrize("kind", ["non_saturating", "hinge", "wasserstein", "least_squares"])
+def test_losses(K, kind):
+  rng = np.random.RandomState(3)
+  b = 37
+  lr_, lf_ = rng.randn(b, 1).astype(np.float32) * 2, rng.randn(b, 1).astype(np.float32) * 2
+  for which in (0, 1):
+    rt, ft = torch.from_numpy(lr_).requires_grad_(True), torch.from_numpy(lf_).requires_grad_(True)
+    losses = ogan.get_losses(kind, torch.sigmoid(rt), torch.sigmoid(ft), rt, ft)
+    target = losses[0] if which == 0 else losses[3]
+    grads = torch.autograd.grad(target, [rt, ft], allow_unused=True)
+    rd, fd = dev(K, lr_, True), dev(K, lf_, True)
+    out = K.gan_losses(kind, rd, fd)
+    for i in range(4):
+      assert_close(out[i].cpu(), np.array([float(losses[i])], np.float32), 1e-5, "%s out%d" % (kind, i))
+    g = tape_grads(K, out[0] if which == 0 else out[3], np.ones(1, np.float32), [rd, fd])
+    for gi, ri, nm in zip(g, grads, ("real", "fake")):
+      refg = np.zeros((b, 1), np.float32) if ri is None else ri.numpy()
+      got = np.zeros((b, 1), np.float32) if gi is None else gi.cpu()
+      assert np.abs(got - refg).max() <= 1e-6 + 1e-5 * np.abs(refg).max(), (kind, which, nm)
+
+
+def test_gp_penalty(K):
+  rng = np.random.RandomState(4)
+  g = rng.randn(5, 4, 4, 3).astype(np.float32) * 0.3
+  gt = torch.from_numpy(g).requires_grad_(True)
+  slopes = torch.sqrt(0.0001 + (gt * gt).sum((1, 2, 3)))
+  pen = ((slopes - 1.0) ** 2).mean()
+  pen.backward()
+  gd = dev(K, g, True)
+  p = K.gp_penalty(gd)
+  assert_close(p.cpu(), np.array([float(pen)], np.float32), 1e-5, "penalty")
+  (dg,) = tape_grads(K, p, np.ones(1, np.float32), [gd])
+  assert_close(dg.cpu(), gt.grad.numpy(), 1e-5, "penalty grad")
+
+
+def test_adam_and_ema(K):
+  rng = np.random.RandomState(5)
+  n = 1000
+  p0, g1, g2 = rng.randn(n).astype(np.float32), rng.randn(n).astype(np.float32), rng.randn(n).astype(np.float32)
+  pt = torch.from_numpy(p0.copy())
+  opt = ogan.TFAdam({"p": pt}, 2e-4, 0.5, 0.999)
+  pd = dev(K, p0)
+  m, v = K.zeros(n), K.zeros(n)
+  ema = dev(K, p0)
+  step = torch.zeros(1, dtype=torch.int32, device="cuda")
+  ema_ref = p0.copy()
+  for i, g in enumerate((g1, g2)):
+    opt.step({"p": torch.from_numpy(g)})
+    K._call("adam_step", pd.ptr, dev(K, g * 2).ptr, m.ptr, v.ptr, n, 2e-4, 0.5, 0.999, 1e-8, 0.5, step.data_ptr(),
+            ema.ptr, 0.9, 1)
+    decay = 0.9 * float(i >= 1)
+    ema_ref = ema_ref - (ema_ref - pt.numpy()) * (1 - decay)
+  assert int(step.item()) == 2
+  assert_close(pd.cpu(), pt.numpy(), 1e-6, "adam params")
+  assert_close(ema.cpu(), ema_ref, 1e-6, "ema")
+
+
+def test_interpolate_colsum_bias(K):
+  rng = np.random.RandomState(6)
+  x, xf = rng.rand(4, 3, 3, 2).astype(np.float32), rng.rand(4, 3, 3, 2).astype(np.float32)
+  al = rng.rand(4, 1, 1, 1).astype(np.float32)
+  y = K.interpolate(dev(K, x), dev(K, xf), dev(K, al))
+  assert_close(y.cpu(), x + al * (xf - x), 1e-6, "interpolate")
+  big = rng.randn(5000, 37).astype(np.float32)
+  assert_close(K.colsum(dev(K, big)).cpu(), big.sum(0), 1e-5, "colsum")
+  assert_close(K.colsum(dev(K, big), groups=5).cpu(), big.reshape(5, 1000, 37).sum(1), 1e-5, "grouped colsum")
+
+
+def test_cov_accumulate_and_fid(K):
+  rng = np.random.RandomState(7)
+  n, d = 300, 70
+  acts = [rng.randn(n, d).astype(np.float32) + 0.3 * i for i in range(2)]
+  s = torch.zeros(d, dtype=torch.float64, device="cuda")
+  sxx = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+  for a in acts:
+    K._call("cov_accumulate", dev(K, a).ptr, n, d, s.data_ptr(), sxx.data_ptr())
+  allact = np.concatenate(acts).astype(np.float64)
+  np.testing.assert_allclose(s.cpu().numpy(), allact.sum(0), rtol=1e-12)
+  np.testing.assert_allclose(sxx.cpu().numpy(), allact.T @ allact, rtol=1e-11, atol=1e-9)
+  from compare_gan_b200.metrics import fid_score
+  real = rng.randn(400, d).astype(np.float32) * 1.5
+  mu, sigma = fid_score.moments_from_sums(s.cpu().numpy(), sxx.cpu().numpy(), 2 * n)
+  mur, sr = real.astype(np.float64).mean(0), np.cov(real.astype(np.float64), rowvar=False)
+  got = fid_score.fid_from_moments(mur, sr, mu, sigma)
+  ref = ometrics.compute_fid_from_activations(real, allact)
+  assert abs(got - ref) <= 5e-3 * abs(ref), (got, ref)
