@@ -1,15 +1,73 @@
-// Public conv entry points: choose between the exact-fp32 gather-GEMM (gemm.cu) and the tcgen05
-// tensor-core implicit GEMM (conv_tc.cu) according to the context's math mode and the shape.
+// Public conv entry points: choose between the exact-fp32 gather-GEMM (gemm.cu, math_mode 0) and the tcgen05
+// tensor-core implicit GEMM (conv_tc.cu, math_mode 1) according to the context's math mode and the shape.
 #include "common.cuh"
+
+bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols);
+int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, const float* wsrc, int taps_total,
+                 int transpose_w, int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap,
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base);
 
 int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
+  // a 1x1 kernel over a zero-inserted input leaves three of the four sub-pixel phases bias-only: not worth a tensor
+  // core launch, the gather-GEMM handles it
+  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 16 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
+      d->oh == (d->upsample ? 2 * d->h : d->h) &&
+      d->ow == (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+    int oh[16], ow[16], wt[16];
+    if (!d->upsample) {
+      int nt = 0;
+      for (int kh = 0; kh < d->kh; ++kh)
+        for (int kw = 0; kw < d->kw; ++kw) {
+          oh[nt] = kh - d->pad_t; ow[nt] = kw - d->pad_l; wt[nt] = kh * d->kw + kw; ++nt;
+        }
+      return cgan_conv_tc(ctx, x, d->n, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, bias, y,
+                          (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0);
+    }
+    // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
+    // pixel (2i+a, 2j+b) only sees the taps whose virtual input coordinate 2i+a+kh-pad is even -> real pixel i+dh.
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        int nt = 0;
+        for (int kh = 0; kh < d->kh; ++kh) {
+          int vh = a + kh - d->pad_t;
+          if (vh & 1) continue;
+          for (int kw = 0; kw < d->kw; ++kw) {
+            int vw = b + kw - d->pad_l;
+            if (vw & 1) continue;
+            oh[nt] = vh / 2; ow[nt] = vw / 2;      // exact: vh, vw even (possibly negative)
+            wt[nt] = kh * d->kw + kw; ++nt;
+          }
+        }
+        long long base = ((long long)a * d->ow + b) * d->cout;
+        if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
+        int rc = cgan_conv_tc(ctx, x, d->n, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, bias, y,
+                              (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base);
+        if (rc) return rc;
+      }
+    return CGAN_OK;
+  }
   return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y);
 }
 
 int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, float* dx) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && dy && w && dx, "null pointer");
+  if (ctx->math_mode == 1 && d->stride == 1 && !d->upsample && d->kh * d->kw <= 16 && d->oh == d->h && d->ow == d->w &&
+      cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+    // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, ih+pad_t-kh, iw+pad_l-kw, co] * w[kh,kw,ci,co]: HWIO is already
+    // [tap][row=ci][k=co], i.e. K-major for this contraction (no transpose).
+    int oh[16], ow[16], wt[16], nt = 0;
+    for (int kh = 0; kh < d->kh; ++kh)
+      for (int kw = 0; kw < d->kw; ++kw) {
+        oh[nt] = d->pad_t - kh; ow[nt] = d->pad_l - kw; wt[nt] = kh * d->kw + kw; ++nt;
+      }
+    return cgan_conv_tc(ctx, dy, d->n, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr, dx,
+                        (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
+  }
   return cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);
 }

@@ -1,0 +1,381 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a — math_mode 1.
+//
+//   out[pixel, co] = sum_{tap, ci} in[pixel + off(tap), ci] * wt[tap][co][ci]        (+ bias[co])
+//
+// * A operand (activations, NHWC fp32): one TMA 4-D tiled load per (tap, 32-channel chunk) brings a
+//   [images x rows x cols x 32ch] box = 128 pixels x 128 B straight into the 128B-swizzled K-major layout
+//   the UMMA descriptor expects; TF SAME padding is the TMA out-of-bounds zero fill (negative coordinates),
+//   so no im2col buffer and no padding pass exist.
+// * B operand (weights): pre-rounded (round-to-nearest TF32) and laid out [tap][row][k] K-major by a small
+//   prep kernel; TMA 3-D loads.
+// * The fp32 activations are rounded to nearest TF32 IN SHARED MEMORY by the (otherwise idle) epilogue
+//   warps before the tensor core reads them — tcgen05 kind::tf32 would otherwise truncate the low 13 bits,
+//   a systematic -2^-11 relative bias per product that accumulates through a 13-layer discriminator.
+// * D accumulates in TMEM (128 lanes x N fp32 columns); one elected thread issues tcgen05.mma
+//   (M=128, N<=256, K=8 per instruction); completion is tracked with tcgen05.commit -> mbarrier.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = operand
+//   rounding during the main loop, then epilogue (tcgen05.ld -> +bias -> global).
+//
+// The same kernel serves forward and input-gradient convolutions (and the four sub-pixel phases of a
+// conv over a zero-inserted 2x upsampled input): the host supplies, per tap, the input offset and the weight
+// slice, and the output pixel strides.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;          // output pixels per CTA tile (UMMA M)
+constexpr int TC_BK = 32;           // fp32 channels per k-block: 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_TAPS = 16;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
+
+struct TcParams {
+  int ntaps, kchunks;               // k-blocks = ntaps * kchunks
+  int off_h[TC_MAX_TAPS], off_w[TC_MAX_TAPS], wtap[TC_MAX_TAPS];
+  int bw, bh, bni;                  // tile box: bw*bh*bni == 128
+  int tiles_w, tiles_h;             // tiles per image row / column
+  int bn;                           // UMMA N (multiple of 32, <= 256)
+  int cout;                         // valid output channels (row length of `out` pixels)
+  long long s_n, s_h, s_w, base;    // output element strides / offset (floats)
+  float* out;
+  const float* bias;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups
+// | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16KB][B bn*128B] | barriers | tmem ptr
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.bn * TC_BK * 4;
+  const int stage_bytes = TC_A_BYTES + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
+  uint64_t* ready_bar = full_bar + TC_STAGES;
+  uint64_t* empty_bar = ready_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = p.ntaps * p.kchunks;
+
+  // tile origin
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int ow0 = tw * p.bw, oh0 = th * p.bh, n0 = tn * p.bni;
+  const int nb0 = blockIdx.y * p.bn;          // first output channel of this CTA
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < TC_STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&ready_bar[s], 4);      // one arrive per rounding warp
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // TMEM: 256 fp32 columns x 128 lanes for the accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + TC_A_BYTES;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        tma_load_4d(sa, &tm_a, &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
+        tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major A/B,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&ready_bar[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 for tf32: 32 B per step inside the 128 B swizzle row
+          umma_tf32(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== warps 2..5: round A to nearest TF32 in smem, then epilogue =====
+    const int q = threadIdx.x - 64;                  // 0..127
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* a4 = reinterpret_cast<float4*>(smem + stage * stage_bytes);
+#pragma unroll
+        for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {   // 1024 float4 / 128 threads = 8 each
+          float4 v = a4[i * 128 + q];
+          v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
+          a4[i * 128 + q] = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[stage]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // TMEM lane quarter is fixed by (warp id % 4); row of the tile = TMEM lane
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int wi = m % p.bw;
+    const int hi = (m / p.bw) % p.bh;
+    const int ni = m / (p.bw * p.bh);
+    float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
+                  (long long)(ow0 + wi) * p.s_w + nb0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr + (uint32_t)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 v;
+        v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+        if (p.bias) {
+          const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        }
+        *reinterpret_cast<float4*>(orow + c0 + j) = v;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// dst[tap][r][k] = rna_tf32(src[tap][k][r]) (transpose) or rna_tf32(src[tap][r][k])
+__global__ void wprep_kernel(float* __restrict__ dst, const float* __restrict__ src, int taps, int rows, int kdim, int transpose) {
+  long long tot = (long long)taps * rows * kdim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % kdim);
+    long long t = i / kdim;
+    int r = (int)(t % rows);
+    int tap = (int)(t / rows);
+    float v = transpose ? src[((long long)tap * kdim + k) * rows + r] : src[i];
+    dst[i] = rna_tf32(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// Geometry the tensor-core path accepts for a stride-1 convolution-like contraction.
+bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
+  if (kdim % TC_BK != 0 || ncols % 32 != 0) return false;
+  if (w > 128 || (128 % w) != 0) {
+    if (w % 128 != 0) return false;
+  }
+  int bw = w < 128 ? w : 128;
+  int bh = 128 / bw;
+  if (bh > h) bh = h;
+  if (h % bh != 0) return false;
+  int bni = 128 / (bw * bh);
+  if (bni < 1 || n % bni != 0) return false;
+  if (bw * bh * bni != 128) return false;
+  int bn = ncols <= 256 ? ncols : (ncols % 256 == 0 ? 256 : (ncols % 192 == 0 ? 192 : (ncols % 128 == 0 ? 128 : 0)));
+  return bn != 0 && bn % 32 == 0;
+}
+
+// in: [n, h, w, kdim] fp32 NHWC; wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim]
+// (transpose_w=0); taps: `ntaps` entries (off_h, off_w, weight slice).  Output pixel (n, y, x) is written at
+// out + base + n*s_n + y*s_h + x*s_w (+ channel), y < h, x < w.
+int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, const float* wsrc, int taps_total,
+                 int transpose_w, int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap,
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable%s", "cgan_conv_tc");
+  if (ntaps > TC_MAX_TAPS) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: too many taps%s", "cgan_conv_tc");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.ntaps = ntaps;
+  p.kchunks = kdim / TC_BK;
+  for (int i = 0; i < ntaps; ++i) { p.off_h[i] = off_h[i]; p.off_w[i] = off_w[i]; p.wtap[i] = wtap[i]; }
+  p.bw = w < 128 ? w : 128;
+  p.bh = 128 / p.bw; if (p.bh > h) p.bh = h;
+  p.bni = 128 / (p.bw * p.bh);
+  p.tiles_w = w / p.bw;
+  p.tiles_h = h / p.bh;
+  p.bn = ncols <= 256 ? ncols : (ncols % 256 == 0 ? 256 : (ncols % 192 == 0 ? 192 : 128));
+  p.cout = ncols;
+  p.s_n = s_n; p.s_h = s_h; p.s_w = s_w; p.base = base;
+  p.out = out;
+  p.bias = bias;
+
+  // weights -> tf32-rounded K-major [taps_total][ncols][kdim] in the workspace
+  void* ws = nullptr;
+  size_t wbytes = (size_t)taps_total * ncols * kdim * sizeof(float);
+  int rc = cgan_ws(ctx, wbytes, &ws);
+  if (rc) return rc;
+  float* wt = reinterpret_cast<float*>(ws);
+  {
+    long long tot = (long long)taps_total * ncols * kdim;
+    long long blocks = (tot + 255) / 256, cap = (long long)ctx->num_sms * 8;
+    wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, kdim, transpose_w);
+    CGAN_LAUNCHED(ctx);
+  }
+
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)kdim, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)kdim * 4, (cuuint64_t)w * kdim * 4, (cuuint64_t)h * w * kdim * 4};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ncols, (cuuint64_t)taps_total};
+    cuuint64_t strides[2] = {(cuuint64_t)kdim * 4, (cuuint64_t)ncols * kdim * 4};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.bn, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) failed%s", "cgan_conv_tc");
+  }
+  size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + (size_t)p.bn * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * (n / p.bni)), (unsigned)(ncols / p.bn));
+  conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_a, tm_b, p);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}

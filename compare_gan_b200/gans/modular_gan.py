@@ -56,7 +56,7 @@ class ModularGAN(AbstractGAN):
   def __init__(self, dataset, parameters, model_dir, deprecated_split_disc_calls=False,
                experimental_joint_gen_for_disc=False, experimental_force_graph_unroll=False, g_use_ema=False,
                ema_decay=0.9999, ema_start_step=40000, g_optimizer_fn=AdamOptimizer, d_optimizer_fn=None,
-               g_lr=0.0002, d_lr=None, conditional=False, fit_label_distribution=False):
+               g_lr=0.0002, d_lr=None, conditional=False, fit_label_distribution=False, math_mode=0):
     super(ModularGAN, self).__init__(dataset=dataset, parameters=parameters, model_dir=model_dir)
     if deprecated_split_disc_calls or fit_label_distribution:
       raise NotImplementedError("deprecated_split_disc_calls / fit_label_distribution are outside the hot path")
@@ -72,6 +72,8 @@ class ModularGAN(AbstractGAN):
       raise ValueError("Option 'conditional' selected but dataset {} does not have labels".format(
           self._dataset.name))
     self._conditional = conditional
+    # 0: exact fp32 contractions (parity mode); 1: tcgen05 kind::tf32 tensor-core convolutions (RN-rounded operands)
+    self._math_mode = math_mode
     self._architecture = parameters["architecture"]
     self._z_dim = parameters["z_dim"]
     self._lambda = parameters["lambda"]
@@ -149,6 +151,7 @@ class ModularGAN(AbstractGAN):
     creates optimizer state and the static input buffers for `batch_size` per sub-step."""
     K.lib()
     K.sync_stream()
+    K.set_math_mode(self._math_mode)
     k = self._disc_iters
     h, w, c = self._dataset.image_shape
     dev = K._RT["device"]

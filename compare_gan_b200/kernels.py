@@ -581,3 +581,9 @@ def gp_penalty(g):
   dg = empty(*g.shape)
   _call("gp_penalty", pen.ptr, dg.ptr, g.ptr, n, g.numel // n, 1.0)
   return attach("gp_penalty", pen, [g], lambda gg, needs: [_scale_by(dg, gg)])
+
+
+def set_math_mode(mode):
+  """0: exact fp32 SIMT contractions; 1: tcgen05 kind::tf32 tensor-core convolutions where the shape allows
+  (operands rounded to nearest TF32, fp32 accumulation in TMEM)."""
+  _call("ctx_set_math_mode", int(mode))

@@ -36,8 +36,8 @@ def get_losses(fn, d_real, d_fake, d_real_logits, d_fake_logits):
     lf = (d_fake ** 2).mean()
     return 0.5 * (lr + lf), lr, lf, 0.5 * ((d_fake - 1.0) ** 2).mean()
   if fn == "hinge":               # :127-148
-    lr = torch.relu(1.0 - d_real_logits).mean()
-    lf = torch.relu(1.0 + d_fake_logits).mean()
+    lr = torch.clamp(1.0 - d_real_logits, min=0).mean()
+    lf = torch.clamp(1.0 + d_fake_logits, min=0).mean()
     return lr + lf, lr, lf, -d_fake_logits.mean()
   raise ValueError(fn)
 
@@ -94,7 +94,8 @@ class GanOracle(object):
 
   def __init__(self, cfg, loss="non_saturating", penalty="no_penalty", lamba=1.0, disc_iters=1,
                g_lr=2e-4, d_lr=None, beta1=0.5, beta2=0.999, conditional=False,
-               g_use_ema=False, ema_decay=0.9999, ema_start_step=40000, z_dim=128, seed=0):
+               g_use_ema=False, ema_decay=0.9999, ema_start_step=40000, z_dim=128, seed=0,
+               dtype=torch.float32):
     self.cfg, self.loss, self.penalty = cfg, loss, penalty
     self.lamba, self.disc_iters = lamba, disc_iters
     self.g_lr, self.d_lr = g_lr, g_lr if d_lr is None else d_lr
@@ -102,7 +103,8 @@ class GanOracle(object):
     self.conditional = conditional
     self.g_use_ema, self.ema_decay, self.ema_start_step = g_use_ema, ema_decay, ema_start_step
     self.z_dim = z_dim
-    self.store = nets.VarStore(seed)
+    self.dtype = dtype
+    self.store = nets.VarStore(seed, dtype)
     self.global_step = 0        # counts G steps  (modular_gan_test.py:175-177)
     self.global_step_disc = 0   # counts D steps
     self.d_opt = self.g_opt = None
@@ -110,12 +112,12 @@ class GanOracle(object):
 
   def one_hot(self, labels):
     return torch.nn.functional.one_hot(torch.as_tensor(labels).long(),
-                                       self.cfg.num_classes).float()
+                                       self.cfg.num_classes).to(self.dtype)
 
   def build(self, batch):
     """Create all variables by one G and one D call (like TF graph construction)."""
     h, w, c = self.cfg.image_shape
-    z = torch.zeros(batch, self.z_dim)
+    z = torch.zeros(batch, self.z_dim, dtype=self.dtype)
     y = self.one_hot(np.zeros(batch, np.int64)) if self.conditional else None
     with torch.no_grad():
       x = nets.generator(self.store, self.cfg, z, y, True)
@@ -159,23 +161,27 @@ class GanOracle(object):
     gens = []
     for i in range(k + 1):
       with torch.set_grad_enabled(i == k):   # only the G-step sample needs a backward graph
-        gens.append(nets.generator(self.store, self.cfg, torch.as_tensor(z[i]), sys_[i], True))
+        gens.append(nets.generator(self.store, self.cfg, torch.as_tensor(z[i]).to(self.dtype), sys_[i], True))
     d_losses = []
     for i in range(k):                                  # _train_discriminator :471-485
       gen = gens[i].detach()
-      d_loss, _ = self.create_loss(torch.as_tensor(images[i]), gen, ys[i], sys_[i],
-                                   None if alphas is None else torch.as_tensor(alphas[i]))
+      d_loss, _ = self.create_loss(torch.as_tensor(images[i]).to(self.dtype), gen, ys[i], sys_[i],
+                                   None if alphas is None else torch.as_tensor(alphas[i]).to(self.dtype))
       params = self.store.trainable_under("discriminator")
       grads = torch.autograd.grad(d_loss, list(params.values()), allow_unused=True)
+      self.last_d_grads = OrderedDict((n, torch.zeros_like(p) if g is None else g.detach().clone())
+                                      for (n, p), g in zip(params.items(), grads))
       self.d_opt.step({n: (g if g is not None else torch.zeros_like(p))
                        for (n, p), g in zip(params.items(), grads)})
       self.global_step_disc += 1
-      d_losses.append(float(d_loss))
+      d_losses.append(float(d_loss.detach()))
     # _train_generator :487-510 — new D forward with updated D, G grads only.
-    _, g_loss = self.create_loss(torch.as_tensor(images[k]), gens[k], ys[k], sys_[k],
+    _, g_loss = self.create_loss(torch.as_tensor(images[k]).to(self.dtype), gens[k], ys[k], sys_[k],
                                  None, for_d=False)
     params = self.store.trainable_under("generator")
     grads = torch.autograd.grad(g_loss, list(params.values()), allow_unused=True)
+    self.last_g_grads = OrderedDict((n, torch.zeros_like(p) if g is None else g.detach().clone())
+                                    for (n, p), g in zip(params.items(), grads))
     self.g_opt.step({n: (g if g is not None else torch.zeros_like(p))
                      for (n, p), g in zip(params.items(), grads)})
     if self.g_use_ema:                                  # :498-508
@@ -184,4 +190,4 @@ class GanOracle(object):
         for n, p in params.items():
           self.ema[n].sub_((self.ema[n] - p) * (1.0 - decay))
     self.global_step += 1
-    return d_losses, float(g_loss)
+    return d_losses, float(g_loss.detach())

@@ -47,7 +47,8 @@ class Cfg(object):
 class VarStore(object):
   """tf.get_variable with AUTO_REUSE over a flat ordered name->tensor dict."""
 
-  def __init__(self, seed=0):
+  def __init__(self, seed=0, dtype=torch.float32):
+    self.dtype = dtype               # float64 gives the "exact" gradients used to calibrate fp32 tolerances
     self.vars = OrderedDict()
     self.trainable = OrderedDict()
     self._scope = []
@@ -86,7 +87,7 @@ class VarStore(object):
       a = T.glorot_normal_init(self.rng, shape)
     else:
       raise ValueError(kind)
-    v = torch.from_numpy(np.ascontiguousarray(a).reshape(tuple(shape)))
+    v = torch.from_numpy(np.ascontiguousarray(a).reshape(tuple(shape))).to(self.dtype)
     if trainable:
       v.requires_grad_(True)
       self.trainable[full] = v
@@ -107,7 +108,7 @@ class VarStore(object):
     with torch.no_grad():
       for k, a in state.items():
         if k in self.vars:
-          self.vars[k].copy_(torch.from_numpy(np.asarray(a, np.float32).reshape(self.vars[k].shape)))
+          self.vars[k].copy_(torch.from_numpy(np.asarray(a, np.float32).reshape(self.vars[k].shape)).to(self.dtype))
 
 
 # --------------------------------------------------------------------------- arch_ops

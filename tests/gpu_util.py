@@ -30,7 +30,7 @@ def make_pair(arch, image_shape, batch, loss="non_saturating", penalty="no_penal
               g_bn="batch_norm", g_sn=False, d_sn=False, sn_singular="left", conditional=False, num_classes=0,
               initializer="normal", use_moving_averages=True, bn_decay=0.9, bn_eps=1e-5, g_lr=2e-4, d_lr=None,
               beta1=0.5, beta2=0.999, z_dim=128, g_use_ema=False, ema_start_step=0, ch=8, extra_bindings=(),
-              project_y=False, seed=0):
+              project_y=False, seed=0, with64=False, math_mode=0):
   """Returns (engine ModularGAN built for `batch`, GanOracle) sharing config and weights."""
   from compare_gan_b200 import gin_lite as gin
   from compare_gan_b200 import datasets
@@ -59,6 +59,7 @@ def make_pair(arch, image_shape, batch, loss="non_saturating", penalty="no_penal
       "resnet_biggan.Discriminator.ch = %d" % ch,
       "resnet_biggan.Discriminator.project_y = %s" % project_y,
       "resnet_cifar.Discriminator.project_y = %s" % project_y,
+      "ModularGAN.math_mode = %d" % math_mode,
   ]
   if d_lr is not None:
     cfg.append("ModularGAN.d_lr = %r" % d_lr)
@@ -88,6 +89,12 @@ def make_pair(arch, image_shape, batch, loss="non_saturating", penalty="no_penal
   assert sorted(onames) == sorted(enames), ("variable sets differ", sorted(set(onames) ^ set(enames))[:10])
   assert [k for k in orc.store.trainable] == [k for k in eng.store.trainable], "trainable variable order differs"
   orc.store.load_numpy(state)
+  if with64:   # float64 twin of the oracle: the yard-stick for what fp32 rounding alone does to a gradient
+    orc64 = ogan.GanOracle(ocfg, loss=loss, penalty=penalty, lamba=lamba, disc_iters=disc_iters, g_lr=g_lr, d_lr=d_lr,
+                           beta1=beta1, beta2=beta2, conditional=conditional, g_use_ema=g_use_ema,
+                           ema_start_step=ema_start_step, z_dim=z_dim, dtype=torch.float64).build(batch)
+    orc64.store.load_numpy(state)
+    return eng, orc, orc64
   return eng, orc
 
 
@@ -105,16 +112,111 @@ def make_inputs(rng, k, batch, image_shape, z_dim, num_classes=0, z_normal=False
   return imgs, zs, labels, sampled, alphas
 
 
-def compare_states(eng, orc, tol, skip=()):
+class ReluSigns(object):
+  """Records the sign pattern of every ReLU / leaky-ReLU input, on the engine (K.act) and on the oracle
+  (torch.relu / tf_ops.lrelu).  A ReLU input that sits within rounding distance of zero takes a different branch in
+  two correct fp32 implementations, and that single mask flip changes the gradients discontinuously (measured: one
+  flipped element out of 262144 moves a generator gradient by 5e-3 rel-L2).  Gradient parity is therefore asserted
+  at the tight tolerance only when the masks agree, and at a loose one otherwise."""
+
+  def __init__(self):
+    self.eng, self.orc = [], []
+
+  def __enter__(self):
+    from compare_gan_b200 import kernels as K
+    from oracle import tf_ops as T
+    self._K, self._T = K, T
+    self._act, self._relu, self._lrelu = K.act, torch.relu, T.lrelu
+    rec = self
+
+    def act(x, kind, leak=0.0):
+      if kind in (K.ACT_RELU, K.ACT_LRELU):
+        rec.eng.append((x.t > 0).cpu().numpy())
+      return rec._act(x, kind, leak)
+
+    def relu(x):
+      rec.orc.append((x.detach() > 0).numpy())
+      return rec._relu(x)
+
+    def lrelu(x, leak=0.2):
+      rec.orc.append((x.detach() > 0).numpy())
+      return rec._lrelu(x, leak)
+    K.act, torch.relu, T.lrelu = act, relu, lrelu
+    return self
+
+  def __exit__(self, *a):
+    self._K.act, torch.relu, self._T.lrelu = self._act, self._relu, self._lrelu
+
+  def start_oracle(self):
+    self.orc = []
+
+  def flips(self):
+    assert len(self.eng) == len(self.orc), (len(self.eng), len(self.orc))
+    return int(sum(int((a != b).sum()) for a, b in zip(self.eng, self.orc)))
+
+
+def compare_grads(eng, orc, tol=1e-3, g_tol=None, orc64=None, flips=0):
+  """Gradients of the last D-update and of the G-update (flat buffers) vs the oracle's autograd gradients.
+  Per tensor: ||g - g_ref|| <= tol * ||g_ref|| + 1e-5 * (largest tensor-gradient norm of that network); the absolute
+  floor covers parameters whose true gradient is zero (e.g. a conv bias that feeds a BatchNorm), where both sides
+  hold only rounding noise."""
+  worst = (0.0, None)
+  if flips:
+    tol = max(tol, 5e-2)       # ReLU masks differ in `flips` elements: only a loose bound is meaningful
+  for prefix, flat, ref in (("discriminator", eng.flat_d, orc.last_d_grads), ("generator", eng.flat_g, orc.last_g_grads)):
+    if orc64 is not None:
+      # against the float64 gradients, allowing what the fp32 CPU oracle itself loses to rounding (x4)
+      ref64 = orc64.last_d_grads if prefix == "discriminator" else orc64.last_g_grads
+      g = flat["grad"].cpu()
+      gmax = max(float(v.norm()) for v in ref64.values())
+      for name, (off, n) in flat["views"].items():
+        a, b64, b32 = g[off:off + n].astype(np.float64), ref64[name].numpy().ravel(), ref[name].numpy().ravel().astype(np.float64)
+        assert np.isfinite(a).all(), name
+        err, err32 = np.linalg.norm(a - b64), np.linalg.norm(b32 - b64)
+        bound = tol * np.linalg.norm(b64) + 1e-5 * gmax + 4.0 * err32
+        assert err <= bound, "%s grad vs fp64: |err| %.3e > %.3e (|ref| %.3e, fp32-oracle err %.3e)" % (
+            name, err, bound, np.linalg.norm(b64), err32)
+        if np.linalg.norm(b64) > 1e-3 * gmax:
+          worst = max(worst, (err / np.linalg.norm(b64), name))
+      continue
+    g = flat["grad"].cpu()
+    gmax = max(float(v.norm()) for v in ref.values())
+    for name, (off, n) in flat["views"].items():
+      a, b = g[off:off + n], ref[name].numpy().ravel()
+      assert np.isfinite(a).all(), name
+      err = np.linalg.norm(a.astype(np.float64) - b)
+      bound = (tol if prefix == "discriminator" or g_tol is None else g_tol) * np.linalg.norm(b) + 1e-5 * gmax
+      assert err <= bound, "%s grad: |err| %.3e > %.3e (|ref| %.3e, net max %.3e)" % (name, err, bound, np.linalg.norm(b), gmax)
+      if np.linalg.norm(b) > 1e-3 * gmax:
+        worst = max(worst, (err / np.linalg.norm(b), name))
+  return worst
+
+
+def compare_states(eng, orc, lr, updates, frac=0.35, skip=()):
+  """Weights after Adam.  Adam's first steps move every element by ~lr*sign(g): elements whose gradient is at the
+  rounding-noise level flip sign in ANY two implementations, so the criterion is in units of the step size:
+  rms(w - w_ref) <= frac * lr * updates per tensor; tensors whose reference gradient is pure noise are skipped."""
   es = eng.state_numpy()
+  refg = {}
+  refg.update(getattr(orc, "last_d_grads", {}) or {})
+  refg.update(getattr(orc, "last_g_grads", {}) or {})
+  gmax = {"generator": 1e-30, "discriminator": 1e-30}
+  for k, v in refg.items():
+    gmax[k.split("/")[0]] = max(gmax[k.split("/")[0]], float(v.norm()))
   worst = (0.0, None)
   for k, v in orc.store.vars.items():
     if any(s in k for s in skip):
       continue
     a, b = es[k], v.detach().numpy()
-    e = rel_err(a, b)
-    if e > worst[0]:
-      worst = (e, k)
     assert np.isfinite(a).all(), k
-    assert e <= tol, "%s: rel-L2 error %.3e > %.1e" % (k, e, tol)
+    if k in orc.store.trainable:
+      if k in refg and float(refg[k].norm()) < 1e-4 * gmax[k.split("/")[0]]:
+        continue   # noise-dominated gradient (zero in exact arithmetic)
+      rms = float(np.sqrt(np.mean((a.astype(np.float64) - b) ** 2)))
+      lim = frac * lr[k.split("/")[0]] * updates[k.split("/")[0]]
+      worst = max(worst, (rms / lim, k))
+      assert rms <= lim, "%s: rms weight error %.3e > %.3e" % (k, rms, lim)
+    else:
+      e = rel_err(a, b)
+      assert e <= 2e-3, "%s (state): rel-L2 error %.3e" % (k, e)
   return worst

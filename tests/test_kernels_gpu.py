@@ -42,6 +42,11 @@ CONV_CASES = [
     (2, 8, 32, 3, 3, 1, False),
     (2, 16, 40, 136, 3, 1, False),
     (1, 6, 8, 200, 3, 1, False),
+    # the generator shapes of resnet_cifar at batch 4
+    (4, 4, 256, 256, 3, 1, True),
+    (4, 16, 256, 256, 3, 1, True),
+    (4, 32, 256, 256, 3, 1, False),
+    (4, 32, 256, 3, 3, 1, False),
 ]
 
 
@@ -122,7 +127,8 @@ def test_bmm_attention_shapes(K):
 
 
 @pytest.mark.parametrize("shape,cond", [((4, 8, 8, 16), False), ((6, 4, 4, 40), True), ((16, 70), False),
-                                        ((3, 16, 16, 3), False)])
+                                        ((3, 16, 16, 3), False), ((4, 4, 4, 256), False),
+                                        ((4, 16, 16, 256), False), ((4, 32, 32, 256), False)])
 def test_bn_train(K, shape, cond):
   rng = np.random.RandomState(len(shape) + shape[-1])
   c, n = shape[-1], shape[0]
@@ -361,3 +367,50 @@ def test_cov_accumulate_and_fid(K):
   got = fid_score.fid_from_moments(mur, sr, mu, sigma)
   ref = ometrics.compute_fid_from_activations(real, allact)
   assert abs(got - ref) <= 5e-3 * abs(ref), (got, ref)
+
+
+TC_CASES = [
+    # n, h, cin, cout, k, upsample      (shapes the tcgen05 path accepts: cin%32==0, cout%32==0, 128-pixel boxes)
+    (2, 8, 32, 32, 3, False),
+    (2, 8, 64, 128, 3, False),
+    (8, 4, 64, 64, 3, False),
+    (2, 16, 32, 256, 3, False),
+    (1, 32, 96, 192, 3, False),
+    (4, 8, 64, 64, 1, False),
+    (2, 8, 64, 32, 3, True),
+    (1, 32, 256, 256, 3, False),
+    (1, 64, 32, 96, 3, False),
+    (2, 16, 384, 512, 3, False),
+]
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,up", TC_CASES)
+def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
+  """math_mode 1: tcgen05 kind::tf32 implicit GEMM (TMA-staged, TMEM accumulators) vs the fp32 oracle.
+  Tolerance 1e-3 rel-L2 (north_star's per-tensor bound); expected ~3e-4 for RN-rounded TF32 operands."""
+  rng = np.random.RandomState(hash((n, h, cin, cout, k, up)) % 2**31)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt = torch.from_numpy(x).requires_grad_(True)
+  wt = torch.from_numpy(w).requires_grad_(True)
+  ref = T.conv2d_same(T.unpool(xt) if up else xt, wt, 1) + torch.from_numpy(b)
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  K.set_math_mode(1)
+  try:
+    xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
+    n0 = K.lib().launch_count()
+    y = K.conv2d(xd, wd, bd, stride=1, upsample=up)
+    launched = K.lib().launch_count() - n0
+    assert launched == (2 if not up else 8), "expected the tcgen05 path (weight prep + conv per phase), got %d launches" % launched
+    assert_close(y.cpu(), ref.detach().numpy(), 1e-3, "tc conv fwd")
+    gx, gw = tape_grads(K, y, gy, [xd, wd])
+    assert_close(gx.cpu(), xt.grad.numpy(), 1e-3, "tc conv dgrad")
+    assert_close(gw.cpu(), wt.grad.numpy(), 1e-3, "wgrad")
+  finally:
+    K.set_math_mode(0)
+  # unbiasedness of the rounding (truncation would shift the mean ratio by ~ -5e-4)
+  yy, rr = y.cpu().astype(np.float64).ravel(), ref.detach().numpy().astype(np.float64).ravel()
+  ratio = float((yy * rr).sum() / (rr * rr).sum())
+  assert abs(ratio - 1.0) < 1.5e-4, ratio
