@@ -159,6 +159,8 @@ def run_ours(args):
   launches_per_cycle = K.lib().launch_count() - n0
   graph = True
   try:
+    if args.eager:
+      raise RuntimeError("--eager")
     eng.capture(warmup=2)
   except Exception as e:      # e.g. NCCL not capturable in this build: run the cycle eagerly
     graph = False
@@ -208,7 +210,7 @@ def run_ours(args):
     pk = peaks()
     dom = time_dominant_kernel(wl, math_mode=mm)
     cyc_tflop = wl["gflop_per_slot_image"] * b / 1e3          # useful TFLOP per cycle per GPU
-    cpu = cpu_baseline_leg(args, sample_cycles=2)
+    cpu = cpu_baseline_leg(args, sample_cycles=2) if not args.no_cpu_baseline else None
     out = {
         "metric": "images/sec G+D step (resnet_cifar10)", "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -301,6 +303,8 @@ def main():
   ap.add_argument("--impl", default="ours")
   ap.add_argument("--workload", default="resnet_cifar10")
   ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+  ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs only)")
+  ap.add_argument("--eager", action="store_true", help="do not capture the cycle into a CUDA graph (profiling runs only)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -3,9 +3,13 @@
 #include "common.cuh"
 
 bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols);
-int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, const float* wsrc, int taps_total,
-                 int transpose_w, int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap,
+int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
+                 long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
+                 int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base);
+bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
+int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
+int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 
 int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
   if (!ctx) return CGAN_ERR_ARG;
@@ -18,13 +22,15 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
     int oh[16], ow[16], wt[16];
+    const long long zero = 0;
     if (!d->upsample) {
       int nt = 0;
       for (int kh = 0; kh < d->kh; ++kh)
         for (int kw = 0; kw < d->kw; ++kw) {
           oh[nt] = kh - d->pad_t; ow[nt] = kw - d->pad_l; wt[nt] = kh * d->kw + kw; ++nt;
         }
-      return cgan_conv_tc(ctx, x, d->n, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, bias, y,
+      return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
+                          d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
                           (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0);
     }
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
@@ -44,7 +50,8 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
         }
         long long base = ((long long)a * d->ow + b) * d->cout;
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
-        int rc = cgan_conv_tc(ctx, x, d->n, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, bias, y,
+        int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
+                              d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
                               (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base);
         if (rc) return rc;
       }
@@ -56,18 +63,48 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
 int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, float* dx) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && dy && w && dx, "null pointer");
-  if (ctx->math_mode == 1 && d->stride == 1 && !d->upsample && d->kh * d->kw <= 16 && d->oh == d->h && d->ow == d->w &&
-      cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+  const bool geom = d->oh == (d->upsample ? 2 * d->h : d->h) && d->ow == (d->upsample ? 2 * d->w : d->w);
+  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 16 && geom &&
+      cgan_tc_shape_ok(d->n, d->h, d->w, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
-    // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, ih+pad_t-kh, iw+pad_l-kw, co] * w[kh,kw,ci,co]: HWIO is already
-    // [tap][row=ci][k=co], i.e. K-major for this contraction (no transpose).
-    int oh[16], ow[16], wt[16], nt = 0;
-    for (int kh = 0; kh < d->kh; ++kh)
+    // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, oh, ow, co] * w[kh,kw,ci,co]: HWIO is already [tap][row=ci][k=co], i.e.
+    // K-major for this contraction (no transpose).
+    int oh[16], ow[16], wt[16], am[16], nt = 0;
+    long long voff[4] = {0, 0, 0, 0};
+    if (!d->upsample) {
+      // oh = ih + pad_t - kh
+      for (int kh = 0; kh < d->kh; ++kh)
+        for (int kw = 0; kw < d->kw; ++kw) {
+          oh[nt] = d->pad_t - kh; ow[nt] = d->pad_l - kw; wt[nt] = kh * d->kw + kw; am[nt] = 0; ++nt;
+        }
+      return cgan_conv_tc(ctx, dy, 1, voff, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
+                          d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
+                          (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
+    }
+    // zero-inserted input: the real pixel ih sits at virtual row 2*ih; tap kh reaches output row oh = 2*ih + pad_t - kh,
+    // i.e. sub-pixel phase a = (pad_t - kh) & 1 of dy at phase-row ih + (pad_t - kh - a)/2.  The four phases are four
+    // strided TMA views of dy.
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) voff[a * 2 + b] = ((long long)a * d->ow + b) * d->cout;
+    for (int kh = 0; kh < d->kh; ++kh) {
+      int th = d->pad_t - kh, a = th & 1;
       for (int kw = 0; kw < d->kw; ++kw) {
-        oh[nt] = d->pad_t - kh; ow[nt] = d->pad_l - kw; wt[nt] = kh * d->kw + kw; ++nt;
+        int tw = d->pad_l - kw, b = tw & 1;
+        oh[nt] = (th - a) / 2; ow[nt] = (tw - b) / 2; wt[nt] = kh * d->kw + kw; am[nt] = a * 2 + b; ++nt;
       }
-    return cgan_conv_tc(ctx, dy, d->n, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr, dx,
+    }
+    return cgan_conv_tc(ctx, dy, 4, voff, 2ll * d->cout, 2ll * d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
+                        d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
                         (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
   }
   return cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);
+}
+
+int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, d && x && dy && dw, "null pointer");
+  if (ctx->math_mode == 1 && cgan_wgrad_tc_ok(d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0)
+    return cgan_wgrad_tc(ctx, d, x, dy, dw);
+  return cgan_conv2d_wgrad_simt(ctx, d, x, dy, dw);
 }

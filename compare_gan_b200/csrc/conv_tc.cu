@@ -19,11 +19,11 @@
 // The same kernel serves forward and input-gradient convolutions (and the four sub-pixel phases of a
 // conv over a zero-inserted 2x upsampled input): the host supplies, per tap, the input offset and the weight
 // slice, and the output pixel strides.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+
+using namespace tc;
 
 constexpr int TC_BM = 128;          // output pixels per CTA tile (UMMA M)
 constexpr int TC_BK = 32;           // fp32 channels per k-block: 128 B = one swizzle row
@@ -34,7 +34,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
 
 struct TcParams {
   int ntaps, kchunks;               // k-blocks = ntaps * kchunks
-  int off_h[TC_MAX_TAPS], off_w[TC_MAX_TAPS], wtap[TC_MAX_TAPS];
+  int off_h[TC_MAX_TAPS], off_w[TC_MAX_TAPS], wtap[TC_MAX_TAPS], amap[TC_MAX_TAPS];   // amap: which input view
   int bw, bh, bni;                  // tile box: bw*bh*bni == 128
   int tiles_w, tiles_h;             // tiles per image row / column
   int bn;                           // UMMA N (multiple of 32, <= 256)
@@ -43,41 +43,6 @@ struct TcParams {
   float* out;
   const float* bias;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(addr), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups
@@ -92,26 +57,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// up to four views of the input tensor (the sub-pixel phases of a 2x-upsampled gradient); plain convs use view 0
+struct AMaps { CUtensorMap m[4]; };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16KB][B bn*128B] | barriers | tmem ptr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -135,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int nb0 = blockIdx.y * p.bn;          // first output channel of this CTA
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_as.m[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
   }
   if (warp == 1) {
@@ -169,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + TC_A_BYTES;
         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-        tma_load_4d(sa, &tm_a, &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
+        tma_load_4d(sa, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
         tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap]);
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -275,22 +225,6 @@ __global__ void wprep_kernel(float* __restrict__ dst, const float* __restrict__ 
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 }  // namespace
 
 // Geometry the tensor-core path accepts for a stride-1 convolution-like contraction.
@@ -310,20 +244,26 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
   return bn != 0 && bn % 32 == 0;
 }
 
-// in: [n, h, w, kdim] fp32 NHWC; wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim]
-// (transpose_w=0); taps: `ntaps` entries (off_h, off_w, weight slice).  Output pixel (n, y, x) is written at
-// out + base + n*s_n + y*s_h + x*s_w (+ channel), y < h, x < w.
-int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, const float* wsrc, int taps_total,
-                 int transpose_w, int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap,
+// in: fp32 NHWC activations seen through `nviews` views of logical size [n, h, w, kdim] (view v starts at
+// in + view_off[v], pixel strides sw/sh/sn floats) — one view for ordinary convs, the four sub-pixel phases of a
+// 2x-upsampled gradient for the input gradient of a conv over a zero-inserted input.
+// wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim] (transpose_w=0).
+// taps: `ntaps` entries (off_h, off_w, weight slice, view).  Output pixel (n, y, x), y < h, x < w, is written at
+// out + base + n*s_n + y*s_h + x*s_w (+ channel).
+int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
+                 long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
+                 int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable%s", "cgan_conv_tc");
-  if (ntaps > TC_MAX_TAPS) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: too many taps%s", "cgan_conv_tc");
+  if (ntaps > TC_MAX_TAPS || nviews > 4) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: too many taps/views%s", "cgan_conv_tc");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.ntaps = ntaps;
   p.kchunks = kdim / TC_BK;
-  for (int i = 0; i < ntaps; ++i) { p.off_h[i] = off_h[i]; p.off_w[i] = off_w[i]; p.wtap[i] = wtap[i]; }
+  for (int i = 0; i < ntaps; ++i) {
+    p.off_h[i] = off_h[i]; p.off_w[i] = off_w[i]; p.wtap[i] = wtap[i]; p.amap[i] = amap ? amap[i] : 0;
+  }
   p.bw = w < 128 ? w : 128;
   p.bh = 128 / p.bw; if (p.bh > h) p.bh = h;
   p.bni = 128 / (p.bw * p.bh);
@@ -348,16 +288,13 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, 
     CGAN_LAUNCHED(ctx);
   }
 
-  CUtensorMap tm_a, tm_b;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)kdim, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)kdim * 4, (cuuint64_t)w * kdim * 4, (cuuint64_t)h * w * kdim * 4};
-    cuuint32_t box[4] = {TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
+  AMaps tm_as;
+  CUtensorMap tm_b;
+  memset(&tm_as, 0, sizeof(tm_as));
+  for (int v = 0; v < 4; ++v) {
+    int vv = v < nviews ? v : 0;
+    if (!make_act_map(&tm_as.m[v], in + view_off[vv], kdim, w, h, n, in_sw, in_sh, in_sn, p.bw, p.bh, p.bni))
+      return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ncols, (cuuint64_t)taps_total};
@@ -375,7 +312,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int n, int h, int w, int kdim, 
     attr_set = true;
   }
   dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * (n / p.bni)), (unsigned)(ncols / p.bn));
-  conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_a, tm_b, p);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_as, tm_b, p);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

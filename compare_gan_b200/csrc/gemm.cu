@@ -393,7 +393,7 @@ int cgan_conv2d_dgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
   return launch<M_DGRAD, true, true>(ctx, p, 1);
 }
 
-int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
+int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
   if (!ctx) return CGAN_ERR_ARG;
   int rc = check_desc(ctx, d);
   if (rc) return rc;

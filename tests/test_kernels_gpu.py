@@ -381,6 +381,11 @@ TC_CASES = [
     (1, 32, 256, 256, 3, False),
     (1, 64, 32, 96, 3, False),
     (2, 16, 384, 512, 3, False),
+    (2, 8, 128, 64, 3, False),
+    (2, 8, 128, 128, 3, True),
+    (8, 4, 256, 96, 3, True),
+    (4, 8, 128, 32, 1, False),
+    (1, 64, 128, 128, 3, False),
 ]
 
 
