@@ -10,6 +10,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
+bool cgan_wgrad_thin_ok(const cgan_conv_desc* d);
+int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 
 int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
   if (!ctx) return CGAN_ERR_ARG;
@@ -20,7 +22,7 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
       d->oh == (d->upsample ? 2 * d->h : d->h) &&
       d->ow == (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0)) {
     int oh[16], ow[16], wt[16];
     const long long zero = 0;
     if (!d->upsample) {
@@ -103,6 +105,8 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
 int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && dy && dw, "null pointer");
+  if (d->n > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0 && cgan_wgrad_thin_ok(d))
+    return cgan_wgrad_thin(ctx, d, x, dy, dw);      // exact fp32 streaming kernels for 3-channel image-side layers
   if (ctx->math_mode == 1 && cgan_wgrad_tc_ok(d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0)
     return cgan_wgrad_tc(ctx, d, x, dy, dw);

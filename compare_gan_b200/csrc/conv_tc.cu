@@ -191,16 +191,27 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr + (uint32_t)c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v;
-        v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
-        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-        if (p.bias) {
-          const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
-          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+          v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+          if (p.bias) {
+            const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          *reinterpret_cast<float4*>(orow + c0 + j) = v;
         }
-        *reinterpret_cast<float4*>(orow + c0 + j) = v;
+      } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nb0 + c0 + j < p.cout) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias) v += p.bias[nb0 + c0 + j];
+            orow[c0 + j] = v;
+          }
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -212,24 +223,35 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   }
 }
 
-// dst[tap][r][k] = rna_tf32(src[tap][k][r]) (transpose) or rna_tf32(src[tap][r][k])
-__global__ void wprep_kernel(float* __restrict__ dst, const float* __restrict__ src, int taps, int rows, int kdim, int transpose) {
-  long long tot = (long long)taps * rows * kdim;
+// dst[tap][r][k] (r < rows_pad) = rna_tf32(src[tap][k][r]) (transpose) or rna_tf32(src[tap][r][k]); rows >= `rows` are 0
+__global__ void wprep_kernel(float* __restrict__ dst, const float* __restrict__ src, int taps, int rows, int rows_pad,
+                             int kdim, int transpose) {
+  long long tot = (long long)taps * rows_pad * kdim;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
     int k = (int)(i % kdim);
     long long t = i / kdim;
-    int r = (int)(t % rows);
-    int tap = (int)(t / rows);
-    float v = transpose ? src[((long long)tap * kdim + k) * rows + r] : src[i];
+    int r = (int)(t % rows_pad);
+    int tap = (int)(t / rows_pad);
+    float v = 0.f;
+    if (r < rows) v = transpose ? src[((long long)tap * kdim + k) * rows + r] : src[((long long)tap * rows + r) * kdim + k];
     dst[i] = rna_tf32(v);
   }
+}
+
+inline int tc_pick_bn(int ncols_pad) {
+  if (ncols_pad <= 256) return ncols_pad;
+  if (ncols_pad % 256 == 0) return 256;
+  if (ncols_pad % 192 == 0) return 192;
+  if (ncols_pad % 128 == 0) return 128;
+  return 0;
 }
 
 }  // namespace
 
 // Geometry the tensor-core path accepts for a stride-1 convolution-like contraction.
 bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
-  if (kdim % TC_BK != 0 || ncols % 32 != 0) return false;
+  if (kdim % TC_BK != 0 || ncols < 1) return false;
+  if (ncols > 256 && ncols % 32 != 0) return false;      // small column counts are zero-padded to a multiple of 32
   if (w > 128 || (128 % w) != 0) {
     if (w % 128 != 0) return false;
   }
@@ -240,7 +262,7 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
   int bni = 128 / (bw * bh);
   if (bni < 1 || n % bni != 0) return false;
   if (bw * bh * bni != 128) return false;
-  int bn = ncols <= 256 ? ncols : (ncols % 256 == 0 ? 256 : (ncols % 192 == 0 ? 192 : (ncols % 128 == 0 ? 128 : 0)));
+  int bn = tc_pick_bn((ncols + 31) / 32 * 32);
   return bn != 0 && bn % 32 == 0;
 }
 
@@ -269,7 +291,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   p.bni = 128 / (p.bw * p.bh);
   p.tiles_w = w / p.bw;
   p.tiles_h = h / p.bh;
-  p.bn = ncols <= 256 ? ncols : (ncols % 256 == 0 ? 256 : (ncols % 192 == 0 ? 192 : 128));
+  const int ncols_pad = (ncols + 31) / 32 * 32;
+  p.bn = tc_pick_bn(ncols_pad);
   p.cout = ncols;
   p.s_n = s_n; p.s_h = s_h; p.s_w = s_w; p.base = base;
   p.out = out;
@@ -277,14 +300,15 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
 
   // weights -> tf32-rounded K-major [taps_total][ncols][kdim] in the workspace
   void* ws = nullptr;
-  size_t wbytes = (size_t)taps_total * ncols * kdim * sizeof(float);
+  size_t wbytes = (size_t)taps_total * ncols_pad * kdim * sizeof(float);
   int rc = cgan_ws(ctx, wbytes, &ws);
   if (rc) return rc;
   float* wt = reinterpret_cast<float*>(ws);
   {
-    long long tot = (long long)taps_total * ncols * kdim;
+    long long tot = (long long)taps_total * ncols_pad * kdim;
     long long blocks = (tot + 255) / 256, cap = (long long)ctx->num_sms * 8;
-    wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, kdim, transpose_w);
+    wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, ncols_pad, kdim,
+                                                                               transpose_w);
     CGAN_LAUNCHED(ctx);
   }
 
@@ -297,8 +321,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
       return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ncols, (cuuint64_t)taps_total};
-    cuuint64_t strides[2] = {(cuuint64_t)kdim * 4, (cuuint64_t)ncols * kdim * 4};
+    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ncols_pad, (cuuint64_t)taps_total};
+    cuuint64_t strides[2] = {(cuuint64_t)kdim * 4, (cuuint64_t)ncols_pad * kdim * 4};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.bn, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -311,7 +335,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
     CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * (n / p.bni)), (unsigned)(ncols / p.bn));
+  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * (n / p.bni)), (unsigned)(ncols_pad / p.bn));
   conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_as, tm_b, p);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;

@@ -1,0 +1,176 @@
+// Filter gradients of "thin" convolutions — the image-side layers of every architecture (3 input channels in the
+// discriminator's first block, 3 output channels in the generator's last conv).  As GEMMs they are 27 x Cout x pixels
+// or (9*Cin) x 3 x pixels: far too skinny for a 128-wide tensor-core tile and purely HBM/L2-bound, so they get
+// streaming fp32 kernels: each CTA walks a contiguous range of output pixels, keeps the whole dW tile in registers,
+// reads dY (resp. X) exactly once with coalesced 128-byte rows, and writes one partial tile; partials are summed in a
+// fixed order (deterministic).  Replaces TF Conv2DBackpropFilter for these shapes (arch_ops.py:568 autodiff).
+#include "common.cuh"
+
+namespace {
+
+constexpr int THIN_MAX_M = 36;    // taps * cin  (3x3x4)
+constexpr int THIN_PB = 32;       // pixels staged per batch
+
+struct ThinParams {
+  cgan_conv_desc d;
+  int vh, vw;
+  long long npix;                 // n * oh * ow
+  long long pix_per_block;
+};
+
+__device__ __forceinline__ long long thin_in_offset(const ThinParams& p, int n, int oh, int ow, int kh, int kw) {
+  const cgan_conv_desc& d = p.d;
+  int vh = oh * d.stride + kh - d.pad_t, vw = ow * d.stride + kw - d.pad_l;
+  if (vh < 0 || vw < 0 || vh >= p.vh || vw >= p.vw) return -1;
+  if (d.upsample) {
+    if ((vh | vw) & 1) return -1;
+    vh >>= 1; vw >>= 1;
+  }
+  return (((long long)n * d.h + vh) * d.w + vw) * d.cin;
+}
+
+// Cin <= 4: thread = output channel; acc[m] over m = (tap, ci)
+template <int M>
+__global__ void wgrad_thin_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial,
+                                      ThinParams p) {
+  __shared__ float xs[THIN_PB][M + 1];
+  const cgan_conv_desc& d = p.d;
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+  const long long p1 = min(p.npix, p0 + p.pix_per_block);
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+  for (long long pb = p0; pb < p1; pb += THIN_PB) {
+    const int nb = (int)min((long long)THIN_PB, p1 - pb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * M; e += blockDim.x) {
+      int pi = e / M, m = e % M;
+      long long pix = pb + pi;
+      int ow = (int)(pix % d.ow);
+      long long t = pix / d.ow;
+      int oh = (int)(t % d.oh);
+      int n = (int)(t / d.oh);
+      int ci = m % d.cin, tap = m / d.cin;
+      long long off = thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw);
+      xs[pi][m] = off < 0 ? 0.f : x[off + ci];
+    }
+    __syncthreads();
+    if (co < d.cout) {
+      for (int pi = 0; pi < nb; ++pi) {
+        float g = dy[(pb + pi) * d.cout + co];
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m] = fmaf(xs[pi][m], g, acc[m]);
+      }
+    }
+  }
+  if (co < d.cout) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) partial[((long long)blockIdx.x * M + m) * d.cout + co] = acc[m];
+  }
+}
+
+// Cout <= 4: thread = input channel; acc[tap][co]
+template <int TAPS, int CO>
+__global__ void wgrad_thin_cout_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial,
+                                       ThinParams p) {
+  __shared__ float gs[THIN_PB][CO];
+  __shared__ long long offs[THIN_PB][TAPS];
+  const cgan_conv_desc& d = p.d;
+  const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+  const long long p1 = min(p.npix, p0 + p.pix_per_block);
+  float acc[TAPS][CO];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[t][c] = 0.f;
+  for (long long pb = p0; pb < p1; pb += THIN_PB) {
+    const int nb = (int)min((long long)THIN_PB, p1 - pb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * TAPS; e += blockDim.x) {
+      int pi = e / TAPS, tap = e % TAPS;
+      long long pix = pb + pi;
+      int ow = (int)(pix % d.ow);
+      long long t = pix / d.ow;
+      int oh = (int)(t % d.oh);
+      int n = (int)(t / d.oh);
+      offs[pi][tap] = thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw);
+    }
+    for (int e = threadIdx.x; e < nb * CO; e += blockDim.x) gs[e / CO][e % CO] = dy[(pb + e / CO) * d.cout + e % CO];
+    __syncthreads();
+    if (ci < d.cin) {
+      for (int pi = 0; pi < nb; ++pi) {
+        float g[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[c] = gs[pi][c];
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+          long long off = offs[pi][t];
+          float xv = off < 0 ? 0.f : x[off + ci];
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[t][c] = fmaf(xv, g[c], acc[t][c]);
+        }
+      }
+    }
+  }
+  if (ci < d.cin) {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int c = 0; c < CO; ++c)
+        partial[(((long long)blockIdx.x * TAPS + t) * d.cin + ci) * CO + c] = acc[t][c];
+  }
+}
+
+__global__ void thin_reduce_kernel(float* __restrict__ out, const float* __restrict__ part, long long n, int blocks) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[(long long)b * n + i];
+  out[i] = s;
+}
+
+}  // namespace
+
+bool cgan_wgrad_thin_ok(const cgan_conv_desc* d) {
+  int m = d->kh * d->kw * d->cin;
+  if (d->cin <= 4 && (m == 9 || m == 18 || m == 27 || m == 36) && d->kh == 3 && d->kw == 3) return true;
+  if (d->cout <= 4 && d->cout == 3 && d->kh == 3 && d->kw == 3) return true;
+  return false;
+}
+
+int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
+  ThinParams p;
+  p.d = *d;
+  p.vh = d->upsample ? 2 * d->h : d->h;
+  p.vw = d->upsample ? 2 * d->w : d->w;
+  p.npix = (long long)d->n * d->oh * d->ow;
+  long long want_blocks = 4ll * ctx->num_sms;
+  long long ppb = (p.npix + want_blocks - 1) / want_blocks;
+  ppb = (ppb + THIN_PB - 1) / THIN_PB * THIN_PB;
+  p.pix_per_block = ppb;
+  int blocks = (int)((p.npix + ppb - 1) / ppb);
+  long long wn = (long long)d->kh * d->kw * d->cin * d->cout;
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, (size_t)blocks * wn * sizeof(float), &ws);
+  if (rc) return rc;
+  float* partial = reinterpret_cast<float*>(ws);
+  if (d->cin <= 4) {
+    int threads = d->cout >= 256 ? 256 : ((d->cout + 31) / 32 * 32);
+    dim3 grid(blocks, (d->cout + threads - 1) / threads);
+    int m = d->kh * d->kw * d->cin;
+    if (m == 9) wgrad_thin_cin_kernel<9><<<grid, threads, 0, ctx->stream>>>(x, dy, partial, p);
+    else if (m == 18) wgrad_thin_cin_kernel<18><<<grid, threads, 0, ctx->stream>>>(x, dy, partial, p);
+    else if (m == 27) wgrad_thin_cin_kernel<27><<<grid, threads, 0, ctx->stream>>>(x, dy, partial, p);
+    else wgrad_thin_cin_kernel<36><<<grid, threads, 0, ctx->stream>>>(x, dy, partial, p);
+  } else {
+    int threads = d->cin >= 256 ? 256 : ((d->cin + 31) / 32 * 32);
+    dim3 grid(blocks, (d->cin + threads - 1) / threads);
+    wgrad_thin_cout_kernel<9, 3><<<grid, threads, 0, ctx->stream>>>(x, dy, partial, p);
+  }
+  CGAN_LAUNCHED(ctx);
+  thin_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, blocks);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}

@@ -249,7 +249,8 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
     }
   p.ntaps = nt;
   long long tiles = (long long)p.ci_tiles * p.co_tiles * nt;
-  int splits = (int)((2ll * ctx->num_sms + tiles - 1) / tiles);
+  // two CTAs' worth of work per SM, rounded DOWN so the grid never spills a few CTAs into an extra wave
+  int splits = (int)((2ll * ctx->num_sms) / tiles);
   int max_splits = p.kblocks / 8 > 0 ? p.kblocks / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -386,6 +386,8 @@ TC_CASES = [
     (8, 4, 256, 96, 3, True),
     (4, 8, 128, 32, 1, False),
     (1, 64, 128, 128, 3, False),
+    (2, 16, 64, 3, 3, False),      # thin image conv: Cout=3 zero-padded to a 32-column tile
+    (2, 8, 32, 20, 1, False),
 ]
 
 
