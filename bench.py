@@ -228,7 +228,10 @@ def run_ours(args):
         "gpu_launches": launches_per_cycle * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": dom["tflops"] / pk["bf16_tflops"], "traffic": None,
+                     "frac": dom["tflops"] / pk["bf16_tflops"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full`
+                     # capture (profiles/r1_ncu_full_tc_kernels.csv): 271 MB + 220 MB vs 2 x 268 MB algorithmic
+                     "traffic": 4.91e8 if (mm and b == 256) else None,
                      "kernel": dom["kernel"], "kernel_ms": dom["ms"],
                      "peak_kind": "%s dense bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 tensor peak is nominally half of it"
                                   % pk["source"],
@@ -238,9 +241,12 @@ def run_ours(args):
         "losses": {"d": d_losses, "g": g_loss},
     }
     print(json.dumps(out))
+    sys.stdout.flush()
   if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+    # leave without tearing NCCL down: destroy_process_group() can block behind captured graphs holding the communicator
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
   return out
 
 

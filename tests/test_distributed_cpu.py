@@ -1,0 +1,68 @@
+"""world_size-2 `gloo` tests (CPU) of the data-parallel exchange logic: the only collectives on the path are
+all-reduce(sum) of a flat gradient buffer and of BN `[mean, mean-of-squares]`."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _worker(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from compare_gan_b200.tape import DT
+  from compare_gan_b200.tpu import tpu_ops
+  out = {}
+  assert tpu_ops.num_replicas() == world
+  # (1) reference tpu/tpu_ops_test.py:79-83: each replica feeds one vector, all get the mean
+  inp = np.array(G["cross_replica_mean"]["inputs"], np.float32)
+  x = DT(torch.from_numpy(inp[rank].copy()))
+  tpu_ops.cross_replica_mean(x)
+  out["mean"] = x.t.numpy().copy()
+  # (2) reference arch_ops_tpu_test.py:112-133: sync-BN over 2 replicas == single-device BN on the whole batch
+  xb = np.array(G["bn_input"]["x"], np.float32)          # [4,2,1,3]; replica r holds images 2r, 2r+1
+  shard = torch.from_numpy(xb[2 * rank:2 * rank + 2])
+  local = torch.cat([shard.mean(dim=(0, 1, 2)), (shard * shard).mean(dim=(0, 1, 2))]).contiguous()
+  mean, var = tpu_ops.cross_replica_moments_from_local(DT(local))
+  y = (shard - mean) * torch.rsqrt(var + 1e-3)
+  out["bn"] = y.numpy().copy()
+  # (3) gradient exchange: flat buffer all-reduce(sum) then 1/world inside the optimizer == mean of per-replica grads
+  g = DT(torch.full((1000,), float(rank + 1)))
+  tpu_ops.cross_replica_sum_(g)
+  out["grad"] = float(g.t[0]) / world
+  q.put((rank, out))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_replica_exchange_logic():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = dict(q.get(timeout=120) for _ in range(2))
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  exp_bn = np.array(G["bn_expected"]["y"], np.float32)
+  for r in range(2):
+    np.testing.assert_allclose(res[r]["mean"], G["cross_replica_mean"]["expected"], atol=1e-6)
+    np.testing.assert_allclose(res[r]["bn"], exp_bn[2 * r:2 * r + 2], rtol=1e-5, atol=1e-5)
+    assert abs(res[r]["grad"] - 1.5) < 1e-6
