@@ -221,6 +221,31 @@ __global__ void maxpool2_bwd_kernel(float* __restrict__ dx, const float* __restr
     for (int k = 0; k < 4; ++k) dx[base + offs[k]] = (k == best) ? dy[i] : 0.f;
   }
 }
+__global__ void pool2d_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int h, int w, int c, int k,
+                                  int stride, int pad_t, int pad_l, int oh, int ow, int mode) {
+  long long tot = (long long)n * oh * ow * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    float acc = mode == 0 ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int dy = 0; dy < k; ++dy) {
+      int iy = oy * stride + dy - pad_t;
+      if (iy < 0 || iy >= h) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        int ix = ox * stride + dx - pad_l;
+        if (ix < 0 || ix >= w) continue;
+        float v = x[((b * h + iy) * w + ix) * c + ch];
+        acc = mode == 0 ? fmaxf(acc, v) : acc + v;
+        ++cnt;
+      }
+    }
+    y[i] = mode == 0 ? acc : acc / (float)max(cnt, 1);
+  }
+}
 // y[n,c] = scale * sum_hw x[n,hw,c]: one thread per (n,c) strides over hw; consecutive threads -> consecutive c
 __global__ void globalpool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int hw, int c, float scale) {
   long long tot = (long long)n * c;
@@ -473,6 +498,14 @@ int cgan_maxpool2_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int
 int cgan_maxpool2_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* x, int n, int h, int w, int c) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && x, "null pointer"); POOL_ARGS_OK(ctx);
   maxpool2_bwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(dx, dy, x, n, h, w, c);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_pool2d_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w, int c, int k, int stride, int pad_t,
+                    int pad_l, int oh, int ow, int mode) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n > 0 && h > 0 && w > 0 && c > 0 && k > 0 && stride > 0 && oh > 0 && ow > 0, "bad argument");
+  CGAN_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (max) or 1 (avg)");
+  pool2d_fwd_kernel<<<ew_grid(ctx, (long long)n * oh * ow * c), 256, 0, ctx->stream>>>(y, x, n, h, w, c, k, stride, pad_t, pad_l,
+                                                                                    oh, ow, mode);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_globalpool_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int hw, int c, float scale) {

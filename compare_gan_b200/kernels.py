@@ -160,10 +160,16 @@ def same_pad(n, k, s):
   return out, total // 2
 
 
-def conv_desc(n, h, w, cin, cout, kh, kw, stride, upsample):
+def conv_desc(n, h, w, cin, cout, kh, kw, stride, upsample, padding="SAME"):
   vh, vw = (2 * h, 2 * w) if upsample else (h, w)
-  oh, pt = same_pad(vh, kh, stride)
-  ow, pl = same_pad(vw, kw, stride)
+  if padding == "SAME":
+    oh, pt = same_pad(vh, kh, stride)
+    ow, pl = same_pad(vw, kw, stride)
+  elif padding == "VALID":
+    oh, pt = (vh - kh) // stride + 1, 0
+    ow, pl = (vw - kw) // stride + 1, 0
+  else:
+    raise ValueError("padding must be SAME or VALID")
   return _lib.ConvDesc(n, h, w, cin, cout, kh, kw, stride, 1 if upsample else 0, oh, ow, pt, pl)
 
 
@@ -173,14 +179,14 @@ def _conv_fwd_raw(d, x, w, bias):
   return y
 
 
-def conv2d(x, w, bias=None, stride=1, upsample=False):
+def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME"):
   """tf.nn.conv2d(..., "SAME") + bias (arch_ops.py:568-572); `upsample` fuses resnet_ops.unpool
   (resnet_ops.py:35-56, 122-123) without materialising the zeros.  w is HWIO."""
   n, h, ww, cin = x.shape
   kh, kw, wcin, cout = w.shape
   if wcin != cin:
     raise ValueError("conv2d: kernel expects %d input channels, got %d" % (wcin, cin))
-  d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, upsample)
+  d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, upsample, padding)
   y = _conv_fwd_raw(d, x, w, bias)
 
   def vjp(g, needs):
@@ -356,6 +362,40 @@ def maxpool2(x):
     _call("maxpool2_bwd", dx.ptr, g.ptr, x.ptr, n, h, w, c)
     return [dx]
   return attach("maxpool2", y, [x], vjp)
+
+
+def pool2d(x, k, stride, padding, mode):
+  """tf.nn.max_pool / tf.nn.avg_pool (TF-GAN's Inception graph); inference only."""
+  n, h, w, c = x.shape
+  if padding == "SAME":
+    oh, pt = same_pad(h, k, stride)
+    ow, pl = same_pad(w, k, stride)
+  else:
+    oh, pt, ow, pl = (h - k) // stride + 1, 0, (w - k) // stride + 1, 0
+  y = empty(n, oh, ow, c)
+  _call("pool2d_fwd", y.ptr, x.ptr, n, h, w, c, k, stride, pt, pl, oh, ow, 0 if mode == "max" else 1)
+  return y
+
+
+def concat_channels(xs):
+  """tf.concat(axis=3) of NHWC tensors (Inception mixed blocks); inference only."""
+  n, h, w = xs[0].shape[:3]
+  ctot = sum(t.shape[3] for t in xs)
+  y = empty(n, h, w, ctot)
+  off = 0
+  for t in xs:
+    c = t.shape[3]
+    _call("copy2d", y.ptr, ctot, off, t.ptr, c, 0, n * h * w, c)
+    off += c
+  return y
+
+
+def resize_bilinear(x, oh, ow, inception_scale=False):
+  """tf.image.resize_bilinear (align_corners=False); with inception_scale also (v*255-128)/128 (eval_utils.py:157-175)."""
+  n, h, w, c = x.shape
+  y = empty(n, oh, ow, c)
+  _call("resize_bilinear", y.ptr, x.ptr, n, h, w, c, oh, ow, 1 if inception_scale else 0)
+  return y
 
 
 def globalpool(x, mean):

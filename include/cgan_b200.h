@@ -134,6 +134,11 @@ int cgan_avgpool2_bwd(cgan_ctx*, float* dx, const float* dy, int n, int h, int w
 /* 2x2 stride-2 max pool (arch_ops.py:741,750) and backward (first-max wins, as TF MaxPoolGrad) */
 int cgan_maxpool2_fwd(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c);
 int cgan_maxpool2_bwd(cgan_ctx*, float* dx, const float* dy, const float* x, int n, int h, int w, int c);
+/* generic k x k pooling, TF semantics: mode 0 = max, 1 = average that EXCLUDES padded cells from the divisor (tf.nn.avg_pool
+ * "SAME"); pad_t/pad_l = leading padding (0 for "VALID"); oh/ow given by the caller.  Inception-v3 feature extractor
+ * (tfgan.eval.run_inception, eval_utils.py:165-175). */
+int cgan_pool2d_fwd(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c, int k, int stride, int pad_t, int pad_l,
+                    int oh, int ow, int mode);
 /* global pool over h*w: out[n,c] = scale * sum_hw x (mean: resnet_cifar.py:156; sum: resnet_biggan.py:405) */
 int cgan_globalpool_fwd(cgan_ctx*, float* y, const float* x, int n, int hw, int c, float scale);
 int cgan_globalpool_bwd(cgan_ctx*, float* dx, const float* dy, int n, int hw, int c, float scale);

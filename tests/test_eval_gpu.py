@@ -1,0 +1,85 @@
+"""Evaluation path parity: TF-style bilinear resize, Inception-v3 features, and the FID / IS / KID numbers of a tiny
+generator, engine (CUDA) vs the CPU oracle with the SAME synthetic Inception weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import inception as oinc
+from oracle import metrics as ometrics
+from tests.gpu_util import assert_close, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+  from compare_gan_b200 import kernels
+  kernels.init(0)
+  return kernels
+
+
+def test_resize_bilinear_matches_tf_semantics(K):
+  rng = np.random.RandomState(0)
+  for (h, oh) in [(32, 299), (128, 299), (5, 7), (300, 299)]:
+    x = rng.rand(2, h, h, 3).astype(np.float32)
+    ref = oinc.resize_bilinear_tf(torch.from_numpy(x), oh, oh).numpy()
+    got = K.resize_bilinear(K.from_numpy(x), oh, oh).cpu()
+    assert_close(got, ref, 1e-5, "resize %d->%d" % (h, oh))
+  x = rng.rand(2, 32, 32, 3).astype(np.float32)
+  got = K.resize_bilinear(K.from_numpy(x), 299, 299, inception_scale=True).cpu()
+  assert_close(got, oinc.preprocess(x).numpy(), 1e-5, "inception preprocessing")
+
+
+def test_pool2d_tf_semantics(K):
+  rng = np.random.RandomState(1)
+  x = rng.randn(2, 9, 9, 5).astype(np.float32)
+  for mode, k, s, pad in [("max", 3, 2, "VALID"), ("avg", 3, 1, "SAME"), ("max", 3, 1, "SAME")]:
+    ref = oinc._pool(torch.from_numpy(x), mode, k, s, pad).numpy()
+    got = K.pool2d(K.from_numpy(x), k, s, pad, mode).cpu()
+    assert_close(got, ref, 1e-6, "pool %s %s" % (mode, pad))
+
+
+def test_inception_v3_features(K):
+  from compare_gan_b200 import inception
+  assert inception.POOL_DIM == 2048 and inception.NUM_CLASSES == 1008
+  assert abs(inception.flops_per_image() / 1e9 - 11.4) < 0.6      # ~11.4 GF / image
+  w = inception.synthetic_weights(0)
+  net = inception.InceptionV3(w)
+  rng = np.random.RandomState(2)
+  x = (rng.rand(2, 299, 299, 3).astype(np.float32) * 2 - 1)
+  pool, logits = net(K.from_numpy(x))
+  rp, rl = oinc.inception_v3(x, w)
+  assert pool.shape == (2, 2048) and logits.shape == (2, 1008)
+  assert_close(pool.cpu(), rp.numpy(), 2e-4, "pool_3")
+  assert_close(logits.cpu(), rl.numpy(), 2e-4, "logits")
+
+
+def test_eval_fid_is_kid_against_oracle(K):
+  from compare_gan_b200 import eval_gan_lib, eval_utils, inception
+  from compare_gan_b200.metrics import fid_score, inception_score, kid_score
+  eng, orc = make_pair("resnet_cifar_arch", (32, 32, 3), 4, d_sn=True)
+  tasks = [fid_score.FIDScoreTask(), inception_score.InceptionScoreTask(), kid_score.KIDScoreTask()]
+  n = 96
+  rng = np.random.RandomState(3)
+  real = rng.rand(n, 32, 32, 3).astype(np.float32)
+  res = eval_gan_lib.evaluate(eng, tasks, num_averaging_runs=1, num_samples=n, batch_size=32, seed=42, real_images=real)
+  assert res["eval_samples_per_sec"] > 0
+  for key in ("fid_score", "inception_score", "kid_score"):
+    assert key + "_mean" in res and key + "_std" in res and key + "_list" in res      # eval_gan_lib_test.py:78-120
+  # oracle: regenerate the same samples (same z stream) with the engine's generator, then features + metrics on the CPU
+  from compare_gan_b200 import runner_lib
+  rs = np.random.RandomState(42)
+  w = eval_utils.get_inception().host_weights
+  fake_acts, fake_logits = [], []
+  for _ in range(n // 32):
+    imgs = eval_gan_lib.generate_batch(eng, 32, rs).cpu()
+    p, l = oinc.inception_v3(oinc.preprocess(imgs), w)
+    fake_acts.append(p.numpy()); fake_logits.append(l.numpy())
+  ra, _ = oinc.inception_v3(oinc.preprocess(real), w)
+  fa, fl, ra = np.concatenate(fake_acts), np.concatenate(fake_logits), ra.numpy()
+  fid_ref = ometrics.compute_fid_from_activations(ra, fa)
+  is_ref = ometrics.inception_score_from_logits(fl)
+  kid_ref = ometrics.kid(fa, ra)
+  assert abs(res["fid_score_mean"] - fid_ref) <= 5e-3 * abs(fid_ref), (res["fid_score_mean"], fid_ref)     # +-0.5 %
+  assert abs(res["inception_score_mean"] - is_ref) <= 5e-3 * abs(is_ref), (res["inception_score_mean"], is_ref)
+  assert abs(res["kid_score_mean"] - kid_ref) <= 5e-3 * abs(kid_ref) + 1e-6, (res["kid_score_mean"], kid_ref)
