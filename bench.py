@@ -21,10 +21,11 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: arch, image_shape, per-GPU batch, disc_iters, extra
-    "resnet_cifar10": dict(arch="resnet_cifar_arch", image=(32, 32, 3), batch=256, k=5, loss="non_saturating",
-                           penalty="no_penalty", lamba=1.0, d_sn=True, g_sn=False, g_lr=2e-4, beta1=0.5, beta2=0.999,
-                           gflop_per_slot_image=39.05),   # BASELINE.md §3 (useful FLOPs per batch-slot image per cycle)
+    # name: per-GPU batch (BASELINE.json configs), useful GFLOP per batch-slot image per cycle
+    "resnet_cifar10": dict(batch=256, gflop_per_slot_image=39.05, eval_samples=2048),
+    "sndcgan_celebahq128": dict(batch=128, gflop_per_slot_image=78.95, eval_samples=512),
+    "resnet_lsun-bedroom128": dict(batch=64, gflop_per_slot_image=559.2, eval_samples=512),
+    "biggan_imagenet128": dict(batch=256, gflop_per_slot_image=434.4, eval_samples=512),
 }
 
 
@@ -80,31 +81,27 @@ class ClockSampler(object):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_engine(wl, seed=0, math_mode=1):
-  from compare_gan_b200 import datasets, gin_lite as gin
-  from compare_gan_b200.gans import modular_gan
+def build_engine(workload, batch, seed=0, math_mode=1):
+  """ModularGAN configured by the reference's example config (restated in compare_gan_b200/configs.py)."""
+  from compare_gan_b200 import configs, datasets, gin_lite as gin, runner_lib
+  from compare_gan_b200.gans import modular_gan  # noqa: F401
   gin.clear_config()
-  gin.parse_config("\n".join([
-      "G.batch_norm_fn = @batch_norm", "G.spectral_norm = %s" % wl["g_sn"], "D.spectral_norm = %s" % wl["d_sn"],
-      "standardize_batch.decay = 0.9", "standardize_batch.epsilon = 1e-5",
-      "loss.fn = @%s" % wl["loss"], "penalty.fn = @%s" % wl["penalty"],
-      "ModularGAN.g_lr = %r" % wl["g_lr"], "ModularGAN.g_optimizer_fn = @tf.train.AdamOptimizer",
-      "tf.train.AdamOptimizer.beta1 = %r" % wl["beta1"], "tf.train.AdamOptimizer.beta2 = %r" % wl["beta2"],
-      "ModularGAN.math_mode = %d" % math_mode]))
-  ds = datasets.ImageDatasetV2("synthetic", wl["image"][0], wl["image"][2], None, 10000)
-  params = {"architecture": wl["arch"], "z_dim": 128, "lambda": wl["lamba"], "disc_iters": wl["k"], "seed": seed}
-  eng = modular_gan.ModularGAN(dataset=ds, parameters=params, model_dir="/tmp/cgan_bench")
-  eng.build(wl["batch"])
-  return eng, ds
+  gin.parse_config(configs.CONFIGS[workload])
+  gin.parse_config("ModularGAN.math_mode = %d" % math_mode)
+  options = runner_lib.get_options_dict()
+  options["seed"] = seed
+  ds = datasets.get_dataset()
+  eng = options["gan_class"](dataset=ds, parameters=options, model_dir="/tmp/cgan_bench")
+  eng.build(batch)
+  return eng, ds, options
 
 
-def time_dominant_kernel(wl, iters=20, math_mode=1):
+def time_dominant_kernel(b, iters=20, math_mode=1):
   """Roofline evidence for the dominant kernel: the 3x3 256->256 conv of G's B3 block at 32x32, batch = bench batch
   (1208 MF/img), timed alone with CUDA events on the launching stream; its 268 MB input and
   268 MB output exceed the 126 MB L2, so every launch streams from HBM."""
   import torch
   from compare_gan_b200 import kernels as K
-  b = wl["batch"]
   K.set_math_mode(math_mode)
   x = K.from_numpy(np.random.RandomState(0).randn(b, 32, 32, 256).astype(np.float32))
   w = K.from_numpy((np.random.RandomState(1).randn(3, 3, 256, 256) * 0.02).astype(np.float32))
@@ -140,17 +137,18 @@ def run_ours(args):
   K.init(local)
   wl = WORKLOADS[args.workload]
   mm = 1 if args.math == "tf32" else 0
-  eng, ds = build_engine(wl, seed=0, math_mode=mm)
-  k, b = wl["k"], wl["batch"]
+  b = args.batch or wl["batch"]
+  eng, ds, options = build_engine(args.workload, b, seed=0, math_mode=mm)
+  k = options["disc_iters"]
   rng = np.random.RandomState(1000 + rank)
 
   # pinned host staging buffers for the e2e arm
   def pinned_cycle():
-    imgs, zs, _, _, alphas = runner_lib.sample_cycle_inputs(eng, ds, b, rng)
+    parts = runner_lib.sample_cycle_inputs(eng, ds, b, rng)
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    return [pin(a) for a in imgs], [pin(a) for a in zs], None, None, [pin(a) for a in alphas]
+    return [None if part is None else [pin(a) for a in part] for part in parts]
   host = [pinned_cycle() for _ in range(2)]
-  h2d_bytes = sum(t.numel() * 4 for part in (host[0][0], host[0][1], host[0][4]) for t in part)
+  h2d_bytes = sum(t.numel() * t.element_size() for part in host[0] if part is not None for t in part)
 
   n0 = K.lib().launch_count()
   eng.set_inputs(*host[0])
@@ -208,17 +206,19 @@ def run_ours(args):
   out = None
   if rank == 0:
     pk = peaks()
-    dom = time_dominant_kernel(wl, math_mode=mm)
+    dom = time_dominant_kernel(b, math_mode=mm)
+    ev = eval_leg(eng, args, wl) if not args.no_eval else None
     cyc_tflop = wl["gflop_per_slot_image"] * b / 1e3          # useful TFLOP per cycle per GPU
     cpu = cpu_baseline_leg(args, sample_cycles=2) if not args.no_cpu_baseline else None
     out = {
-        "metric": "images/sec G+D step (resnet_cifar10)", "value": value, "unit": "images/sec", "n_gpus": world,
+        "metric": "images/sec G+D step (%s)" % args.workload, "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32" if mm else "f32", "data": "synthetic",
-        "config": {"workload": "resnet_cifar10.gin: resnet_cifar_arch 32x32x3, batch %d per GPU, disc_iters %d, "
-                               "non_saturating, spectral_norm on D, BN in G, Adam(2e-4,0.5,0.999); "
-                               "step = 5 D-updates + 1 G-update on %d images" % (b, k, b * (k + 1)),
+        "config": {"workload": "%s.gin (bindings restated in compare_gan_b200/configs.py): %s %dx%dx%d synthetic, batch %d "
+                               "per GPU, disc_iters %d; step = %d D-updates + 1 G-update on %d fresh images per GPU"
+                               % (args.workload, options["architecture"], ds.image_shape[0], ds.image_shape[1],
+                                  ds.image_shape[2], b, k, k, b * (k + 1)),
                    "global_batch": b * world, "parallelism": "dp%d" % world, "cuda_graph": graph,
                    "l2": "activations per cycle (GBs) exceed the 126 MB L2: inputs larger than L2",
                    "math_mode": ("1: tcgen05 kind::tf32 convolutions (operands rounded to nearest TF32, fp32 TMEM accumulate) "
@@ -238,6 +238,7 @@ def run_ours(args):
                      "step_useful_tflops_per_gpu": cyc_tflop / (ms_dev / args.steps / 1e3),
                      "step_frac": cyc_tflop / (ms_dev / args.steps / 1e3) / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])},
         "cpu_baseline": cpu,
+        "eval": ev,
         "losses": {"d": d_losses, "g": g_loss},
     }
     print(json.dumps(out))
@@ -250,20 +251,35 @@ def run_ours(args):
   return out
 
 
+def eval_leg(eng, args, wl):
+  """FID samples/sec (BASELINE metric): inference-mode G (batch 64, as the reference evaluates) -> bilinear 299x299 ->
+  Inception-v3 -> float64 (sum, sum xx^T) on the device; a bounded sample of the config's N."""
+  from compare_gan_b200 import eval_gan_lib, inception
+  from compare_gan_b200.metrics import fid_score, inception_score
+  n = args.eval_samples or wl["eval_samples"]
+  tasks = [fid_score.FIDScoreTask(), inception_score.InceptionScoreTask()]
+  eval_gan_lib.evaluate(eng, tasks, num_averaging_runs=1, num_samples=128, batch_size=64, num_accu_examples=256)   # warm-up
+  res = eval_gan_lib.evaluate(eng, tasks, num_averaging_runs=1, num_samples=n, batch_size=64, num_accu_examples=256)
+  return {"fid_samples_per_sec": res["eval_samples_per_sec"], "samples": n, "batch": 64,
+          "inception_gflop_per_sample": inception.flops_per_image() / 1e9,
+          "note": "Inception weights are synthetic (real graph not available offline): throughput is real, scores are not",
+          "fid_score": res["fid_score_mean"], "inception_score": res["inception_score_mean"]}
+
+
 def cpu_baseline_leg(args, sample_cycles=2, batch=64):
-  """The CPU restatement of the reference (TF cannot run here) on config C1: resnet_cifar, B=64, full cycle."""
+  """The CPU restatement of the reference (TF cannot run here) on BASELINE config C1: resnet_cifar10.gin, batch 64,
+  one full cycle = 5 D-updates + 1 G-update (the reference's own CPU-runnable case)."""
   import torch
   from oracle import gan as ogan, nets as onets
-  wl = WORKLOADS[args.workload]
-  cfg = onets.Cfg(architecture=wl["arch"], image_shape=wl["image"], g_bn="batch_norm", d_sn=wl["d_sn"], g_sn=wl["g_sn"],
+  cfg = onets.Cfg(architecture="resnet_cifar_arch", image_shape=(32, 32, 3), g_bn="batch_norm", d_sn=True, g_sn=False,
                   bn_decay=0.9, bn_eps=1e-5)
-  o = ogan.GanOracle(cfg, loss=wl["loss"], penalty=wl["penalty"], lamba=wl["lamba"], disc_iters=wl["k"],
-                     g_lr=wl["g_lr"], beta1=wl["beta1"], beta2=wl["beta2"]).build(2)
+  k = 5
+  o = ogan.GanOracle(cfg, loss="non_saturating", penalty="no_penalty", lamba=1.0, disc_iters=k, g_lr=2e-4, beta1=0.5,
+                     beta2=0.999).build(2)
   rng = np.random.RandomState(547)
-  k = wl["k"]
 
   def one():
-    imgs = [rng.rand(batch, *wl["image"]).astype(np.float32) for _ in range(k + 1)]
+    imgs = [rng.rand(batch, 32, 32, 3).astype(np.float32) for _ in range(k + 1)]
     zs = [rng.uniform(-1, 1, (batch, 128)).astype(np.float32) for _ in range(k + 1)]
     o.cycle(imgs, zs)
   one()   # warm-up
@@ -283,8 +299,6 @@ def run_reference(args):
   if rank != 0:
     return
   import torch
-  wl = WORKLOADS[args.workload]
-  k = wl["k"]
   batch = 64
   steps = max(1, min(args.steps, 3))
   t0 = time.time()
@@ -309,6 +323,9 @@ def main():
   ap.add_argument("--impl", default="ours")
   ap.add_argument("--workload", default="resnet_cifar10")
   ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+  ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+  ap.add_argument("--eval-samples", type=int, default=0)
+  ap.add_argument("--no-eval", action="store_true")
   ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs only)")
   ap.add_argument("--eager", action="store_true", help="do not capture the cycle into a CUDA graph (profiling runs only)")
   args = ap.parse_args()

@@ -59,6 +59,27 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
       }
     return CGAN_OK;
   }
+  // stride 2 (SNDCGAN D, sndcgan.py:109-121): the input is read through its four (row, column) parity phases, each a
+  // strided TMA view of the output's spatial size; tap (kh,kw) lands in phase ((kh-pad_t)&1, (kw-pad_l)&1).
+  if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 16 && !(d->h & 1) && !(d->w & 1) &&
+      d->oh == d->h / 2 && d->ow == d->w / 2 && cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cin, d->cout) &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+    int oh[16], ow[16], wt[16], am[16], nt = 0;
+    long long voff[4];
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) voff[a * 2 + b] = ((long long)a * d->w + b) * d->cin;
+    for (int kh = 0; kh < d->kh; ++kh) {
+      int th = kh - d->pad_t, a = th & 1;
+      for (int kw = 0; kw < d->kw; ++kw) {
+        int tw = kw - d->pad_l, b = tw & 1;
+        oh[nt] = (th - a) / 2; ow[nt] = (tw - b) / 2; wt[nt] = kh * d->kw + kw; am[nt] = a * 2 + b; ++nt;
+      }
+    }
+    return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->oh,
+                        d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am, bias, y,
+                        (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0);
+  }
   return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y);
 }
 
@@ -98,6 +119,35 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
     return cgan_conv_tc(ctx, dy, 4, voff, 2ll * d->cout, 2ll * d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
                         d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
                         (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
+  }
+  // stride 2 (also tf.nn.conv2d_transpose of SNDCGAN's generator, arch_ops.py:588-589): input pixel 2i+a only receives
+  // the taps with kh = a + pad_t (mod 2), from output row i + (a + pad_t - kh)/2 -> four launches, one per input phase,
+  // each writing a strided quarter of dx.
+  if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 16 && !(d->h & 1) && !(d->w & 1) &&
+      d->oh == d->h / 2 && d->ow == d->w / 2 && d->kh >= 2 && d->kw >= 2 &&
+      cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && d->cin % 4 == 0) {
+    const long long zero = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        int oh[16], ow[16], wt[16], nt = 0;
+        for (int kh = 0; kh < d->kh; ++kh) {
+          int th = a + d->pad_t - kh;
+          if (th & 1) continue;
+          for (int kw = 0; kw < d->kw; ++kw) {
+            int tw = b + d->pad_l - kw;
+            if (tw & 1) continue;
+            oh[nt] = th / 2; ow[nt] = tw / 2; wt[nt] = kh * d->kw + kw; ++nt;
+          }
+        }
+        if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty phase%s", "cgan_conv2d_dgrad");
+        int rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
+                              d->n, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr, nullptr,
+                              dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
+                              ((long long)a * d->w + b) * d->cin);
+        if (rc) return rc;
+      }
+    return CGAN_OK;
   }
   return cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);
 }

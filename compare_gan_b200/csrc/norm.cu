@@ -153,9 +153,11 @@ __global__ void bn_accumulate_kernel(float* mean_var, const float* batch, int C,
     mean_var[c] = m / counter;
     mean_var[C + c] = v / counter;
   }
-  __syncthreads();
-  // every thread has read *ac above; a single thread publishes the new counter (one block only)
-  if (update && blockIdx.x == 0 && threadIdx.x == 0) *ac = counter;
+}
+
+// runs after bn_accumulate_kernel on the same stream: every block of that kernel read the OLD counter
+__global__ void bn_accu_counter_kernel(float* ac, const float* upd) {
+  if (*upd == 1.0f) *ac += 1.0f;
 }
 
 __global__ void bn_apply_kernel(float* __restrict__ y, const float* __restrict__ x, long long total, int C,
@@ -283,9 +285,11 @@ int cgan_bn_accumulate(cgan_ctx* ctx, float* mean_var2c, const float* batch, int
                        float* accu_counter, const float* update_accus_dev) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, mean_var2c && batch && accu_mean && accu_var && accu_counter && update_accus_dev, "null pointer");
-  CGAN_REQUIRE(ctx, c > 0 && c <= 1024, "channels must be in (0,1024] (single block)");
-  bn_accumulate_kernel<<<1, 1024, 0, ctx->stream>>>(mean_var2c, batch, c, accu_mean, accu_var, accu_counter,
-                                                     update_accus_dev);
+  CGAN_REQUIRE(ctx, c > 0, "channels must be positive");
+  bn_accumulate_kernel<<<cdiv(c, 256), 256, 0, ctx->stream>>>(mean_var2c, batch, c, accu_mean, accu_var, accu_counter,
+                                                              update_accus_dev);
+  CGAN_LAUNCHED(ctx);
+  bn_accu_counter_kernel<<<1, 1, 0, ctx->stream>>>(accu_counter, update_accus_dev);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

@@ -30,7 +30,7 @@ constexpr int WG_MAX_TAPS = 16;
 
 struct WgParams {
   int ntaps;
-  int off_h[WG_MAX_TAPS], off_w[WG_MAX_TAPS], bmap[WG_MAX_TAPS], wtap[WG_MAX_TAPS];
+  int off_h[WG_MAX_TAPS], off_w[WG_MAX_TAPS], amap[WG_MAX_TAPS], bmap[WG_MAX_TAPS], wtap[WG_MAX_TAPS];
   int bw, bh, bni, tiles_w, tiles_h;     // 32-pixel box geometry
   int kblocks, kb_per_split;
   int ci_tiles, co_tiles, bn;
@@ -53,7 +53,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ BMaps tm_dy, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMaps tm_dy, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = (p.bn / 32) * WG_BOX;
@@ -76,7 +76,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const int ci0 = ci_t * 128, co0 = co_t * p.bn;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x.m[p.amap[tap]]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dy.m[p.bmap[tap]]) : "memory");
   }
   if (warp == 1) {
@@ -101,6 +101,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* mb = &tm_dy.m[p.bmap[tap]];
+      const CUtensorMap* ma = &tm_x.m[p.amap[tap]];
       const int dh = p.off_h[tap], dw = p.off_w[tap];
       int stage = 0;
       uint32_t phase = 0;
@@ -115,7 +116,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         uint8_t* sb = sa + WG_A_BYTES;
         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * WG_BOX, &tm_x, &full_bar[stage], ci0 + g * 32, w0 + dw, h0 + dh, n0);
+        for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * WG_BOX, ma, &full_bar[stage], ci0 + g * 32, w0 + dw, h0 + dh, n0);
         for (int g = 0; g < p.bn / 32; ++g) tma_load_4d(sb + g * WG_BOX, mb, &full_bar[stage], co0 + g * 32, w0, h0, n0);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -167,13 +168,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int row = quarter * 32 + lane;           // ci within the tile
     float* orow = p.partial + (((long long)split * p.taps_total + p.wtap[tap]) * p.cin + ci0 + row) * p.cout + co0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool row_ok = ci0 + row < p.cin;       // the last ci tile may hang over Cin (TMA zero-filled those channels)
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t r[32];
-      tmem_ld32(taddr + (uint32_t)c0, r);
+      tmem_ld32(taddr + (uint32_t)c0, r);       // warp-collective: every lane takes part, stores are predicated
+      if (row_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(orow + c0 + j) =
-            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(orow + c0 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -215,8 +219,14 @@ int pick_bn(int ncols) {
 }  // namespace
 
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d) {
-  if (d->stride != 1 || d->kh * d->kw > WG_MAX_TAPS) return false;
-  if (d->cin % 128 != 0 || pick_bn(d->cout) == 0) return false;
+  if ((d->stride != 1 && d->stride != 2) || d->kh * d->kw > WG_MAX_TAPS) return false;
+  if (d->stride == 2) {
+    if (d->upsample || (d->h & 1) || (d->w & 1) || d->oh != d->h / 2 || d->ow != d->w / 2) return false;
+    if (d->cin % 32 != 0 || d->cin < 64 || pick_bn(d->cout) == 0) return false;
+    int bw, bh, bni;
+    return box32(d->n, d->oh, d->ow, &bw, &bh, &bni);
+  }
+  if (d->cin % 32 != 0 || d->cin < 64 || pick_bn(d->cout) == 0) return false;   // Cin tiles of 128, last one zero-padded
   if (d->oh != (d->upsample ? 2 * d->h : d->h) || d->ow != (d->upsample ? 2 * d->w : d->w)) return false;
   int bw, bh, bni;
   return box32(d->n, d->h, d->w, &bw, &bh, &bni);
@@ -225,19 +235,26 @@ bool cgan_wgrad_tc_ok(const cgan_conv_desc* d) {
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
   WgParams p;
   memset(&p, 0, sizeof(p));
-  if (!box32(d->n, d->h, d->w, &p.bw, &p.bh, &p.bni)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: geometry%s", "cgan_wgrad_tc");
-  p.tiles_w = d->w / p.bw;
-  p.tiles_h = d->h / p.bh;
-  p.kblocks = (int)((long long)d->n * d->h * d->w / WG_P);
+  const int gh = d->stride == 2 ? d->oh : d->h, gw = d->stride == 2 ? d->ow : d->w;     // pixel-loop grid
+  if (!box32(d->n, gh, gw, &p.bw, &p.bh, &p.bni)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: geometry%s", "cgan_wgrad_tc");
+  p.tiles_w = gw / p.bw;
+  p.tiles_h = gh / p.bh;
+  p.kblocks = (int)((long long)d->n * gh * gw / WG_P);
   p.bn = pick_bn(d->cout);
-  p.ci_tiles = d->cin / 128;
+  p.ci_tiles = (d->cin + 127) / 128;
   p.co_tiles = d->cout / p.bn;
   p.cin = d->cin; p.cout = d->cout; p.taps_total = d->kh * d->kw;
-  // taps: pixel loop runs over the REAL input grid (i, j); tap (kh,kw) pairs X[i+dh, j+dw] with dY view `bmap`
+  // taps: the pixel loop runs over a grid (i, j) of gh x gw cells: the input grid (stride 1, incl. zero-inserted
+  // inputs) or the output grid (stride 2); tap (kh,kw) pairs X view `amap` at [i+dh, j+dw] with dY view `bmap` at [i, j]
   int nt = 0;
   for (int kh = 0; kh < d->kh; ++kh)
     for (int kw = 0; kw < d->kw; ++kw) {
-      if (!d->upsample) {
+      p.amap[nt] = 0;
+      if (d->stride == 2) {
+        // output (i,j) reads input row 2i + kh - pad_t = 2(i + dh) + a: phase view a of X
+        int th = kh - d->pad_t, tw = kw - d->pad_l, a = th & 1, b = tw & 1;
+        p.off_h[nt] = (th - a) / 2; p.off_w[nt] = (tw - b) / 2; p.amap[nt] = a * 2 + b; p.bmap[nt] = 0;
+      } else if (!d->upsample) {
         p.off_h[nt] = kh - d->pad_t; p.off_w[nt] = kw - d->pad_l; p.bmap[nt] = 0;
       } else {
         // output row 2i+a reads virtual row 2i+a+kh-pad_t, real only when even: a = (pad_t - kh) & 1, dh = (a+kh-pad_t)/2
@@ -267,16 +284,26 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
   }
   p.partial = partial;
 
-  CUtensorMap tm_x;
-  BMaps tm_dy;
+  BMaps tm_x, tm_dy;
+  memset(&tm_x, 0, sizeof(tm_x));
   memset(&tm_dy, 0, sizeof(tm_dy));
-  if (!make_act_map(&tm_x, x, d->cin, d->w, d->h, d->n, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin,
-                    p.bw, p.bh, p.bni, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-    return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(x) failed%s", "cgan_wgrad_tc");
+  for (int v = 0; v < 4; ++v) {
+    bool ok;
+    if (d->stride == 2) {     // X seen through its four stride-2 phases, each of the OUTPUT's spatial size
+      int a = v >> 1, b = v & 1;
+      ok = make_act_map(&tm_x.m[v], x + ((long long)a * d->w + b) * d->cin, d->cin, gw, gh, d->n, 2ll * d->cin,
+                        2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, p.bw, p.bh, p.bni,
+                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    } else {
+      ok = make_act_map(&tm_x.m[v], x, d->cin, d->w, d->h, d->n, d->cin, (long long)d->w * d->cin,
+                        (long long)d->h * d->w * d->cin, p.bw, p.bh, p.bni, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    }
+    if (!ok) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(x) failed%s", "cgan_wgrad_tc");
+  }
   for (int v = 0; v < 4; ++v) {
     bool ok;
     if (!d->upsample) {
-      ok = make_act_map(&tm_dy.m[v], dy, d->cout, d->w, d->h, d->n, d->cout, (long long)d->ow * d->cout,
+      ok = make_act_map(&tm_dy.m[v], dy, d->cout, gw, gh, d->n, d->cout, (long long)d->ow * d->cout,
                         (long long)d->oh * d->ow * d->cout, p.bw, p.bh, p.bni, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     } else {
       int a = v >> 1, b = v & 1;

@@ -197,19 +197,22 @@ class ModularGAN(AbstractGAN):
   def _cycle(self):
     k = self._disc_iters
     with V.use(self.store):
-      # _split_inputs_and_generate_samples (:428-469): all G forwards first; only the last one is differentiated
-      gens = []
-      for i in range(k + 1):
+      # _split_inputs_and_generate_samples (:428-469).  G's weights only change in the last sub-step, so the sample each
+      # D-update consumes is generated right before that update and freed after it, and the differentiated sample of
+      # the G-update is generated after the D-updates: same values as generating all k+1 up front (the TF graph leaves
+      # the order of the BN moving-average update ops undefined), but the G activation stash no longer lives through
+      # the D-updates — the difference between fitting BigGAN-128 at 256 images per GPU in 180 GB and not.
+      def gen(i, record):
         f = self.inputs[i]
         sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
-        with tape.record(i == k):
-          gens.append(self.generator(f["z"], y=sy, is_training=True))
+        with tape.record(record):
+          return self.generator(f["z"], y=sy, is_training=True)
       d_params = self.store.trainable_under("discriminator")
       g_params = self.store.trainable_under("generator")
       ones = K.fill_(K.empty(1), 1.0)
       for i in range(k):                                # _train_discriminator (:471-485)
         f = dict(self.inputs[i])
-        f["generated"] = tape.DT(gens[i].t)             # tf.stop_gradient
+        f["generated"] = tape.DT(gen(i, False).t)       # tf.stop_gradient
         self.create_loss(f, f.get("labels"), for_discriminator=True)
         grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add)
         scale = self._apply_grads("discriminator", self.flat_d, grads, list(d_params.keys()))
@@ -217,7 +220,7 @@ class ModularGAN(AbstractGAN):
         K._call("copy", self.losses.ptr + 4 * i, self.d_loss.ptr, 1)
         self.d_loss = self.g_loss = None
       f = dict(self.inputs[k])                          # _train_generator (:487-510)
-      f["generated"] = gens[k]
+      f["generated"] = gen(k, True)
       self.create_loss(f, f.get("labels"), for_discriminator=False)
       grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add)
       scale = self._apply_grads("generator", self.flat_g, grads, list(g_params.keys()))
@@ -261,6 +264,9 @@ class ModularGAN(AbstractGAN):
         self._cycle()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    # the warm-up's activation memory sits cached in the default pool; the graph allocates from its own private pool, so
+    # hand the cache back to the driver first (otherwise the peak is paid twice: BigGAN-128 at 256/GPU would not fit)
+    torch.cuda.empty_cache()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
       K.sync_stream()

@@ -304,7 +304,9 @@ def bias_add(x, bias):
 def act(x, kind, leak=0.0):
   y = empty(*x.shape)
   _call("act_fwd", y.ptr, x.ptr, kind, float(leak), y.numel)
-  ref = x if kind in (ACT_RELU, ACT_LRELU) else y
+  # a closure must never hold its own output DT (that would be a DT -> node -> closure -> DT reference cycle and delay
+  # freeing the stash until a cyclic GC pass): wrap the storage in a fresh, tape-less DT instead
+  ref = x if kind in (ACT_RELU, ACT_LRELU) else DT(y.t)
   return attach("act%d" % kind, y, [x], lambda g, needs: [act_bwd(g, ref, kind, leak)])
 
 
@@ -423,12 +425,14 @@ def softmax(x):
   """tf.nn.softmax over the last axis (arch_ops.py:745)."""
   cols = x.shape[-1]
   rows = x.numel // cols
-  y = empty(*x.shape)
+  shape = x.shape
+  y = empty(*shape)
   _call("softmax_fwd", y.ptr, x.ptr, rows, cols)
+  yv = DT(y.t)
 
   def vjp(g, needs):
-    dx = empty(*x.shape)
-    _call("softmax_bwd", dx.ptr, g.ptr, y.ptr, rows, cols)
+    dx = empty(*shape)
+    _call("softmax_bwd", dx.ptr, g.ptr, yv.ptr, rows, cols)
     return [dx]
   return attach("softmax", y, [x], vjp)
 
@@ -516,9 +520,11 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
   _call("bn_apply", y.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr,
         None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
 
+  yv = DT(y.t) if relu_after else None
+
   def vjp(g, needs):
     if relu_after:
-      g = act_bwd(g, y, ACT_RELU)     # y>0 <=> pre-activation>0
+      g = act_bwd(g, yv, ACT_RELU)    # y>0 <=> pre-activation>0
     sums = empty(2 * c)
     dgamma = dbeta = None
     if gamma is not None and needs[1]:
@@ -578,9 +584,11 @@ def spectral_normalize(w, u, left, eps=1e-12):
   u_used = empty(*u.shape)
   _call("copy", u_used.ptr, u.ptr, u.numel)
 
+  wbar_v = DT(wbar.t)
+
   def vjp(g, needs):
     dw = empty(*w.shape)
-    _call("spectral_norm_bwd", dw.ptr, g.ptr, wbar.ptr, rows, cols, int(left), u_used.ptr, v.ptr, sigma.ptr)
+    _call("spectral_norm_bwd", dw.ptr, g.ptr, wbar_v.ptr, rows, cols, int(left), u_used.ptr, v.ptr, sigma.ptr)
     return [dw]
   return attach("spectral_norm", wbar, [w], vjp)
 

@@ -9,13 +9,14 @@ WGAN-GP second backward needs no special casing.  PyTorch is used for device mem
 when the whole cycle is captured into a CUDA graph (gans/modular_gan.py of this package).
 """
 import contextlib
+import weakref
 
 import torch
 
 
 class DT(object):
   """Device tensor: float32 (or int32 labels), C-contiguous; 4-D tensors are NHWC."""
-  __slots__ = ("t", "node", "req")
+  __slots__ = ("t", "node", "req", "__weakref__")
 
   def __init__(self, t, req=False):
     assert t.is_contiguous()
@@ -44,10 +45,16 @@ class DT(object):
 
 
 class Node(object):
-  __slots__ = ("name", "inputs", "vjp", "out")
+  """`out` is held weakly: DT -> node -> inputs is then a DAG without reference cycles, so dropping the loss tensor
+  frees a whole sub-step's activation stash immediately by reference counting (a cyclic-GC delay here costs tens of GB)."""
+  __slots__ = ("name", "inputs", "vjp", "_out")
 
   def __init__(self, name, inputs, vjp, out):
-    self.name, self.inputs, self.vjp, self.out = name, inputs, vjp, out
+    self.name, self.inputs, self.vjp, self._out = name, inputs, vjp, weakref.ref(out)
+
+  @property
+  def out(self):
+    return self._out()
 
 
 _RECORD = [True]
@@ -106,9 +113,14 @@ def backward(roots, wrt, add_fn, create_graph=False):
   Returns the list of gradients for `wrt` (None where unreachable)."""
   order = _topo([r for r, _ in roots])
   dep = set(id(w) for w in wrt)
+  outs = {}                      # strong refs for the duration of this backward pass
   for node in order:
+    out = node.out
+    if out is None:
+      continue
+    outs[id(node)] = out
     if any(i is not None and id(i) in dep for i in node.inputs):
-      dep.add(id(node.out))
+      dep.add(id(out))
   grads = {}
   keep = set(id(w) for w in wrt)
   for r, seed in roots:
@@ -116,7 +128,9 @@ def backward(roots, wrt, add_fn, create_graph=False):
       grads[id(r)] = ("seed", seed) if id(r) not in grads else grads[id(r)]
   with record(create_graph):
     for node in reversed(order):
-      oid = id(node.out)
+      if id(node) not in outs:
+        continue
+      oid = id(outs[id(node)])
       if oid not in grads or oid not in dep:
         continue
       g = grads[oid]

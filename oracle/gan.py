@@ -157,14 +157,15 @@ class GanOracle(object):
     k = self.disc_iters
     ys = [self.one_hot(l) for l in labels] if self.conditional else [None] * (k + 1)
     sys_ = [self.one_hot(l) for l in sampled_labels] if self.conditional else [None] * (k + 1)
-    # _split_inputs_and_generate_samples :428-469 — all G forwards up front.
-    gens = []
-    for i in range(k + 1):
-      with torch.set_grad_enabled(i == k):   # only the G-step sample needs a backward graph
-        gens.append(nets.generator(self.store, self.cfg, torch.as_tensor(z[i]).to(self.dtype), sys_[i], True))
+    # _split_inputs_and_generate_samples :428-469.  The reference builds all k+1 G forwards up front; G's weights do not
+    # change before the last sub-step, so evaluating sample i right before it is consumed gives identical values (the
+    # G calls still happen in the order 0..k, which is what the BN moving averages see).
+    def gen_sample(i, grad):
+      with torch.set_grad_enabled(grad):     # only the G-step sample needs a backward graph
+        return nets.generator(self.store, self.cfg, torch.as_tensor(z[i]).to(self.dtype), sys_[i], True)
     d_losses = []
     for i in range(k):                                  # _train_discriminator :471-485
-      gen = gens[i].detach()
+      gen = gen_sample(i, False).detach()
       d_loss, _ = self.create_loss(torch.as_tensor(images[i]).to(self.dtype), gen, ys[i], sys_[i],
                                    None if alphas is None else torch.as_tensor(alphas[i]).to(self.dtype))
       params = self.store.trainable_under("discriminator")
@@ -176,7 +177,7 @@ class GanOracle(object):
       self.global_step_disc += 1
       d_losses.append(float(d_loss.detach()))
     # _train_generator :487-510 — new D forward with updated D, G grads only.
-    _, g_loss = self.create_loss(torch.as_tensor(images[k]).to(self.dtype), gens[k], ys[k], sys_[k],
+    _, g_loss = self.create_loss(torch.as_tensor(images[k]).to(self.dtype), gen_sample(k, True), ys[k], sys_[k],
                                  None, for_d=False)
     params = self.store.trainable_under("generator")
     grads = torch.autograd.grad(g_loss, list(params.values()), allow_unused=True)

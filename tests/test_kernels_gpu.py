@@ -388,7 +388,35 @@ TC_CASES = [
     (1, 64, 128, 128, 3, False),
     (2, 16, 64, 3, 3, False),      # thin image conv: Cout=3 zero-padded to a 32-column tile
     (2, 8, 32, 20, 1, False),
+    (2, 16, 96, 192, 3, False),    # Cin not a multiple of 128: zero-padded ci tile in the tensor-core wgrad
+    (2, 8, 192, 96, 3, True),
 ]
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k", [(2, 16, 64, 128, 4), (8, 8, 128, 256, 4), (2, 32, 64, 64, 3), (1, 64, 128, 128, 4)])
+def test_conv2d_stride2_tcgen05(K, n, h, cin, cout, k):
+  """Stride-2 convs (SNDCGAN D 4x4 s2, and its generator's transposed convs = their input gradient) on tcgen05 through
+  the four parity-phase TMA views."""
+  rng = np.random.RandomState(n * 100 + h + cin + k)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt, wt = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(w).requires_grad_(True)
+  ref = T.conv2d_same(xt, wt, 2) + torch.from_numpy(b)
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  K.set_math_mode(1)
+  try:
+    xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
+    n0 = K.lib().launch_count()
+    y = K.conv2d(xd, wd, bd, stride=2)
+    assert K.lib().launch_count() - n0 == 2, "expected weight prep + one tcgen05 launch"
+    assert_close(y.cpu(), ref.detach().numpy(), 1e-3, "s2 fwd")
+    gx, gw = tape_grads(K, y, gy, [xd, wd])
+    assert_close(gx.cpu(), xt.grad.numpy(), 1e-3, "s2 dgrad")
+    assert_close(gw.cpu(), wt.grad.numpy(), 1e-3, "s2 wgrad")
+  finally:
+    K.set_math_mode(0)
 
 
 @pytest.mark.parametrize("n,h,cin,cout,k,up", TC_CASES)
