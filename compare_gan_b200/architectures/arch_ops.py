@@ -90,7 +90,7 @@ def _bn_state(c, use_moving_averages):
 @gin.configurable(whitelist=["decay", "epsilon", "use_cross_replica_mean", "use_moving_averages"])
 def standardize_batch(inputs, is_training, decay=0.999, epsilon=1e-3, data_format="NHWC",
                       use_moving_averages=True, use_cross_replica_mean=None,
-                      _gamma=None, _beta=None, _cond=False):
+                      _gamma=None, _beta=None, _cond=False, _relu=False):
   """Batch standardisation (reference arch_ops.py:194-319).  The private `_gamma/_beta` arguments let
   batch_norm / conditional_batch_norm fuse their scale+offset into the same kernel."""
   if data_format not in {"NCHW", "NHWC"}:
@@ -106,9 +106,9 @@ def standardize_batch(inputs, is_training, decay=0.999, epsilon=1e-3, data_forma
   st = _bn_state(c, use_moving_averages)
   if is_training:
     return K.bn_train(inputs, _gamma, _beta, epsilon, st if use_moving_averages else None, decay, cond=_cond,
-                      allreduce=tpu_ops.cross_replica_sum_ if use_cross_replica_mean else None,
+                      relu_after=_relu, allreduce=tpu_ops.cross_replica_sum_ if use_cross_replica_mean else None,
                       world=tpu_ops.num_replicas() if use_cross_replica_mean else 1)
-  return K.bn_infer(inputs, _gamma, _beta, epsilon, st, use_moving_averages, cond=_cond)
+  return K.bn_infer(inputs, _gamma, _beta, epsilon, st, use_moving_averages, cond=_cond, relu_after=_relu)
 
 
 @gin.configurable(blacklist=["inputs"])
@@ -117,7 +117,7 @@ def no_batch_norm(inputs):
 
 
 @gin.configurable(blacklist=["inputs", "is_training", "center", "scale", "name"])
-def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm"):
+def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm", _relu=False):
   """Vanilla batch norm with trainable gamma/beta (reference arch_ops.py:327-367)."""
   with V.variable_scope(name):
     c = inputs.shape[-1]
@@ -125,7 +125,7 @@ def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm"):
     _bn_state_peek(c)
     gamma = V.get_variable("gamma", (c,), ones_init) if scale else None
     beta = V.get_variable("beta", (c,), zeros_init) if center else None
-    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta)
+    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _relu=_relu)
 
 
 def _bn_state_peek(c):
@@ -136,7 +136,7 @@ def _bn_state_peek(c):
 
 @gin.configurable(whitelist=["use_bias"])
 def conditional_batch_norm(inputs, y, is_training, use_sn, center=True, scale=True, name="batch_norm",
-                           use_bias=False):
+                           use_bias=False, _relu=False):
   """Conditional batch normalization (reference arch_ops.py:423-445): gamma(y), beta(y) = linear(y)."""
   if y is None:
     raise ValueError("You must provide y for conditional batch normalization.")
@@ -151,7 +151,17 @@ def conditional_batch_norm(inputs, y, is_training, use_sn, center=True, scale=Tr
         gamma = linear(y, c, scope="gamma", use_sn=use_sn, use_bias=use_bias)
       if center:
         beta = linear(y, c, scope="beta", use_sn=use_sn, use_bias=use_bias)
-    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _cond=True)
+    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _cond=True, _relu=_relu)
+
+
+def norm_relu(norm_fn, inputs, **kwargs):
+  """relu(norm_fn(inputs)): when the configured normaliser is one of the BN kernels above, the ReLU is fused into the
+  BN-apply kernel (one pass over the activation instead of two); any other normaliser is followed by a plain ReLU."""
+  fn = getattr(norm_fn, "__self__", None)
+  bn_fn = getattr(fn, "_batch_norm_fn", None) if fn is not None else None
+  if bn_fn in (batch_norm, conditional_batch_norm):
+    return norm_fn(inputs, _relu=True, **kwargs)
+  return K.relu(norm_fn(inputs, **kwargs))
 
 
 # ----------------------------------------------------------------------------- spectral norm

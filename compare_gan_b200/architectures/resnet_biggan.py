@@ -21,11 +21,9 @@ class BigGanResNetBlock(resnet_ops.ResNetBlock):
           self._in_channels, inputs.shape[-1]))
     with V.variable_scope(self._name):
       outputs = inputs
-      outputs = self.batch_norm(outputs, z=z, y=y, is_training=is_training, name="bn1")
-      outputs = K.relu(outputs)
+      outputs = ops.norm_relu(self.batch_norm, outputs, z=z, y=y, is_training=is_training, name="bn1")
       outputs = self._get_conv(outputs, self._in_channels, self._out_channels, self._scale1, suffix="conv1")
-      outputs = self.batch_norm(outputs, z=z, y=y, is_training=is_training, name="bn2")
-      outputs = K.relu(outputs)
+      outputs = ops.norm_relu(self.batch_norm, outputs, z=z, y=y, is_training=is_training, name="bn2")
       outputs = self._get_conv(outputs, self._out_channels, self._out_channels, self._scale2, suffix="conv2")
       if self._add_shortcut:
         shortcut = self._get_conv(inputs, self._in_channels, self._out_channels, self._scale, kernel_size=(1, 1),

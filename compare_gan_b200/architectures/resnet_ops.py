@@ -59,11 +59,9 @@ class ResNetBlock(object):
       output = inputs
       shortcut = self._get_conv(output, self._in_channels, self._out_channels, self._scale,
                                 suffix="conv_shortcut")
-      output = self.batch_norm(output, z=z, y=y, is_training=is_training, name="bn1")
-      output = K.relu(output)
+      output = ops.norm_relu(self.batch_norm, output, z=z, y=y, is_training=is_training, name="bn1")
       output = self._get_conv(output, self._in_channels, self._out_channels, self._scale1, suffix="conv1")
-      output = self.batch_norm(output, z=z, y=y, is_training=is_training, name="bn2")
-      output = K.relu(output)
+      output = ops.norm_relu(self.batch_norm, output, z=z, y=y, is_training=is_training, name="bn2")
       output = self._get_conv(output, self._out_channels, self._out_channels, self._scale2, suffix="conv2")
       return K.add(output, shortcut)
 

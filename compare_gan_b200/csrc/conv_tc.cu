@@ -27,7 +27,7 @@ using namespace tc;
 
 constexpr int TC_BM = 128;          // output pixels per CTA tile (UMMA M)
 constexpr int TC_BK = 32;           // fp32 channels per k-block: 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 4;   // the pipeline depth is chosen per launch so that TWO CTAs fit an SM (see host code)
 constexpr int TC_MAX_TAPS = 16;
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
@@ -38,6 +38,8 @@ struct TcParams {
   int bw, bh, bni;                  // tile box: bw*bh*bni == 128
   int tiles_w, tiles_h;             // tiles per image row / column
   int bn;                           // UMMA N (multiple of 32, <= 256)
+  int stages;                       // smem pipeline depth (2..4)
+  int tmem_cols;                    // power of two >= bn
   int cout;                         // valid output channels (row length of `out` pixels)
   long long s_n, s_h, s_w, base;    // output element strides / offset (floats)
   float* out;
@@ -60,17 +62,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // up to four views of the input tensor (the sub-pixel phases of a 2x-upsampled gradient); plain convs use view 0
 struct AMaps { CUtensorMap m[4]; };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16KB][B bn*128B] | barriers | tmem ptr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.bn * TC_BK * 4;
   const int stage_bytes = TC_A_BYTES + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
-  uint64_t* ready_bar = full_bar + TC_STAGES;
-  uint64_t* empty_bar = ready_bar + TC_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* ready_bar = full_bar + p.stages;
+  uint64_t* empty_bar = ready_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < TC_STAGES; ++s) {
+      for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&ready_bar[s], 4);      // one arrive per rounding warp
         mbar_init(&empty_bar[s], 1);
@@ -100,7 +102,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     }
     __syncwarp();
     // TMEM: 256 fp32 columns x 128 lanes for the accumulator
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -121,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
         tma_load_4d(sa, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
         tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap]);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -145,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
-      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else {
     // ===== warps 2..5: round A to nearest TF32 in smem, then epilogue =====
@@ -165,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA) reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready_bar[stage]);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
     mbar_wait(tmem_full_bar, 0);
@@ -219,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -329,7 +331,15 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) failed%s", "cgan_conv_tc");
   }
-  size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + (size_t)p.bn * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+  // Two CTAs per SM (each owns 256 of the 512 TMEM columns): one CTA's epilogue and prologue overlap the other's main
+  // loop, which matters for the short-K convolutions (3x3x128: 36 k-blocks).  ~110 KB of smem each.
+  const size_t stage_bytes = TC_A_BYTES + (size_t)p.bn * TC_BK * 4;
+  p.stages = (int)((110 * 1024) / stage_bytes);
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

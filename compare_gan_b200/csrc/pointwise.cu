@@ -185,6 +185,39 @@ __global__ void avgpool2_bwd_kernel(float* __restrict__ dx, const float* __restr
     dx[i] = 0.25f * dy[(((b * oh + yy / 2) * ow) + xx / 2) * c + ch];
   }
 }
+// 4-channel vectorised variants (C % 4 == 0): one thread per pooled pixel x channel quad.  The scalar kernels above are
+// instruction-bound (five integer divisions per element); these do the index arithmetic once per 16 output floats.
+__global__ void avgpool2_fwd_v4_kernel(float4* __restrict__ y, const float4* __restrict__ x, int n, int h, int w, int c4) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * oh * ow * c4;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    const float4* p = x + (((b * h + 2 * oy) * w) + 2 * ox) * c4 + ch;
+    float4 a = p[0], bb = p[c4], cc = p[(long long)w * c4], d = p[(long long)w * c4 + c4];
+    y[i] = make_float4((a.x + bb.x + cc.x + d.x) * 0.25f, (a.y + bb.y + cc.y + d.y) * 0.25f,
+                       (a.z + bb.z + cc.z + d.z) * 0.25f, (a.w + bb.w + cc.w + d.w) * 0.25f);
+  }
+}
+__global__ void avgpool2_bwd_v4_kernel(float4* __restrict__ dx, const float4* __restrict__ dy, int n, int h, int w, int c4) {
+  int oh = h / 2, ow = w / 2;
+  long long tot = (long long)n * oh * ow * c4;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    float4 g = dy[i];
+    g.x *= 0.25f; g.y *= 0.25f; g.z *= 0.25f; g.w *= 0.25f;
+    float4* p = dx + (((b * h + 2 * oy) * w) + 2 * ox) * c4 + ch;
+    p[0] = g; p[c4] = g; p[(long long)w * c4] = g; p[(long long)w * c4 + c4] = g;
+  }
+}
+
 __global__ void maxpool2_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int h, int w, int c) {
   int oh = h / 2, ow = w / 2;
   long long tot = (long long)n * oh * ow * c;
@@ -482,12 +515,20 @@ int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n)
 #define POOL_ARGS_OK(ctx) CGAN_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "need even h,w")
 int cgan_avgpool2_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w, int c) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, y && x, "null pointer"); POOL_ARGS_OK(ctx);
-  avgpool2_fwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(y, x, n, h, w, c);
+  if (c % 4 == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) == 0)
+    avgpool2_fwd_v4_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 16), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), n, h, w, c / 4);
+  else
+    avgpool2_fwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 4), 256, 0, ctx->stream>>>(y, x, n, h, w, c);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_avgpool2_bwd(cgan_ctx* ctx, float* dx, const float* dy, int n, int h, int w, int c) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy, "null pointer"); POOL_ARGS_OK(ctx);
-  avgpool2_bwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c), 256, 0, ctx->stream>>>(dx, dy, n, h, w, c);
+  if (c % 4 == 0 && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0)
+    avgpool2_bwd_v4_kernel<<<ew_grid(ctx, (long long)n * h * w * c / 16), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy), n, h, w, c / 4);
+  else
+    avgpool2_bwd_kernel<<<ew_grid(ctx, (long long)n * h * w * c), 256, 0, ctx->stream>>>(dx, dy, n, h, w, c);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_maxpool2_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w, int c) {

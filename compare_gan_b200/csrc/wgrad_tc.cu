@@ -21,7 +21,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int WG_STAGES = 4;
+constexpr int WG_MAX_STAGES = 4;
 constexpr int WG_P = 32;                 // pixels per k-block
 constexpr int WG_BOX = WG_P * 128;       // 4 KB: 32 pixel rows x 32 channels fp32
 constexpr int WG_A_BYTES = 4 * WG_BOX;   // 128 input channels
@@ -35,6 +35,7 @@ struct WgParams {
   int kblocks, kb_per_split;
   int ci_tiles, co_tiles, bn;
   int cin, cout, taps_total;
+  int stages, tmem_cols;                 // pipeline depth chosen so that two CTAs share an SM; TMEM columns = pow2 >= bn
   float* partial;                        // [split][taps_total][cin][cout]
 };
 
@@ -52,16 +53,16 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMaps tm_dy, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = (p.bn / 32) * WG_BOX;
   const int stage_bytes = WG_A_BYTES + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_bytes);
-  uint64_t* ready_bar = full_bar + WG_STAGES;
-  uint64_t* empty_bar = ready_bar + WG_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + WG_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* ready_bar = full_bar + p.stages;
+  uint64_t* empty_bar = ready_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +82,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < WG_STAGES; ++s) {
+      for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&ready_bar[s], 4);
         mbar_init(&empty_bar[s], 1);
@@ -90,7 +91,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -118,7 +119,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
 #pragma unroll
         for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * WG_BOX, ma, &full_bar[stage], ci0 + g * 32, w0 + dw, h0 + dh, n0);
         for (int g = 0; g < p.bn / 32; ++g) tma_load_4d(sb + g * WG_BOX, mb, &full_bar[stage], co0 + g * 32, w0, h0, n0);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -140,7 +141,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = threadIdx.x - 64;
@@ -159,7 +160,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready_bar[stage]);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
     mbar_wait(tmem_full_bar, 0);
@@ -184,7 +185,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -313,7 +314,13 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
     }
     if (!ok) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(dy) failed%s", "cgan_wgrad_tc");
   }
-  size_t smem = (size_t)WG_STAGES * (WG_A_BYTES + (size_t)(p.bn / 32) * WG_BOX) + 1024 + 256;
+  const size_t stage_bytes = WG_A_BYTES + (size_t)(p.bn / 32) * WG_BOX;
+  p.stages = (int)((110 * 1024) / stage_bytes);
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     CGAN_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -301,7 +301,13 @@ def bias_add(x, bias):
 
 # ------------------------------------------------------------------------------------ pointwise / pooling
 
+RELU_OBSERVERS = []     # test hook: callables receiving the boolean "input > 0" mask of every (leaky-)ReLU evaluated
+
+
 def act(x, kind, leak=0.0):
+  if RELU_OBSERVERS and kind in (ACT_RELU, ACT_LRELU):
+    for fn in RELU_OBSERVERS:
+      fn(x.t > 0)
   y = empty(*x.shape)
   _call("act_fwd", y.ptr, x.ptr, kind, float(leak), y.numel)
   # a closure must never hold its own output DT (that would be a DT -> node -> closure -> DT reference cycle and delay
@@ -521,6 +527,9 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
         None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
 
   yv = DT(y.t) if relu_after else None
+  if relu_after and RELU_OBSERVERS:
+    for fn in RELU_OBSERVERS:
+      fn(y.t > 0)
 
   def vjp(g, needs):
     if relu_after:

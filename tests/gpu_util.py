@@ -126,13 +126,10 @@ class ReluSigns(object):
     from compare_gan_b200 import kernels as K
     from oracle import tf_ops as T
     self._K, self._T = K, T
-    self._act, self._relu, self._lrelu = K.act, torch.relu, T.lrelu
+    self._relu, self._lrelu = torch.relu, T.lrelu
     rec = self
-
-    def act(x, kind, leak=0.0):
-      if kind in (K.ACT_RELU, K.ACT_LRELU):
-        rec.eng.append((x.t > 0).cpu().numpy())
-      return rec._act(x, kind, leak)
+    self._obs = lambda mask: rec.eng.append(mask.cpu().numpy())
+    K.RELU_OBSERVERS.append(self._obs)
 
     def relu(x):
       rec.orc.append((x.detach() > 0).numpy())
@@ -141,11 +138,12 @@ class ReluSigns(object):
     def lrelu(x, leak=0.2):
       rec.orc.append((x.detach() > 0).numpy())
       return rec._lrelu(x, leak)
-    K.act, torch.relu, T.lrelu = act, relu, lrelu
+    torch.relu, T.lrelu = relu, lrelu
     return self
 
   def __exit__(self, *a):
-    self._K.act, torch.relu, self._T.lrelu = self._act, self._relu, self._lrelu
+    self._K.RELU_OBSERVERS.remove(self._obs)
+    torch.relu, self._T.lrelu = self._relu, self._lrelu
 
   def start_oracle(self):
     self.orc = []
