@@ -90,5 +90,6 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 // internal (C++ linkage) entry points shared between translation units
-int cgan_conv2d_fwd_simt(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const float* bias, float* y);
+int cgan_conv2d_fwd_simt(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const float* bias, float* y,
+                         int relu = 0);
 int cgan_conv2d_dgrad_simt(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, float* dx);

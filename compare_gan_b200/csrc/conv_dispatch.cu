@@ -6,7 +6,7 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols);
 int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
                  long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
-                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base);
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
@@ -14,16 +14,23 @@ bool cgan_wgrad_thin_ok(const cgan_conv_desc* d);
 int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 
 int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
+  return cgan_conv2d_fwd_act(ctx, d, x, w, bias, 0, y);
+}
+
+int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, int act,
+                        float* y) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
+  CGAN_REQUIRE(ctx, act == 0 || act == CGAN_ACT_RELU, "act must be 0 or CGAN_ACT_RELU");
+  const int relu = act == CGAN_ACT_RELU;
   // a 1x1 kernel over a zero-inserted input leaves three of the four sub-pixel phases bias-only: not worth a tensor
   // core launch, the gather-GEMM handles it
-  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 16 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
+  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
       d->oh == (d->upsample ? 2 * d->h : d->h) &&
       d->ow == (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0)) {
-    int oh[16], ow[16], wt[16];
+    int oh[32], ow[32], wt[32];
     const long long zero = 0;
     if (!d->upsample) {
       int nt = 0;
@@ -33,7 +40,7 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
         }
       return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
                           d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                          (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0);
+                          (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
     }
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
     // pixel (2i+a, 2j+b) only sees the taps whose virtual input coordinate 2i+a+kh-pad is even -> real pixel i+dh.
@@ -54,7 +61,7 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
         int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
                               d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                              (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base);
+                              (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base, relu);
         if (rc) return rc;
       }
     return CGAN_OK;
@@ -78,21 +85,21 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
     }
     return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->oh,
                         d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am, bias, y,
-                        (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0);
+                        (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
   }
-  return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y);
+  return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu);
 }
 
 int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, float* dx) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && dy && w && dx, "null pointer");
   const bool geom = d->oh == (d->upsample ? 2 * d->h : d->h) && d->ow == (d->upsample ? 2 * d->w : d->w);
-  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 16 && geom &&
+  if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && geom &&
       cgan_tc_shape_ok(d->n, d->h, d->w, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
     // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, oh, ow, co] * w[kh,kw,ci,co]: HWIO is already [tap][row=ci][k=co], i.e.
     // K-major for this contraction (no transpose).
-    int oh[16], ow[16], wt[16], am[16], nt = 0;
+    int oh[32], ow[32], wt[32], am[32], nt = 0;
     long long voff[4] = {0, 0, 0, 0};
     if (!d->upsample) {
       // oh = ih + pad_t - kh
@@ -102,7 +109,7 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
         }
       return cgan_conv_tc(ctx, dy, 1, voff, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
                           d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
-                          (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
+                          (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
     }
     // zero-inserted input: the real pixel ih sits at virtual row 2*ih; tap kh reaches output row oh = 2*ih + pad_t - kh,
     // i.e. sub-pixel phase a = (pad_t - kh) & 1 of dy at phase-row ih + (pad_t - kh - a)/2.  The four phases are four
@@ -118,7 +125,7 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
     }
     return cgan_conv_tc(ctx, dy, 4, voff, 2ll * d->cout, 2ll * d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
                         d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
-                        (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0);
+                        (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
   }
   // stride 2 (also tf.nn.conv2d_transpose of SNDCGAN's generator, arch_ops.py:588-589): input pixel 2i+a only receives
   // the taps with kh = a + pad_t (mod 2), from output row i + (a + pad_t - kh)/2 -> four launches, one per input phase,
@@ -144,7 +151,7 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
         int rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
                               d->n, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr, nullptr,
                               dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
-                              ((long long)a * d->w + b) * d->cin);
+                              ((long long)a * d->w + b) * d->cin, 0);
         if (rc) return rc;
       }
     return CGAN_OK;

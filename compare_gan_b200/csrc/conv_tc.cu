@@ -28,7 +28,7 @@ using namespace tc;
 constexpr int TC_BM = 128;          // output pixels per CTA tile (UMMA M)
 constexpr int TC_BK = 32;           // fp32 channels per k-block: 128 B = one swizzle row
 constexpr int TC_MAX_STAGES = 4;   // the pipeline depth is chosen per launch so that TWO CTAs fit an SM (see host code)
-constexpr int TC_MAX_TAPS = 16;
+constexpr int TC_MAX_TAPS = 32;
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
 
@@ -37,6 +37,9 @@ struct TcParams {
   int off_h[TC_MAX_TAPS], off_w[TC_MAX_TAPS], wtap[TC_MAX_TAPS], amap[TC_MAX_TAPS];   // amap: which input view
   int bw, bh, bni;                  // tile box: bw*bh*bni == 128
   int tiles_w, tiles_h;             // tiles per image row / column
+  int rows_used;                    // bw*bh*bni <= 128 pixel rows actually filled by the TMA box
+  int img_n, img_h, img_w;          // extent of the pixel grid (tiles at the border hang over; those rows are not stored)
+  int relu;                         // fused ReLU in the epilogue (inference-only callers)
   int bn;                           // UMMA N (multiple of 32, <= 256)
   int stages;                       // smem pipeline depth (2..4)
   int tmem_cols;                    // power of two >= bn
@@ -120,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + TC_A_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.rows_used * TC_BK * 4 + b_bytes));
         tma_load_4d(sa, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
         tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -178,6 +181,8 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     const int wi = m % p.bw;
     const int hi = (m / p.bw) % p.bh;
     const int ni = m / (p.bw * p.bh);
+    // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
+    const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
     float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
                   (long long)(ow0 + wi) * p.s_w + nb0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -193,6 +198,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr + (uint32_t)c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;                 // (the tcgen05.ld above is warp-collective; only the stores are predicated)
       if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -203,6 +209,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
             const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           }
+          if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           *reinterpret_cast<float4*>(orow + c0 + j) = v;
         }
       } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
@@ -211,6 +218,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
           if (nb0 + c0 + j < p.cout) {
             float v = __uint_as_float(r[j]);
             if (p.bias) v += p.bias[nb0 + c0 + j];
+            if (p.relu) v = fmaxf(v, 0.f);
             orow[c0 + j] = v;
           }
         }
@@ -227,17 +235,32 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
 
 // dst[tap][r][k] (r < rows_pad) = rna_tf32(src[tap][k][r]) (transpose) or rna_tf32(src[tap][r][k]); rows >= `rows` are 0
 __global__ void wprep_kernel(float* __restrict__ dst, const float* __restrict__ src, int taps, int rows, int rows_pad,
-                             int kdim, int transpose) {
-  long long tot = (long long)taps * rows_pad * kdim;
+                             int kdim, int kdim_pad, int transpose) {
+  long long tot = (long long)taps * rows_pad * kdim_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(i % kdim);
-    long long t = i / kdim;
+    int k = (int)(i % kdim_pad);
+    long long t = i / kdim_pad;
     int r = (int)(t % rows_pad);
     int tap = (int)(t / rows_pad);
     float v = 0.f;
-    if (r < rows) v = transpose ? src[((long long)tap * kdim + k) * rows + r] : src[((long long)tap * rows + r) * kdim + k];
+    if (r < rows && k < kdim)
+      v = transpose ? src[((long long)tap * kdim + k) * rows + r] : src[((long long)tap * rows + r) * kdim + k];
     dst[i] = rna_tf32(v);
   }
+}
+
+// 128-pixel tile = bni images x bh rows x bw columns (bw*bh*bni <= 128).  Any grid size is accepted: border tiles hang
+// over (TMA zero-fills, the epilogue masks), e.g. Inception's 35x35 maps use 35x3 boxes (105 of 128 MMA rows).
+inline void tc_geometry(int n, int h, int w, int* bw, int* bh, int* bni, int* tw, int* th, int* tn) {
+  int parts = (w + 127) / 128;
+  *bw = (w + parts - 1) / parts;
+  *tw = (w + *bw - 1) / *bw;
+  *bh = 128 / *bw; if (*bh > h) *bh = h; if (*bh < 1) *bh = 1;
+  *th = (h + *bh - 1) / *bh;
+  *bni = (*bh == h) ? 128 / (*bw * *bh) : 1;
+  if (*bni < 1) *bni = 1;
+  if (*bni > n) *bni = n;
+  *tn = (n + *bni - 1) / *bni;
 }
 
 inline int tc_pick_bn(int ncols_pad) {
@@ -252,18 +275,9 @@ inline int tc_pick_bn(int ncols_pad) {
 
 // Geometry the tensor-core path accepts for a stride-1 convolution-like contraction.
 bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
-  if (kdim % TC_BK != 0 || ncols < 1) return false;
+  if (n < 1 || h < 1 || w < 1 || ncols < 1) return false;
+  if (kdim < 8 || kdim % 4 != 0) return false;           // TMA needs 16-byte pixel strides; K is zero-padded to 32
   if (ncols > 256 && ncols % 32 != 0) return false;      // small column counts are zero-padded to a multiple of 32
-  if (w > 128 || (128 % w) != 0) {
-    if (w % 128 != 0) return false;
-  }
-  int bw = w < 128 ? w : 128;
-  int bh = 128 / bw;
-  if (bh > h) bh = h;
-  if (h % bh != 0) return false;
-  int bni = 128 / (bw * bh);
-  if (bni < 1 || n % bni != 0) return false;
-  if (bw * bh * bni != 128) return false;
   int bn = tc_pick_bn((ncols + 31) / 32 * 32);
   return bn != 0 && bn % 32 == 0;
 }
@@ -277,22 +291,23 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
 int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
                  long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
-                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base) {
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable%s", "cgan_conv_tc");
   if (ntaps > TC_MAX_TAPS || nviews > 4) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: too many taps/views%s", "cgan_conv_tc");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.ntaps = ntaps;
-  p.kchunks = kdim / TC_BK;
+  const int kdim_pad = (kdim + TC_BK - 1) / TC_BK * TC_BK;
+  p.kchunks = kdim_pad / TC_BK;
   for (int i = 0; i < ntaps; ++i) {
     p.off_h[i] = off_h[i]; p.off_w[i] = off_w[i]; p.wtap[i] = wtap[i]; p.amap[i] = amap ? amap[i] : 0;
   }
-  p.bw = w < 128 ? w : 128;
-  p.bh = 128 / p.bw; if (p.bh > h) p.bh = h;
-  p.bni = 128 / (p.bw * p.bh);
-  p.tiles_w = w / p.bw;
-  p.tiles_h = h / p.bh;
+  int tiles_n;
+  tc_geometry(n, h, w, &p.bw, &p.bh, &p.bni, &p.tiles_w, &p.tiles_h, &tiles_n);
+  p.rows_used = p.bw * p.bh * p.bni;
+  p.img_n = n; p.img_h = h; p.img_w = w;
+  p.relu = relu;
   const int ncols_pad = (ncols + 31) / 32 * 32;
   p.bn = tc_pick_bn(ncols_pad);
   p.cout = ncols;
@@ -302,15 +317,15 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
 
   // weights -> tf32-rounded K-major [taps_total][ncols][kdim] in the workspace
   void* ws = nullptr;
-  size_t wbytes = (size_t)taps_total * ncols_pad * kdim * sizeof(float);
+  size_t wbytes = (size_t)taps_total * ncols_pad * kdim_pad * sizeof(float);
   int rc = cgan_ws(ctx, wbytes, &ws);
   if (rc) return rc;
   float* wt = reinterpret_cast<float*>(ws);
   {
-    long long tot = (long long)taps_total * ncols_pad * kdim;
+    long long tot = (long long)taps_total * ncols_pad * kdim_pad;
     long long blocks = (tot + 255) / 256, cap = (long long)ctx->num_sms * 8;
     wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, ncols_pad, kdim,
-                                                                               transpose_w);
+                                                                               kdim_pad, transpose_w);
     CGAN_LAUNCHED(ctx);
   }
 
@@ -323,8 +338,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
       return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)kdim, (cuuint64_t)ncols_pad, (cuuint64_t)taps_total};
-    cuuint64_t strides[2] = {(cuuint64_t)kdim * 4, (cuuint64_t)ncols_pad * kdim * 4};
+    cuuint64_t dims[3] = {(cuuint64_t)kdim_pad, (cuuint64_t)ncols_pad, (cuuint64_t)taps_total};
+    cuuint64_t strides[2] = {(cuuint64_t)kdim_pad * 4, (cuuint64_t)ncols_pad * kdim_pad * 4};
     cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.bn, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -345,7 +360,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
     CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * (n / p.bni)), (unsigned)(ncols_pad / p.bn));
+  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * tiles_n), (unsigned)(ncols_pad / p.bn));
   conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_as, tm_b, p);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;

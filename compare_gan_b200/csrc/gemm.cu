@@ -25,6 +25,7 @@ struct GP {
   int vh, vw;             // virtual (post-upsample) input size
   int splits, k_per_split;  // split-K (WGRAD) — blockIdx.z = split; partial results to `C` + z*M*N
   int vecA, vecB;         // host-verified: 8-wide vector loads are legal
+  int relu;               // fused ReLU (inference-only callers)
 };
 
 constexpr int BM = 128, BK = 16, NT = 256;
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(NT, 2) gather_gemm_kernel(GP p) {
         r *= p.alpha;
         if (p.beta != 0.f) r += p.beta * p.C[idx];
         if (p.bias) r += p.bias[n];
+        if (p.relu) r = fmaxf(r, 0.f);
       }
       p.C[idx] = r;
     }
@@ -365,7 +367,8 @@ GP conv_gp(const cgan_conv_desc* d) {
 
 }  // namespace
 
-int cgan_conv2d_fwd_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
+int cgan_conv2d_fwd_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                         int relu) {
   int rc = check_desc(ctx, d);
   if (rc) return rc;
   GP p = conv_gp(d);
@@ -373,6 +376,7 @@ int cgan_conv2d_fwd_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x,
   p.N = d->cout;
   p.K = d->kh * d->kw * d->cin;
   p.A = x; p.B = w; p.C = y; p.bias = bias;
+  p.relu = relu;
   p.ldc = d->cout;
   p.vecA = (d->cin % 8 == 0) && al16(x);
   p.vecB = (d->cout % 8 == 0) && al16(w);

@@ -153,9 +153,8 @@ class InceptionV3(object):
     for it in items:
       if it[0] == "conv":
         _, name, _, _, _, stride, padding = it
-        x = K.conv2d(x, self.w["inception/%s%s/kernel" % (pre, name)], self.w["inception/%s%s/bias" % (pre, name)],
-                     stride=stride, padding=padding)
-        x = K.relu(x)
+        x = K.conv2d_relu(x, self.w["inception/%s%s/kernel" % (pre, name)], self.w["inception/%s%s/bias" % (pre, name)],
+                          stride=stride, padding=padding)
       elif it[0] == "pool":
         _, mode, k, s, pad = it
         x = K.pool2d(x, k, s, pad, mode)

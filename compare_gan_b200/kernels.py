@@ -179,6 +179,16 @@ def _conv_fwd_raw(d, x, w, bias):
   return y
 
 
+def conv2d_relu(x, w, bias, stride=1, padding="SAME"):
+  """relu(conv2d(x, w) + bias) in one kernel; inference only (no tape)."""
+  n, h, ww, cin = x.shape
+  kh, kw, _, cout = w.shape
+  d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, False, padding)
+  y = empty(d.n, d.oh, d.ow, d.cout)
+  _call("conv2d_fwd_act", ctypes.byref(d), x.ptr, w.ptr, None if bias is None else bias.ptr, ACT_RELU, y.ptr)
+  return y
+
+
 def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME"):
   """tf.nn.conv2d(..., "SAME") + bias (arch_ops.py:568-572); `upsample` fuses resnet_ops.unpool
   (resnet_ops.py:35-56, 122-123) without materialising the zeros.  w is HWIO."""

@@ -70,6 +70,10 @@ typedef struct {
 /* y = conv(x, w) + bias   — tf.nn.conv2d(..., "SAME") + bias_add, arch_ops.py:568-572;
  * with desc.upsample: conv(unpool(x)), resnet_ops.py:122-130. */
 int cgan_conv2d_fwd(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const float* bias, float* y);
+/* same with a fused activation (act = 0 or CGAN_ACT_RELU): conv + folded-BN bias + ReLU of the Inception graph
+ * (tfgan.eval.run_inception, eval_utils.py:165-175); inference only. */
+int cgan_conv2d_fwd_act(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const float* bias, int act,
+                        float* y);
 /* dx = d/dx of the above (TF Conv2DBackpropInput); this is also tf.nn.conv2d_transpose, arch_ops.py:588-589. */
 int cgan_conv2d_dgrad(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w_hwio, float* dx);
 /* dw = d/dw (TF Conv2DBackpropFilter); deterministic split-K. */

@@ -83,3 +83,23 @@ def test_eval_fid_is_kid_against_oracle(K):
   assert abs(res["fid_score_mean"] - fid_ref) <= 5e-3 * abs(fid_ref), (res["fid_score_mean"], fid_ref)     # +-0.5 %
   assert abs(res["inception_score_mean"] - is_ref) <= 5e-3 * abs(is_ref), (res["inception_score_mean"], is_ref)
   assert abs(res["kid_score_mean"] - kid_ref) <= 5e-3 * abs(kid_ref) + 1e-6, (res["kid_score_mean"], kid_ref)
+
+
+def test_inception_v3_features_tf32(K):
+  """math_mode 1: the stride-1 SAME convolutions of Inception (35x35 / 17x17 / 8x8 maps, 1x7 / 7x1 / 5x5 kernels, 48/80-
+  channel inputs) run on tcgen05 through border-overhanging 128-pixel boxes and zero-padded K; pool_3 within 2e-3."""
+  from compare_gan_b200 import inception
+  w = inception.synthetic_weights(0)
+  rng = np.random.RandomState(2)
+  x = (rng.rand(2, 299, 299, 3).astype(np.float32) * 2 - 1)
+  rp, rl = oinc.inception_v3(x, w)
+  K.set_math_mode(1)
+  try:
+    net = inception.InceptionV3(w)
+    n0 = K.lib().launch_count()
+    pool, logits = net(K.from_numpy(x))
+    assert K.lib().launch_count() - n0 > 94
+  finally:
+    K.set_math_mode(0)
+  assert_close(pool.cpu(), rp.numpy(), 2e-3, "pool_3 (tf32)")
+  assert_close(logits.cpu(), rl.numpy(), 3e-3, "logits (tf32)")

@@ -390,6 +390,10 @@ TC_CASES = [
     (2, 8, 32, 20, 1, False),
     (2, 16, 96, 192, 3, False),    # Cin not a multiple of 128: zero-padded ci tile in the tensor-core wgrad
     (2, 8, 192, 96, 3, True),
+    (3, 35, 48, 64, 5, False),     # Inception-A: 35x35 map (105-row boxes), 25 taps, K=48 zero-padded to 64
+    (2, 17, 128, 192, 7, False),   # 17x17 map; square 7x7 here (49 taps) falls back to the gather-GEMM
+    (5, 8, 80, 96, 3, False),      # 8x8 maps, odd batch: the last tile hangs over the batch
+    (1, 147, 32, 64, 3, False),    # 147-wide rows split into two 74-pixel boxes
 ]
 
 
@@ -438,7 +442,8 @@ def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
     n0 = K.lib().launch_count()
     y = K.conv2d(xd, wd, bd, stride=1, upsample=up)
     launched = K.lib().launch_count() - n0
-    assert launched == (2 if not up else 8), "expected the tcgen05 path (weight prep + conv per phase), got %d launches" % launched
+    if k * k <= 32:
+      assert launched == (2 if not up else 8), "expected the tcgen05 path (weight prep + conv per phase), got %d launches" % launched
     assert_close(y.cpu(), ref.detach().numpy(), 1e-3, "tc conv fwd")
     gx, gw = tape_grads(K, y, gy, [xd, wd])
     assert_close(gx.cpu(), xt.grad.numpy(), 1e-3, "tc conv dgrad")
