@@ -4,7 +4,8 @@
 
 bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols);
 int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
-                 long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
+                 long long in_sn, int n, int h, int w, int gh, int gw, int kdim, const float* wsrc, int taps_total,
+                 int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
@@ -26,8 +27,8 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
   // a 1x1 kernel over a zero-inserted input leaves three of the four sub-pixel phases bias-only: not worth a tensor
   // core launch, the gather-GEMM handles it
   if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
-      d->oh == (d->upsample ? 2 * d->h : d->h) &&
-      d->ow == (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
+      (!d->upsample || (d->oh == 2 * d->h && d->ow == 2 * d->w)) && d->oh <= (d->upsample ? 2 * d->h : d->h) &&
+      d->ow <= (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0)) {
     int oh[32], ow[32], wt[32];
@@ -39,7 +40,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
           oh[nt] = kh - d->pad_t; ow[nt] = kw - d->pad_l; wt[nt] = kh * d->kw + kw; ++nt;
         }
       return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
-                          d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
+                          d->w, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
                           (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
     }
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
@@ -60,7 +61,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
         long long base = ((long long)a * d->ow + b) * d->cout;
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
         int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
-                              d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
+                              d->h, d->w, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
                               (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base, relu);
         if (rc) return rc;
       }
@@ -84,7 +85,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
       }
     }
     return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->oh,
-                        d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am, bias, y,
+                        d->ow, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am, bias, y,
                         (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
   }
   return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu);
@@ -108,7 +109,7 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
           oh[nt] = d->pad_t - kh; ow[nt] = d->pad_l - kw; wt[nt] = kh * d->kw + kw; am[nt] = 0; ++nt;
         }
       return cgan_conv_tc(ctx, dy, 1, voff, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
-                          d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
+                          d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
                           (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
     }
     // zero-inserted input: the real pixel ih sits at virtual row 2*ih; tap kh reaches output row oh = 2*ih + pad_t - kh,
@@ -124,7 +125,7 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
       }
     }
     return cgan_conv_tc(ctx, dy, 4, voff, 2ll * d->cout, 2ll * d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
-                        d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
+                        d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
                         (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
   }
   // stride 2 (also tf.nn.conv2d_transpose of SNDCGAN's generator, arch_ops.py:588-589): input pixel 2i+a only receives
@@ -149,7 +150,8 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
         }
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty phase%s", "cgan_conv2d_dgrad");
         int rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
-                              d->n, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr, nullptr,
+                              d->n, d->oh, d->ow, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr,
+                              nullptr,
                               dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
                               ((long long)a * d->w + b) * d->cin, 0);
         if (rc) return rc;

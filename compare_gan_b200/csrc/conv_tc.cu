@@ -286,10 +286,11 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
 // in + view_off[v], pixel strides sw/sh/sn floats) — one view for ordinary convs, the four sub-pixel phases of a
 // 2x-upsampled gradient for the input gradient of a conv over a zero-inserted input.
 // wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim] (transpose_w=0).
-// taps: `ntaps` entries (off_h, off_w, weight slice, view).  Output pixel (n, y, x), y < h, x < w, is written at
+// taps: `ntaps` entries (off_h, off_w, weight slice, view).  Output pixel (n, y, x), y < gh, x < gw, is written at
 // out + base + n*s_n + y*s_h + x*s_w (+ channel).
 int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
-                 long long in_sn, int n, int h, int w, int kdim, const float* wsrc, int taps_total, int transpose_w,
+                 long long in_sn, int n, int h, int w, int gh, int gw, int kdim, const float* wsrc, int taps_total,
+                 int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu) {
   EncodeTiledFn enc = get_encode();
@@ -304,9 +305,11 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
     p.off_h[i] = off_h[i]; p.off_w[i] = off_w[i]; p.wtap[i] = wtap[i]; p.amap[i] = amap ? amap[i] : 0;
   }
   int tiles_n;
-  tc_geometry(n, h, w, &p.bw, &p.bh, &p.bni, &p.tiles_w, &p.tiles_h, &tiles_n);
+  // the pixel grid that is tiled (gh x gw: the OUTPUT extent) may differ from the extent of the input views (h x w):
+  // VALID convolutions shrink it, their taps only carry non-negative offsets
+  tc_geometry(n, gh, gw, &p.bw, &p.bh, &p.bni, &p.tiles_w, &p.tiles_h, &tiles_n);
   p.rows_used = p.bw * p.bh * p.bni;
-  p.img_n = n; p.img_h = h; p.img_w = w;
+  p.img_n = n; p.img_h = gh; p.img_w = gw;
   p.relu = relu;
   const int ncols_pad = (ncols + 31) / 32 * 32;
   p.bn = tc_pick_bn(ncols_pad);

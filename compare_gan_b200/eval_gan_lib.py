@@ -61,8 +61,71 @@ class use_ema_weights(object):
       g.flat_g["param"].t.copy_(self.saved)
 
 
+class _EvalBatchGraph(object):
+  """One evaluation batch — inference-mode G, bilinear resize, Inception, float64 statistics update — captured into a
+  CUDA graph (~330 kernel launches per batch of 64 would otherwise be paid in Python on every batch)."""
+
+  def __init__(self, gan, batch_size, acc):
+    dev = K._RT["device"]
+    self.gan, self.b, self.acc = gan, batch_size, acc
+    self.z = tape.DT(torch.zeros(batch_size, gan._z_dim, device=dev))
+    self.labels = tape.DT(torch.zeros(batch_size, dtype=torch.int32, device=dev)) if gan.conditional else None
+    self.pool = tape.DT(torch.zeros(batch_size, eval_utils.inception.POOL_DIM, device=dev))
+    self.logits = tape.DT(torch.zeros(batch_size, eval_utils.inception.NUM_CLASSES, device=dev))
+    snap_s, snap_sxx = acc.s.clone(), acc.sxx.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      K.sync_stream()
+      for _ in range(2):
+        self._body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    self.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self.graph):
+      K.sync_stream()
+      self._body()
+    K.sync_stream()
+    torch.cuda.synchronize()
+    acc.s.copy_(snap_s)
+    acc.sxx.copy_(snap_sxx)
+
+  def _body(self):
+    g = self.gan
+    y = K.one_hot(self.labels, g._dataset.num_classes) if g.conditional else None
+    with V.use(g.store), tape.no_record():
+      imgs = g.generator(self.z, y=y, is_training=False)
+    pool, logits = eval_utils.inception_transform(imgs)
+    K._call("cov_accumulate", pool.ptr, self.b, self.acc.dim, self.acc.s.data_ptr(), self.acc.sxx.data_ptr())
+    K.copy_(self.pool, pool)
+    K.copy_(self.logits, logits)
+
+  def run_batches(self, rng, num_batches):
+    """Draws the latents of all batches first (same RNG order as the eager path: z then labels, batch by batch), ships
+    them to the device in one copy, then replays the graph back to back with no host synchronisation in between."""
+    g = self.gan
+    zs, ls = [], []
+    for _ in range(num_batches):
+      zs.append(eval_z_generator((self.b, g._z_dim), rng=rng))
+      if g.conditional:
+        ls.append(rng.randint(0, g._dataset.num_classes, self.b).astype(np.int32))
+    dev = self.z.t.device
+    z_all = torch.from_numpy(np.stack(zs)).pin_memory().to(dev, non_blocking=True)
+    l_all = torch.from_numpy(np.stack(ls)).pin_memory().to(dev, non_blocking=True) if g.conditional else None
+    for i in range(num_batches):
+      self.z.t.copy_(z_all[i], non_blocking=True)
+      if g.conditional:
+        self.labels.t.copy_(l_all[i], non_blocking=True)
+      self.graph.replay()
+      self.acc.n += self.b
+      if self.acc.keep:     # device-side copies; one device->host transfer at finish()
+        self.acc.acts.append(self.pool.t.clone())
+        self.acc.logits.append(self.logits.t.clone())
+
+
 def evaluate(gan, eval_tasks, num_averaging_runs=1, num_samples=None, batch_size=64, seed=42, num_accu_examples=204800,
-             keep_features=True, real_images=None):
+             keep_features=True, real_images=None, use_graph=True):
   """Mirrors evaluate_tfhub_module (reference eval_gan_lib.py:95-212).  Returns the result dict with
   `<label>_mean/_std/_list` keys plus `eval_samples_per_sec` (generation + Inception + statistics)."""
   dataset = gan._dataset
@@ -76,9 +139,14 @@ def evaluate(gan, eval_tasks, num_averaging_runs=1, num_samples=None, batch_size
     _update_bn_accumulators(gan, batch_size, num_accu_examples, rng)
     for _ in range(num_averaging_runs):
       acc = eval_utils.FeatureAccumulator(keep_features=keep_features)
+      graph = _EvalBatchGraph(gan, batch_size, acc) if (use_graph and n_local >= 4 * batch_size) else None
       torch.cuda.synchronize()
       t0 = time.time()
       done = 0
+      if graph is not None:
+        nb = n_local // batch_size
+        graph.run_batches(rng, nb)
+        done += nb * batch_size
       while done < n_local:
         imgs = generate_batch(gan, batch_size, rng)
         pool, logits = eval_utils.inception_transform(imgs)

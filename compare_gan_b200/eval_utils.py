@@ -67,8 +67,8 @@ class FeatureAccumulator(object):
     K._call("cov_accumulate", pool.ptr, int(valid), self.dim, self.s.data_ptr(), self.sxx.data_ptr())
     self.n += int(valid)
     if self.keep:
-      self.acts.append(pool.t[:valid].cpu())
-      self.logits.append(logits.t[:valid].cpu())
+      self.acts.append(pool.t[:valid].clone())
+      self.logits.append(logits.t[:valid].clone())
 
   def finish(self, sample):
     from .metrics import fid_score
@@ -81,7 +81,7 @@ class FeatureAccumulator(object):
       self.n = int(cnt.item())
     sample.moments = fid_score.moments_from_sums(self.s.cpu().numpy(), self.sxx.cpu().numpy(), self.n)
     if self.keep:
-      sample.set_inception_features(torch.cat(self.acts).numpy(), torch.cat(self.logits).numpy())
+      sample.set_inception_features(torch.cat(self.acts).cpu().numpy(), torch.cat(self.logits).cpu().numpy())
     return sample
 
 

@@ -103,3 +103,16 @@ def test_inception_v3_features_tf32(K):
     K.set_math_mode(0)
   assert_close(pool.cpu(), rp.numpy(), 2e-3, "pool_3 (tf32)")
   assert_close(logits.cpu(), rl.numpy(), 3e-3, "logits (tf32)")
+
+
+def test_eval_cuda_graph_equals_eager(K):
+  """The CUDA-graph-captured evaluation batch must give exactly the statistics of the eager path."""
+  from compare_gan_b200 import eval_gan_lib
+  from compare_gan_b200.metrics import fid_score, inception_score
+  eng, _ = make_pair("resnet_cifar_arch", (32, 32, 3), 4, d_sn=True)
+  tasks = [fid_score.FIDScoreTask(), inception_score.InceptionScoreTask()]
+  real = np.random.RandomState(5).rand(64, 32, 32, 3).astype(np.float32)
+  kw = dict(num_averaging_runs=1, num_samples=144, batch_size=32, seed=7, real_images=real)
+  a = eval_gan_lib.evaluate(eng, tasks, use_graph=True, **kw)
+  b = eval_gan_lib.evaluate(eng, tasks, use_graph=False, **kw)
+  assert a["fid_score_mean"] == b["fid_score_mean"] and a["inception_score_mean"] == b["inception_score_mean"]

@@ -454,3 +454,27 @@ def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
   yy, rr = y.cpu().astype(np.float64).ravel(), ref.detach().numpy().astype(np.float64).ravel()
   ratio = float((yy * rr).sum() / (rr * rr).sum())
   assert abs(ratio - 1.0) < 1.5e-4, ratio
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k", [(2, 35, 64, 96, 3), (1, 71, 80, 192, 3), (3, 8, 32, 64, 5)])
+def test_conv2d_valid_padding_tcgen05(K, n, h, cin, cout, k):
+  """VALID (unpadded) stride-1 convolutions (Inception stem) on tcgen05: the tile grid is the smaller output extent."""
+  import torch.nn.functional as F
+  rng = np.random.RandomState(h + cin)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  ref = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(3, 2, 0, 1)).permute(0, 2, 3, 1) + torch.from_numpy(b)
+  for mode, tol in ((0, 2e-5), (1, 1e-3)):
+    K.set_math_mode(mode)
+    try:
+      n0 = K.lib().launch_count()
+      y = K.conv2d(dev(K, x), dev(K, w), dev(K, b), padding="VALID")
+      if mode == 1:
+        assert K.lib().launch_count() - n0 == 2
+      yr = K.conv2d_relu(dev(K, x), dev(K, w), dev(K, b), padding="VALID")
+    finally:
+      K.set_math_mode(0)
+    assert y.shape == tuple(ref.shape)
+    assert_close(y.cpu(), ref.numpy(), tol, "valid conv mode %d" % mode)
+    assert_close(yr.cpu(), torch.relu(ref).numpy(), tol * 2, "valid conv+relu mode %d" % mode)
