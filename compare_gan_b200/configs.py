@@ -102,7 +102,29 @@ run_config.iterations_per_loop = 500
 run_config.save_checkpoints_steps = 2500
 """
 
+DCGAN_CELEBA64 = """
+dataset.name = "celeb_a"
+options.architecture = "dcgan_arch"
+options.batch_size = 64
+options.gan_class = @ModularGAN
+options.lamba = 1
+options.training_steps = 100000
+options.z_dim = 128
+G.batch_norm_fn = @batch_norm
+standardize_batch.decay = 0.9
+standardize_batch.epsilon = 1e-5
+options.disc_iters = 1
+D.spectral_norm = False
+loss.fn = @non_saturating
+penalty.fn = @no_penalty
+ModularGAN.g_lr = 0.0002
+ModularGAN.g_optimizer_fn = @tf.train.AdamOptimizer
+tf.train.AdamOptimizer.beta1 = 0.5
+tf.train.AdamOptimizer.beta2 = 0.999
+"""
+
 CONFIGS = {
+    "dcgan_celeba64": DCGAN_CELEBA64,
     "resnet_cifar10": RESNET_CIFAR10,
     "sndcgan_celebahq128": SNDCGAN_CELEBAHQ128,
     "resnet_lsun-bedroom128": RESNET_LSUN_BEDROOM128,

@@ -424,6 +424,37 @@ def _disc_resnet5(store, cfg, x, y, is_training, ch=64, channels=(1, 2, 4, 4, 8,
   return torch.sigmoid(logit), logit, feat
 
 
+def _gen_dcgan(store, cfg, z, y, is_training):
+  """dcgan.Generator.apply — dcgan.py:39-84 (5x5 stride-2 transposed convs, asymmetric SAME padding)."""
+  bn = cfg.g_bn
+  b = z.shape[0]
+  sh, sw, colors = cfg.image_shape
+  c2 = lambda s: -(-s // 2)
+  sh2, sw2 = c2(sh), c2(sw); sh4, sw4 = c2(sh2), c2(sw2); sh8, sw8 = c2(sh4), c2(sw4); sh16, sw16 = c2(sh8), c2(sw8)
+  h = linear(store, cfg, z, 512 * sh16 * sw16, "g_fc1").reshape(-1, sh16, sw16, 512)
+  h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "g_bn1", False))
+  h = deconv2d(store, cfg, h, (b, sh8, sw8, 256), 5, 5, 2, "g_dc1")
+  h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "g_bn2", False))
+  h = deconv2d(store, cfg, h, (b, sh4, sw4, 128), 5, 5, 2, "g_dc2")
+  h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "g_bn3", False))
+  h = deconv2d(store, cfg, h, (b, sh2, sw2, 64), 5, 5, 2, "g_dc3")
+  h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "g_bn4", False))
+  h = deconv2d(store, cfg, h, (b, sh, sw, colors), 5, 5, 2, "g_dc4")
+  return 0.5 * torch.tanh(h) + 0.5
+
+
+def _disc_dcgan(store, cfg, x, y, is_training):
+  """dcgan.Discriminator.apply — dcgan.py:87-129."""
+  sn, bn = cfg.d_sn, cfg.d_bn
+  h = T.lrelu(conv2d(store, cfg, x, 64, 5, 5, 2, "d_conv1", use_sn=sn))
+  for i, co in enumerate((128, 256, 512)):
+    h = conv2d(store, cfg, h, co, 5, 5, 2, "d_conv%d" % (i + 2), use_sn=sn)
+    h = T.lrelu(apply_bn(store, cfg, bn, h, y, is_training, "d_bn%d" % (i + 1), sn))
+  feat = h
+  logit = linear(store, cfg, h.reshape(x.shape[0], -1), 1, "d_fc4", use_sn=sn)
+  return torch.sigmoid(logit), logit, feat
+
+
 _BIGGAN_G = {512: [16, 16, 8, 8, 4, 2, 1, 1], 256: [16, 16, 8, 8, 4, 2, 1],
              128: [16, 16, 8, 4, 2, 1], 64: [16, 16, 8, 4, 2], 32: [4, 4, 4, 4]}
 _BIGGAN_D = {512: [1, 1, 2, 4, 8, 8, 16, 16], 256: [1, 2, 4, 8, 8, 16, 16],
@@ -500,9 +531,9 @@ def _disc_biggan(store, cfg, x, y, is_training):
   return torch.sigmoid(logit), logit, feat
 
 
-_GENS = {"resnet_cifar_arch": _gen_resnet_cifar, "sndcgan_arch": _gen_sndcgan,
+_GENS = {"dcgan_arch": _gen_dcgan, "resnet_cifar_arch": _gen_resnet_cifar, "sndcgan_arch": _gen_sndcgan,
          "resnet5_arch": _gen_resnet5, "resnet_biggan_arch": _gen_biggan}
-_DISCS = {"resnet_cifar_arch": _disc_resnet_cifar, "sndcgan_arch": _disc_sndcgan,
+_DISCS = {"dcgan_arch": _disc_dcgan, "resnet_cifar_arch": _disc_resnet_cifar, "sndcgan_arch": _disc_sndcgan,
           "resnet5_arch": _disc_resnet5, "resnet_biggan_arch": _disc_biggan}
 
 

@@ -120,6 +120,14 @@ def test_sndcgan_forward_and_cycle():
   _cycles_both(eng, orc, 4, (32, 32, 3), 128, 1)
 
 
+def test_dcgan_forward_and_cycle():
+  # dcgan_celeba64.gin structure: 5x5 stride-2 convs / transposed convs with TF's asymmetric SAME padding
+  _frozen_d_gradients(4, (32, 32, 3), 128, 1, arch="dcgan_arch")
+  eng, orc = make_pair("dcgan_arch", (32, 32, 3), 4, disc_iters=1)
+  _forward_both(eng, orc, 4, 128)
+  _cycles_both(eng, orc, 4, (32, 32, 3), 128, 1)
+
+
 def test_resnet5_wgangp_cycle():
   # config 4 structure (resnet_lsun-bedroom128.gin: WGAN-GP, lambda 10, no SN, Adam(0.5,0.9) lr 1e-4) at 64x64
   _frozen_d_gradients(2, (64, 64, 3), 128, 2, gp=True, tol=2e-3, arch="resnet5_arch", loss="wasserstein",

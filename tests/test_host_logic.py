@@ -71,12 +71,17 @@ tf.train.AdamOptimizer.beta2 = 0.999
   assert opts["architecture"] == "resnet_cifar_arch" and opts["disc_iters"] == 5 and opts["lambda"] == 1
   assert opts["gan_class"] is modular_gan.ModularGAN
   assert gin.query_parameter("standardize_batch.decay") == 0.9
-  if os.path.isdir(REF_CONFIGS):   # in the build container: every shipped config must parse unmodified
+  if os.path.isdir(REF_CONFIGS):   # in the build container: every shipped config must parse unmodified ...
+    from compare_gan_b200 import configs
     for fn in sorted(os.listdir(REF_CONFIGS)):
-      if fn.endswith(".gin") and "dcgan" not in fn:
+      if fn.endswith(".gin"):
         gin.clear_config()
         gin.parse_config(open(os.path.join(REF_CONFIGS, fn)).read())
         assert runner_lib.get_options_dict()["gan_class"] is modular_gan.ModularGAN
+        from_file = gin.operative_config_str()
+        gin.clear_config()
+        gin.parse_config(configs.CONFIGS[fn[:-4]])     # ... and the restated copy must bind exactly the same values
+        assert gin.operative_config_str() == from_file, fn
   gin.clear_config()
 
 
