@@ -308,6 +308,49 @@ class ModularGAN(AbstractGAN):
     self.losses.t.copy_(s["losses"])
     torch.cuda.synchronize()
 
+  # Checkpoints use the reference's variable key space: model variables under their TF names, Adam slots as
+  # `<var>/Adam`, `<var>/Adam_1`, EMA shadows as `<var>/ExponentialMovingAverage`, plus global_step / global_step_disc.
+  def checkpoint_dict(self):
+    out = dict(self.store.state_numpy())
+    for prefix, flat, opt in (("generator", self.flat_g, self.g_opt), ("discriminator", self.flat_d, self.d_opt)):
+      m, v = opt.m.cpu(), opt.v.cpu()
+      ema = self.ema.cpu() if (prefix == "generator" and self.ema is not None) else None
+      for name, (off, n) in flat["views"].items():
+        shape = self.store.vars[name].shape
+        out[name + "/Adam"] = m[off:off + n].reshape(shape).copy()
+        out[name + "/Adam_1"] = v[off:off + n].reshape(shape).copy()
+        if ema is not None:
+          out[name + "/ExponentialMovingAverage"] = ema[off:off + n].reshape(shape).copy()
+    out["global_step"] = np.array(self.global_step, np.int64)
+    out["global_step_disc"] = np.array(self.global_step_disc, np.int64)
+    return out
+
+  def save_checkpoint(self, model_dir):
+    import os
+    os.makedirs(model_dir, exist_ok=True)
+    path = os.path.join(model_dir, "model.ckpt-%d.npz" % self.global_step)
+    np.savez(path, **{k.replace("/", "|"): v for k, v in self.checkpoint_dict().items()})
+    return path
+
+  def load_checkpoint(self, path):
+    data = {k.replace("|", "/"): v for k, v in np.load(path).items()}
+    self.store.load_numpy({k: v for k, v in data.items() if k in self.store.vars})
+    for prefix, flat, opt in (("generator", self.flat_g, self.g_opt), ("discriminator", self.flat_d, self.d_opt)):
+      m, v = opt.m.cpu(), opt.v.cpu()
+      ema = self.ema.cpu() if (prefix == "generator" and self.ema is not None) else None
+      for name, (off, n) in flat["views"].items():
+        if name + "/Adam" in data:
+          m[off:off + n] = data[name + "/Adam"].ravel()
+          v[off:off + n] = data[name + "/Adam_1"].ravel()
+        if ema is not None and name + "/ExponentialMovingAverage" in data:
+          ema[off:off + n] = data[name + "/ExponentialMovingAverage"].ravel()
+      opt.m.t.copy_(torch.from_numpy(m)); opt.v.t.copy_(torch.from_numpy(v))
+      if ema is not None:
+        self.ema.t.copy_(torch.from_numpy(ema))
+    self.g_opt.step.fill_(int(data["global_step"]))
+    self.d_opt.step.fill_(int(data["global_step_disc"]))
+    torch.cuda.synchronize()
+
   def state_numpy(self):
     return self.store.state_numpy()
 

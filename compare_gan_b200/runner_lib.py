@@ -1,6 +1,10 @@
 """Runner surface (reference runner_lib.py:72-111, 280-354): the gin `options` dict and a plain Python
 training loop in place of TPUEstimator.train.  Checkpoint polling / CSV task manager are out of the
 accelerated path."""
+import csv
+import glob
+import os
+import re
 import time
 
 import numpy as np
@@ -64,12 +68,131 @@ def sample_cycle_inputs(gan, dataset, batch_size, rng):
   return images, z, labels, sampled, alphas
 
 
+class TaskManager(object):
+  """Interface for managing a task (reference runner_lib.py:114-199); checkpoints are `model.ckpt-<step>.npz`."""
+
+  def __init__(self, model_dir):
+    self._model_dir = model_dir
+
+  @property
+  def model_dir(self):
+    return self._model_dir
+
+  def mark_training_done(self):
+    os.makedirs(self.model_dir, exist_ok=True)
+    open(os.path.join(self.model_dir, "TRAIN_DONE"), "w").close()
+
+  def is_training_done(self):
+    return os.path.exists(os.path.join(self.model_dir, "TRAIN_DONE"))
+
+  def add_eval_result(self, checkpoint_path, result_dict, default_value):
+    pass
+
+  def get_checkpoints_with_results(self):
+    return set()
+
+  def unevaluated_checkpoints(self, timeout=0, eval_every_steps=None):
+    """Generator for checkpoints without evaluation results (reference :137-180)."""
+    evaluated = self.get_checkpoints_with_results()
+    last_eval = time.time()
+    while True:
+      ckpts = set(glob.glob(os.path.join(self.model_dir, "model.ckpt-*.npz")))
+      todo = sorted([(int(re.findall(r"ckpt-(\d+)\.npz$", c)[0]), c) for c in ckpts - evaluated])
+      if eval_every_steps:
+        todo = [(s, c) for s, c in todo if s > 0 and s % eval_every_steps == 0]
+      for _, c in todo:
+        yield c
+      if todo:
+        evaluated |= set(c for _, c in todo)
+        last_eval = time.time()
+        continue
+      if time.time() - last_eval > timeout or self.is_training_done():
+        break
+      time.sleep(60)
+
+  def report_progress(self, message):
+    pass
+
+
+class TaskManagerWithCsvResults(TaskManager):
+  """Task Manager that writes results to a CSV file (reference runner_lib.py:182-232): columns are
+  checkpoint_path, step, the sorted result keys, then the sorted operative gin bindings."""
+
+  def __init__(self, model_dir, score_file=None):
+    super(TaskManagerWithCsvResults, self).__init__(model_dir)
+    self._score_file = score_file or os.path.join(model_dir, "scores.csv")
+
+  def _get_config_for_step(self, step):
+    saved = glob.glob(os.path.join(self.model_dir, "operative_config-*.gin"))
+    steps = sorted(int(re.findall(r"operative_config-(\d+).gin", fn)[0]) for fn in saved)
+    assert steps
+    last = [s for s in steps if s <= int(step)][-1]
+    config = {}
+    for line in open(os.path.join(self.model_dir, "operative_config-%d.gin" % last)):
+      if "=" in line:
+        k, v = line.split("=", 1)
+        config[k.strip()] = v.strip()
+    return config
+
+  def add_eval_result(self, checkpoint_path, result_dict, default_value):
+    step = re.findall(r"ckpt-(\d+)\.npz$", checkpoint_path)[0]
+    config = self._get_config_for_step(step)
+    header = ["checkpoint_path", "step"] + sorted(result_dict) + sorted(config)
+    write_header = not os.path.exists(self._score_file)
+    row = dict(checkpoint_path=checkpoint_path, step=step, **config)
+    for k, v in result_dict.items():
+      row[k] = "{:.3f}".format(v) if isinstance(v, float) else v
+    with open(self._score_file, "a") as f:
+      writer = csv.DictWriter(f, fieldnames=header, extrasaction="ignore")
+      if write_header:
+        writer.writeheader()
+      writer.writerow(row)
+
+  def get_checkpoints_with_results(self):
+    if not os.path.exists(self._score_file):
+      return set()
+    with open(self._score_file) as f:
+      return {r["checkpoint_path"] for r in csv.DictReader(f)}
+
+
+def _run_eval(gan, task_manager, eval_tasks=None, num_averaging_runs=1, num_samples=None, eval_every_steps=None,
+              timeout=0):
+  """Evaluates all unevaluated checkpoints (reference runner_lib.py:235-277); NaN samples score NAN_DETECTED."""
+  from . import eval_gan_lib
+  from .metrics import fid_score, inception_score
+  eval_tasks = eval_tasks or [inception_score.InceptionScoreTask(), fid_score.FIDScoreTask()]
+  results = {}
+  for ckpt in task_manager.unevaluated_checkpoints(timeout=timeout, eval_every_steps=eval_every_steps):
+    gan.load_checkpoint(ckpt)
+    default_value = -1.0
+    try:
+      result_dict = eval_gan_lib.evaluate(gan, eval_tasks, num_averaging_runs=num_averaging_runs, num_samples=num_samples)
+    except ValueError:
+      result_dict = {}
+    except Exception as e:       # NanFoundError
+      if type(e).__name__ != "NanFoundError":
+        raise
+      result_dict = {}
+      default_value = eval_gan_lib.NAN_DETECTED
+    task_manager.add_eval_result(ckpt, result_dict, default_value)
+    results[ckpt] = result_dict
+  return results
+
+
 def run_with_schedule(schedule, options=None, model_dir="/tmp/compare_gan_b200", num_cycles=None, use_graph=True,
-                      seed=0):
-  """Run the `train` schedule on synthetic data (reference runner_lib.py:280-354)."""
-  if schedule != "train":
-    raise ValueError("Schedule {} not supported on the accelerated path.".format(schedule))
+                      seed=0, task_manager=None, save_every_cycles=None, eval_kwargs=None):
+  """Run the schedule `train` / `eval_after_train` / `continuous_eval` on synthetic data (reference
+  runner_lib.py:280-354)."""
+  if schedule not in ("train", "eval_after_train", "continuous_eval"):
+    raise ValueError("Schedule {} not supported.".format(schedule))
   options = options or get_options_dict()
+  task_manager = task_manager or TaskManagerWithCsvResults(model_dir)
+  if schedule == "continuous_eval":
+    dataset = datasets.get_dataset()
+    gan = options["gan_class"](dataset=dataset, parameters=options, model_dir=model_dir)
+    from .tpu import tpu_ops as _t
+    gan.build(options["batch_size"] // _t.num_replicas())
+    return {"eval": _run_eval(gan, task_manager, timeout=24 * 3600, **(eval_kwargs or {})), "gan": gan}
   dataset = datasets.get_dataset()
   gan = options["gan_class"](dataset=dataset, parameters=options, model_dir=model_dir)
   from .tpu import tpu_ops
@@ -83,8 +206,18 @@ def run_with_schedule(schedule, options=None, model_dir="/tmp/compare_gan_b200",
   for _ in range(cycles):
     gan.set_inputs(*sample_cycle_inputs(gan, dataset, per_replica, rng))
     gan.run_cycle()
+    if save_every_cycles and (_ + 1) % save_every_cycles == 0:
+      gan.save_checkpoint(model_dir)
   d_losses, g_loss = gan.read_losses()
-  return {"d_loss": d_losses, "g_loss": g_loss, "cycles": cycles, "seconds": time.time() - t0, "gan": gan}
+  os.makedirs(model_dir, exist_ok=True)
+  with open(os.path.join(model_dir, "operative_config-0.gin"), "w") as f:     # GinConfigSaverHook, runner_lib.py:319
+    f.write(gin.operative_config_str())
+  gan.save_checkpoint(model_dir)
+  task_manager.mark_training_done()
+  out = {"d_loss": d_losses, "g_loss": g_loss, "cycles": cycles, "seconds": time.time() - t0, "gan": gan}
+  if schedule == "eval_after_train":
+    out["eval"] = _run_eval(gan, task_manager, **(eval_kwargs or {}))
+  return out
 
 
 @gin.configurable("run_config")

@@ -116,3 +116,36 @@ def test_eval_cuda_graph_equals_eager(K):
   a = eval_gan_lib.evaluate(eng, tasks, use_graph=True, **kw)
   b = eval_gan_lib.evaluate(eng, tasks, use_graph=False, **kw)
   assert a["fid_score_mean"] == b["fid_score_mean"] and a["inception_score_mean"] == b["inception_score_mean"]
+
+
+def test_eval_after_train_schedule_and_checkpoint_roundtrip(K, tmp_path):
+  """runner_lib.run_with_schedule("eval_after_train") (reference runner_lib_test.py:149-255): trains a few cycles, writes
+  model.ckpt-<step>.npz in the reference's variable key space + operative_config-0.gin + TRAIN_DONE, evaluates the
+  checkpoint and appends a row to scores.csv; loading the checkpoint restores the state bit for bit."""
+  import csv, os
+  from compare_gan_b200 import configs, gin_lite as gin, runner_lib
+  from compare_gan_b200.gans import modular_gan  # noqa: F401
+  gin.clear_config()
+  gin.parse_config(configs.RESNET_CIFAR10)
+  gin.parse_config("options.batch_size = 8\nModularGAN.g_use_ema = True\nModularGAN.ema_start_step = 0")
+  md = str(tmp_path / "run")
+  out = runner_lib.run_with_schedule("eval_after_train", model_dir=md, num_cycles=2, use_graph=False,
+                                     eval_kwargs=dict(num_samples=64, num_averaging_runs=1))
+  gan = out["gan"]
+  assert os.path.exists(os.path.join(md, "TRAIN_DONE")) and os.path.exists(os.path.join(md, "operative_config-0.gin"))
+  ckpt = os.path.join(md, "model.ckpt-2.npz")
+  assert os.path.exists(ckpt)
+  keys = set(k.replace("|", "/") for k in np.load(ckpt).keys())
+  for k in ("generator/B1/up_conv1/kernel", "generator/B1/up_conv1/kernel/Adam", "generator/B1/up_conv1/kernel/Adam_1",
+            "generator/B1/up_conv1/kernel/ExponentialMovingAverage", "discriminator/B1/same_conv1/kernel/u_var",
+            "generator/B1/bn1/moving_mean", "global_step", "global_step_disc"):
+    assert k in keys, k
+  rows = list(csv.DictReader(open(os.path.join(md, "scores.csv"))))
+  assert len(rows) == 1 and rows[0]["step"] == "2" and "fid_score_mean" in rows[0] and "inception_score_mean" in rows[0]
+  before = gan.checkpoint_dict()
+  gan.store.vars["generator/fc_noise/kernel"].t.zero_()
+  gan.g_opt.m.t.zero_()
+  gan.load_checkpoint(ckpt)
+  after = gan.checkpoint_dict()
+  for k in before:
+    np.testing.assert_array_equal(before[k], after[k], err_msg=k)
