@@ -7,7 +7,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  long long in_sn, int n, int h, int w, int gh, int gw, int kdim, const float* wsrc, int taps_total,
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
-                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu);
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
+                 const int* view_phase_of = nullptr);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
@@ -69,11 +70,13 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
   }
   // stride 2 (SNDCGAN D, sndcgan.py:109-121): the input is read through its four (row, column) parity phases, each a
   // strided TMA view of the output's spatial size; tap (kh,kw) lands in phase ((kh-pad_t)&1, (kw-pad_l)&1).
-  if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 16 && !(d->h & 1) && !(d->w & 1) &&
-      d->oh == d->h / 2 && d->ow == d->w / 2 && cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cin, d->cout) &&
+  // Any size / SAME or VALID: phase a holds the rows 2r+a < H, i.e. (H-a+1)/2 of them (Inception's 35->17, 17->8).
+  if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 32 && d->h >= 2 && d->w >= 2 &&
+      (d->oh - 1) * 2 + d->kh - d->pad_t <= d->h + d->kh && cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
-    int oh[16], ow[16], wt[16], am[16], nt = 0;
+    int oh[32], ow[32], wt[32], am[32], nt = 0;
+    const int hw[2] = {d->h, d->w};
     long long voff[4];
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) voff[a * 2 + b] = ((long long)a * d->w + b) * d->cin;
@@ -84,9 +87,9 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
         oh[nt] = (th - a) / 2; ow[nt] = (tw - b) / 2; wt[nt] = kh * d->kw + kw; am[nt] = a * 2 + b; ++nt;
       }
     }
-    return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->oh,
-                        d->ow, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am, bias, y,
-                        (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
+    return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
+                        (d->h + 1) / 2, (d->w + 1) / 2, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am,
+                        bias, y, (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu, hw);
   }
   return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu);
 }

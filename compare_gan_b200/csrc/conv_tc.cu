@@ -263,11 +263,10 @@ inline void tc_geometry(int n, int h, int w, int* bw, int* bh, int* bni, int* tw
   *tn = (n + *bni - 1) / *bni;
 }
 
-inline int tc_pick_bn(int ncols_pad) {
+inline int tc_pick_bn(int ncols_pad) {     // largest UMMA N <= 256 (multiple of 32) that divides the padded column count
   if (ncols_pad <= 256) return ncols_pad;
-  if (ncols_pad % 256 == 0) return 256;
-  if (ncols_pad % 192 == 0) return 192;
-  if (ncols_pad % 128 == 0) return 128;
+  for (int b = 256; b >= 32; b -= 32)
+    if (ncols_pad % b == 0) return b;
   return 0;
 }
 
@@ -292,7 +291,9 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  long long in_sn, int n, int h, int w, int gh, int gw, int kdim, const float* wsrc, int taps_total,
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
-                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu) {
+                 const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
+                 const int* view_phase_of) {
+  // view_phase_of: {H, W} of the tensor whose four stride-2 parity phases the views are (nullptr: all views h x w)
   EncodeTiledFn enc = get_encode();
   if (!enc) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable%s", "cgan_conv_tc");
   if (ntaps > TC_MAX_TAPS || nviews > 4) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: too many taps/views%s", "cgan_conv_tc");
@@ -337,7 +338,11 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   memset(&tm_as, 0, sizeof(tm_as));
   for (int v = 0; v < 4; ++v) {
     int vv = v < nviews ? v : 0;
-    if (!make_act_map(&tm_as.m[v], in + view_off[vv], kdim, w, h, n, in_sw, in_sh, in_sn, p.bw, p.bh, p.bni))
+    // stride-2 phase views of an odd-sized tensor differ in extent: rows 2r+a < H  =>  (H - a + 1) / 2 rows in phase a
+    int vh = h, vw = w;
+    if (nviews == 4 && view_phase_of) { vh = (view_phase_of[0] - (vv >> 1) + 1) / 2; vw = (view_phase_of[1] - (vv & 1) + 1) / 2; }
+    if (vh < 1 || vw < 1) { vh = h; vw = w; vv = 0; }
+    if (!make_act_map(&tm_as.m[v], in + view_off[vv], kdim, vw, vh, n, in_sw, in_sh, in_sn, p.bw, p.bh, p.bni))
       return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
   }
   {

@@ -279,6 +279,33 @@ __global__ void pool2d_fwd_kernel(float* __restrict__ y, const float* __restrict
     y[i] = mode == 0 ? acc : acc / (float)max(cnt, 1);
   }
 }
+__global__ void pool2d_fwd_v4_kernel(float4* __restrict__ y, const float4* __restrict__ x, int n, int h, int w, int c4, int k,
+                                     int stride, int pad_t, int pad_l, int oh, int ow, int mode) {
+  long long tot = (long long)n * oh * ow * c4;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c4);
+    long long t = i / c4;
+    int ox = (int)(t % ow); t /= ow;
+    int oy = (int)(t % oh);
+    long long b = t / oh;
+    float4 acc = mode == 0 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int dy = 0; dy < k; ++dy) {
+      int iy = oy * stride + dy - pad_t;
+      if (iy < 0 || iy >= h) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        int ix = ox * stride + dx - pad_l;
+        if (ix < 0 || ix >= w) continue;
+        float4 v = x[((b * h + iy) * w + ix) * c4 + ch];
+        if (mode == 0) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        ++cnt;
+      }
+    }
+    if (mode != 0) { float inv = 1.0f / (float)max(cnt, 1); acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+    y[i] = acc;
+  }
+}
 // y[n,c] = scale * sum_hw x[n,hw,c]: one thread per (n,c) strides over hw; consecutive threads -> consecutive c
 __global__ void globalpool_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int hw, int c, float scale) {
   long long tot = (long long)n * c;
@@ -545,8 +572,12 @@ int cgan_pool2d_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int h, int w
                     int pad_l, int oh, int ow, int mode) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n > 0 && h > 0 && w > 0 && c > 0 && k > 0 && stride > 0 && oh > 0 && ow > 0, "bad argument");
   CGAN_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (max) or 1 (avg)");
-  pool2d_fwd_kernel<<<ew_grid(ctx, (long long)n * oh * ow * c), 256, 0, ctx->stream>>>(y, x, n, h, w, c, k, stride, pad_t, pad_l,
-                                                                                    oh, ow, mode);
+  if (c % 4 == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) == 0)
+    pool2d_fwd_v4_kernel<<<ew_grid(ctx, (long long)n * oh * ow * c / 4), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), n, h, w, c / 4, k, stride, pad_t, pad_l, oh, ow, mode);
+  else
+    pool2d_fwd_kernel<<<ew_grid(ctx, (long long)n * oh * ow * c), 256, 0, ctx->stream>>>(y, x, n, h, w, c, k, stride, pad_t, pad_l,
+                                                                                      oh, ow, mode);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_globalpool_fwd(cgan_ctx* ctx, float* y, const float* x, int n, int hw, int c, float scale) {

@@ -478,3 +478,30 @@ def test_conv2d_valid_padding_tcgen05(K, n, h, cin, cout, k):
     assert y.shape == tuple(ref.shape)
     assert_close(y.cpu(), ref.numpy(), tol, "valid conv mode %d" % mode)
     assert_close(yr.cpu(), torch.relu(ref).numpy(), tol * 2, "valid conv+relu mode %d" % mode)
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,pad", [(2, 17, 192, 320, 3, "VALID"), (2, 35, 288, 384, 3, "VALID"),
+                                                 (2, 9, 64, 64, 3, "SAME"), (3, 299, 3, 32, 3, "VALID")])
+def test_conv2d_stride2_any_size_tcgen05(K, n, h, cin, cout, k, pad):
+  """Stride-2 convs on odd-sized maps, SAME or VALID (Inception's reductions 35->17->8): the four parity phases have
+  different extents, each gets its own TMA view."""
+  import torch.nn.functional as F
+  rng = np.random.RandomState(h + cin)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  if pad == "SAME":
+    ref = T.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), 2) + torch.from_numpy(b)
+  else:
+    ref = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1) + torch.from_numpy(b)
+  K.set_math_mode(1)
+  try:
+    n0 = K.lib().launch_count()
+    y = K.conv2d_relu(dev(K, x), dev(K, w), dev(K, b), stride=2, padding=pad)
+    launched = K.lib().launch_count() - n0
+  finally:
+    K.set_math_mode(0)
+  if cin % 4 == 0:
+    assert launched == 2, "expected the tcgen05 path"
+  assert y.shape == tuple(ref.shape)
+  assert_close(y.cpu(), torch.relu(ref).numpy(), 1e-3, "stride-2 %s conv" % pad)
