@@ -25,8 +25,21 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
   CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
   CGAN_REQUIRE(ctx, act == 0 || act == CGAN_ACT_RELU, "act must be 0 or CGAN_ACT_RELU");
   const int relu = act == CGAN_ACT_RELU;
-  // a 1x1 kernel over a zero-inserted input leaves three of the four sub-pixel phases bias-only: not worth a tensor
-  // core launch, the gather-GEMM handles it
+  // a 1x1 kernel over a zero-inserted input (BigGAN's up-sampling shortcut): phase (0,0) is a plain 1x1 conv written to the
+  // even pixels, the other three phases are bias only
+  if (ctx->math_mode == 1 && d->stride == 1 && d->upsample && d->kh == 1 && d->kw == 1 && d->oh == 2 * d->h &&
+      d->ow == 2 * d->w && d->pad_t == 0 && d->pad_l == 0 && d->cout % 4 == 0 &&
+      cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+    const long long zero = 0;
+    const int o0 = 0, t0 = 0;
+    int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
+                          d->w, d->h, d->w, d->cin, w, 1, 1, d->cout, 1, &o0, &o0, &t0, nullptr, bias, y,
+                          (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, 0, relu);
+    if (rc) return rc;
+    if (relu && bias) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: fused relu on bias-only phases%s", "cgan_conv2d_fwd");
+    return cgan_upsample1x1_bias_phases(ctx, y, bias, d->n, d->oh, d->ow, d->cout);
+  }
   if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
       (!d->upsample || (d->oh == 2 * d->h && d->ow == 2 * d->w)) && d->oh <= (d->upsample ? 2 * d->h : d->h) &&
       d->ow <= (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&

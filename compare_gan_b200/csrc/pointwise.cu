@@ -358,6 +358,69 @@ __global__ void softmax_bwd_kernel(float* __restrict__ dx, const float* __restri
   s = block_sum(s, sh);
   for (int j = threadIdx.x; j < cols; j += blockDim.x) dx[off + j] = y[off + j] * (dy[off + j] - s);
 }
+// Warp-per-row softmax for rows of up to 1024 columns (attention: 1024 keys): the row lives in registers (float4 x NV per
+// lane), so forward reads and writes each element exactly once and backward reads dy, y once and writes dx once.
+template <int NV>      // float4s per lane: cols == 128 * NV
+__global__ void softmax_fwd_warp_kernel(float4* __restrict__ y, const float4* __restrict__ x, long long rows) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = x + row * (32 * NV);
+  float4 v[NV];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  s = warp_sum(s);
+  float inv = 1.0f / s;
+  float4* yr = y + row * (32 * NV);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+}
+template <int NV>
+__global__ void softmax_bwd_warp_kernel(float4* __restrict__ dx, const float4* __restrict__ dy, const float4* __restrict__ y,
+                                        long long rows) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long off = row * (32 * NV);
+  float4 g[NV], p[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = dy[off + i * 32 + lane];
+    p[i] = y[off + i * 32 + lane];
+    s += (g[i].x * p[i].x + g[i].y * p[i].y) + (g[i].z * p[i].z + g[i].w * p[i].w);
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    dx[off + i * 32 + lane] = make_float4(p[i].x * (g[i].x - s), p[i].y * (g[i].y - s), p[i].z * (g[i].z - s), p[i].w * (g[i].w - s));
+}
+
+// out[n, 2i+a, 2j+b, :] = bias for (a,b) != (0,0): the three bias-only sub-pixel phases of a 1x1 conv over a zero-inserted
+// input (BigGAN's up-sampling shortcut, resnet_biggan.py:143-146)
+__global__ void upsample1x1_bias_phases_kernel(float* __restrict__ out, const float* __restrict__ bias, int n, int oh, int ow, int c) {
+  long long tot = (long long)n * oh * ow * c;
+  EW_LOOP(i, tot) {
+    int ch = (int)(i % c);
+    long long t = i / c;
+    int x = (int)(t % ow);
+    int yy = (int)((t / ow) % oh);
+    if ((x | yy) & 1) out[i] = bias ? bias[ch] : 0.f;
+  }
+}
+
 __global__ void rowdot_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, long long rows, int cols) {
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -592,12 +655,33 @@ int cgan_globalpool_bwd(cgan_ctx* ctx, float* dx, const float* dy, int n, int hw
 }
 int cgan_softmax_fwd(cgan_ctx* ctx, float* y, const float* x, int64_t rows, int cols) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && rows > 0 && cols > 0 && rows < (1ll << 31), "bad argument");
-  softmax_fwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(y, x, cols);
+  const bool al = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+  const unsigned wblocks = (unsigned)((rows * 32 + 255) / 256);
+  if (al && cols == 1024)
+    softmax_fwd_warp_kernel<8><<<wblocks, 256, 0, ctx->stream>>>(reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), rows);
+  else if (al && cols == 256)
+    softmax_fwd_warp_kernel<2><<<wblocks, 256, 0, ctx->stream>>>(reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), rows);
+  else
+    softmax_fwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(y, x, cols);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_softmax_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* y, int64_t rows, int cols) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && y && rows > 0 && cols > 0 && rows < (1ll << 31), "bad argument");
-  softmax_bwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(dx, dy, y, cols);
+  const bool al = ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const unsigned wblocks = (unsigned)((rows * 32 + 255) / 256);
+  if (al && cols == 1024)
+    softmax_bwd_warp_kernel<8><<<wblocks, 256, 0, ctx->stream>>>(reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy),
+                                                                 reinterpret_cast<const float4*>(y), rows);
+  else if (al && cols == 256)
+    softmax_bwd_warp_kernel<2><<<wblocks, 256, 0, ctx->stream>>>(reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy),
+                                                                 reinterpret_cast<const float4*>(y), rows);
+  else
+    softmax_bwd_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(dx, dy, y, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_upsample1x1_bias_phases(cgan_ctx* ctx, float* out, const float* bias, int n, int oh, int ow, int c) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && n > 0 && oh > 0 && ow > 0 && c > 0, "bad argument");
+  upsample1x1_bias_phases_kernel<<<ew_grid(ctx, (long long)n * oh * ow * c), 256, 0, ctx->stream>>>(out, bias, n, oh, ow, c);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_rowdot(cgan_ctx* ctx, float* out, const float* a, const float* b, int64_t rows, int cols) {

@@ -394,6 +394,8 @@ TC_CASES = [
     (2, 17, 128, 192, 7, False),   # 17x17 map; square 7x7 here (49 taps) falls back to the gather-GEMM
     (5, 8, 80, 96, 3, False),      # 8x8 maps, odd batch: the last tile hangs over the batch
     (1, 147, 32, 64, 3, False),    # 147-wide rows split into two 74-pixel boxes
+    (8, 4, 32, 64, 1, True),       # 1x1 over a zero-inserted input: phase (0,0) on tcgen05 + bias-only phases
+    (2, 16, 192, 96, 1, True),
 ]
 
 
@@ -442,7 +444,9 @@ def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
     n0 = K.lib().launch_count()
     y = K.conv2d(xd, wd, bd, stride=1, upsample=up)
     launched = K.lib().launch_count() - n0
-    if k * k <= 32:
+    if k == 1 and up:
+      assert launched == 3, "1x1 up-sampling conv: weight prep + one tcgen05 phase + bias fill, got %d" % launched
+    elif k * k <= 32:
       assert launched == (2 if not up else 8), "expected the tcgen05 path (weight prep + conv per phase), got %d launches" % launched
     assert_close(y.cpu(), ref.detach().numpy(), 1e-3, "tc conv fwd")
     gx, gw = tape_grads(K, y, gy, [xd, wd])
@@ -505,3 +509,18 @@ def test_conv2d_stride2_any_size_tcgen05(K, n, h, cin, cout, k, pad):
     assert launched == 2, "expected the tcgen05 path"
   assert y.shape == tuple(ref.shape)
   assert_close(y.cpu(), torch.relu(ref).numpy(), 1e-3, "stride-2 %s conv" % pad)
+
+
+@pytest.mark.parametrize("rows,cols", [(70, 1024), (33, 256), (5, 100)])
+def test_softmax_rows(K, rows, cols):
+  rng = np.random.RandomState(cols)
+  x = (rng.randn(rows, cols) * 3).astype(np.float32)
+  gy = rng.randn(rows, cols).astype(np.float32)
+  xt = torch.from_numpy(x).requires_grad_(True)
+  ref = torch.softmax(xt, -1)
+  ref.backward(torch.from_numpy(gy))
+  xd = dev(K, x, True)
+  y = K.softmax(xd)
+  assert_close(y.cpu(), ref.detach().numpy(), 1e-6, "softmax")
+  (gx,) = tape_grads(K, y, gy, [xd])
+  assert_close(gx.cpu(), xt.grad.numpy(), 2e-5, "softmax grad")
