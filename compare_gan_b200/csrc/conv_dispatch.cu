@@ -8,7 +8,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
-                 const int* view_phase_of = nullptr);
+                 const int* view_phase_of = nullptr, int wimg_stride = 0);
+int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
@@ -186,4 +187,45 @@ int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, co
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0)
     return cgan_wgrad_tc(ctx, d, x, dy, dw);
   return cgan_conv2d_wgrad_simt(ctx, d, x, dy, dw);
+}
+
+
+// ---- batched GEMM on tensor cores (attention, arch_ops.py:744, 753 and their gradients) ------------------------------
+// rows of each matrix are laid out as an h x w pixel grid so the conv tiling applies; m = h*w must be >= 128.
+static bool rows_as_grid(int m, int* h, int* w) {
+  if (m < 128) return false;
+  for (int ww = 128; ww >= 8; ww >>= 1)
+    if (m % ww == 0) { *w = ww; *h = m / ww; return true; }
+  return false;
+}
+
+int cgan_gemm_batched(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda, int64_t sa,
+                      const float* b, int ldb, int64_t sb, float beta, float* c, int ldc, int64_t sc, int batch) {
+  if (!ctx) return CGAN_ERR_ARG;
+  const bool plain = alpha == 1.0f && beta == 0.0f && batch > 1 && a && b && c &&
+                     ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+  int h, w;
+  if (ctx->math_mode == 1 && plain && !ta && rows_as_grid(m, &h, &w) && lda == k && sa == (int64_t)m * k && ldc == n &&
+      sc == (int64_t)m * n && k % 4 == 0 && k >= 8 && n % 4 == 0 && cgan_tc_shape_ok(batch, h, w, k, n)) {
+    // C[i] = A[i] * op(B[i]):  A[i] rows = pixels, k = channels; B[i] is the per-image "weight" slice
+    const bool nt = tb && ldb == k && sb == (int64_t)n * k;        // B[i] stored [n, k]  (K-major already)
+    const bool nn = !tb && ldb == n && sb == (int64_t)k * n;       // B[i] stored [k, n]  (transposed by the prep kernel)
+    if (nt || nn) {
+      const long long zero = 0;
+      const int o0 = 0;
+      return cgan_conv_tc(ctx, a, 1, &zero, k, (long long)w * k, (long long)m * k, batch, h, w, h, w, k, b, batch, nn ? 1 : 0, n,
+                          1, &o0, &o0, &o0, nullptr, nullptr, c, (long long)m * n, (long long)w * n, n, 0, 0, nullptr, 1);
+    }
+  }
+  if (ctx->math_mode == 1 && plain && ta && !tb && rows_as_grid(k, &h, &w) && lda == m && sa == (int64_t)k * m && ldb == n &&
+      sb == (int64_t)k * n && ldc == n && sc == (int64_t)m * n && m % 32 == 0 && m >= 64 && n % 4 == 0 && n <= 256 && k % 32 == 0) {
+    // C[i] = A[i]^T * B[i]: the reduction runs over the rows (pixels) -> the filter-gradient kernel, one image per CTA row
+    return cgan_wgrad_tc_batched(ctx, a, b, c, batch, h, w, m, n);
+  }
+  return cgan_gemm_batched_simt(ctx, ta, tb, m, n, k, alpha, a, lda, sa, b, ldb, sb, beta, c, ldc, sc, batch);
+}
+
+int cgan_gemm(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda, const float* b,
+              int ldb, float beta, float* c, int ldc) {
+  return cgan_gemm_batched_simt(ctx, ta, tb, m, n, k, alpha, a, lda, 0, b, ldb, 0, beta, c, ldc, 0, 1);
 }

@@ -40,6 +40,7 @@ struct TcParams {
   int rows_used;                    // bw*bh*bni <= 128 pixel rows actually filled by the TMA box
   int img_n, img_h, img_w;          // extent of the pixel grid (tiles at the border hang over; those rows are not stored)
   int relu;                         // fused ReLU in the epilogue (inference-only callers)
+  int wimg_stride;                  // batched GEMM: weight slice = wtap + image * wimg_stride (tiles never span images)
   int bn;                           // UMMA N (multiple of 32, <= 256)
   int stages;                       // smem pipeline depth (2..4)
   int tmem_cols;                    // power of two >= bn
@@ -125,7 +126,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         uint8_t* sb = sa + TC_A_BYTES;
         mbar_expect_tx(&full_bar[stage], (uint32_t)(p.rows_used * TC_BK * 4 + b_bytes));
         tma_load_4d(sa, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
-        tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap]);
+        tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap] + n0 * p.wimg_stride);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -292,7 +293,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
-                 const int* view_phase_of) {
+                 const int* view_phase_of, int wimg_stride) {
+  // wimg_stride != 0: batched GEMM — image i multiplies weight slice wtap + i*wimg_stride (needs one image per tile)
   // view_phase_of: {H, W} of the tensor whose four stride-2 parity phases the views are (nullptr: all views h x w)
   EncodeTiledFn enc = get_encode();
   if (!enc) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable%s", "cgan_conv_tc");
@@ -312,6 +314,9 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   p.rows_used = p.bw * p.bh * p.bni;
   p.img_n = n; p.img_h = gh; p.img_w = gw;
   p.relu = relu;
+  p.wimg_stride = wimg_stride;
+  if (wimg_stride != 0 && p.bni != 1)
+    return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: batched GEMM needs >= 128 rows per matrix%s", "cgan_conv_tc");
   const int ncols_pad = (ncols + 31) / 32 * 32;
   p.bn = tc_pick_bn(ncols_pad);
   p.cout = ncols;

@@ -437,7 +437,7 @@ int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
   return CGAN_OK;
 }
 
-int cgan_gemm_batched(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda,
+int cgan_gemm_batched_simt(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda,
                       int64_t sa, const float* b, int ldb, int64_t sb, float beta, float* c, int ldc, int64_t sc,
                       int batch) {
   if (!ctx) return CGAN_ERR_ARG;
@@ -461,7 +461,3 @@ int cgan_gemm_batched(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float 
   return launch<M_GEMM, false, true>(ctx, p, batch);
 }
 
-int cgan_gemm(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda, const float* b,
-              int ldb, float beta, float* c, int ldc) {
-  return cgan_gemm_batched(ctx, ta, tb, m, n, k, alpha, a, lda, 0, b, ldb, 0, beta, c, ldc, 0, 1);
-}

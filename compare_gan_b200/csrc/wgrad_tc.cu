@@ -174,10 +174,16 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
       uint32_t r[32];
       tmem_ld32(taddr + (uint32_t)c0, r);       // warp-collective: every lane takes part, stores are predicated
       if (row_ok) {
+        if (co0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(orow + c0 + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + c0 + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {        // Cout zero-padded to the 32-column tile (e.g. the 24-wide attention projections)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (co0 + c0 + j < p.cout) orow[c0 + j] = __uint_as_float(r[j]);
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -209,6 +215,7 @@ bool box32(int n, int h, int w, int* bw, int* bh, int* bni) {
 }
 
 int pick_bn(int ncols) {
+  if (ncols <= 256 && ncols % 4 == 0) return (ncols + 31) / 32 * 32;     // zero-padded tile, stores are masked
   if (ncols % 32) return 0;
   if (ncols <= 256) return ncols;
   if (ncols % 256 == 0) return 256;
@@ -243,7 +250,7 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
   p.kblocks = (int)((long long)d->n * gh * gw / WG_P);
   p.bn = pick_bn(d->cout);
   p.ci_tiles = (d->cin + 127) / 128;
-  p.co_tiles = d->cout / p.bn;
+  p.co_tiles = (d->cout + p.bn - 1) / p.bn;
   p.cin = d->cin; p.cout = d->cout; p.taps_total = d->kh * d->kw;
   // taps: the pixel loop runs over a grid (i, j) of gh x gw cells: the input grid (stride 1, incl. zero-inserted
   // inputs) or the output grid (stride 2); tap (kh,kw) pairs X view `amap` at [i+dh, j+dw] with dY view `bmap` at [i, j]
@@ -333,5 +340,53 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
     wg_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, splits);
     CGAN_LAUNCHED(ctx);
   }
+  return CGAN_OK;
+}
+
+
+// C[i][k1, k2] = sum_pixels A[i][pixel, k1] * B[i][pixel, k2]   (per-image A^T B; attention's d(phi), d(g))
+int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2) {
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  if (!box32(1, h, w, &p.bw, &p.bh, &p.bni) || p.bni != 1)
+    return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: geometry%s", "cgan_wgrad_tc_batched");
+  p.tiles_w = w / p.bw;
+  p.tiles_h = h / p.bh;
+  const int kb_per_image = h * w / WG_P;
+  p.kblocks = kb_per_image * batch;
+  p.kb_per_split = kb_per_image;            // "split" i = image i: its partial tile IS the result C[i]
+  p.bn = pick_bn(k2);
+  if (p.bn == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: columns%s", "cgan_wgrad_tc_batched");
+  p.ci_tiles = (k1 + 127) / 128;
+  p.co_tiles = (k2 + p.bn - 1) / p.bn;
+  p.cin = k1; p.cout = k2; p.taps_total = 1;
+  p.ntaps = 1;
+  p.partial = c;
+  BMaps tm_x, tm_dy;
+  memset(&tm_x, 0, sizeof(tm_x));
+  memset(&tm_dy, 0, sizeof(tm_dy));
+  for (int v = 0; v < 4; ++v) {
+    if (!make_act_map(&tm_x.m[v], a, k1, w, h, batch, k1, (long long)w * k1, (long long)h * w * k1, p.bw, p.bh, p.bni,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_act_map(&tm_dy.m[v], b, k2, w, h, batch, k2, (long long)w * k2, (long long)h * w * k2, p.bw, p.bh, p.bni,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_wgrad_tc_batched");
+  }
+  const size_t stage_bytes = WG_A_BYTES + (size_t)(p.bn / 32) * WG_BOX;
+  p.stages = (int)((110 * 1024) / stage_bytes);
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGAN_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (batch > 65535) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: batch exceeds grid.y%s", "cgan_wgrad_tc_batched");
+  dim3 grid((unsigned)(p.ci_tiles * p.co_tiles), (unsigned)batch);
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, ctx->stream>>>(tm_x, tm_dy, p);
+  CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

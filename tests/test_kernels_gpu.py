@@ -524,3 +524,34 @@ def test_softmax_rows(K, rows, cols):
   assert_close(y.cpu(), ref.detach().numpy(), 1e-6, "softmax")
   (gx,) = tape_grads(K, y, gy, [xd])
   assert_close(gx.cpu(), xt.grad.numpy(), 2e-5, "softmax grad")
+
+
+@pytest.mark.parametrize("bsz,m,kv,ca,cg", [(3, 1024, 256, 24, 96), (2, 4096, 1024, 12, 48), (5, 256, 64, 32, 64)])
+def test_tc_batched_matmul_attention(K, bsz, m, kv, ca, cg):
+  """math_mode 1: the attention products of the non-local block (arch_ops.py:744, 753) and all four of their
+  gradients run as per-image GEMMs on tcgen05: nt / nn through the conv kernel (per-image weight slice), tn through
+  the filter-gradient kernel (one image per CTA row)."""
+  rng = np.random.RandomState(m + kv)
+  theta = rng.randn(bsz, m, ca).astype(np.float32)
+  phi = rng.randn(bsz, kv, ca).astype(np.float32)
+  g = rng.randn(bsz, kv, cg).astype(np.float32)
+  tt, pt, gt = [torch.from_numpy(a).requires_grad_(True) for a in (theta, phi, g)]
+  logits = torch.bmm(tt, pt.transpose(1, 2)) / np.sqrt(ca)
+  ref = torch.bmm(logits, gt)
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  K.set_math_mode(1)
+  try:
+    td, pd, gd = dev(K, theta, True), dev(K, phi, True), dev(K, g, True)
+    n0 = K.lib().launch_count()
+    s = K.affine(K.bmm(td, pd, False, True), 1.0 / np.sqrt(ca))
+    y = K.bmm(s, gd)
+    assert K.lib().launch_count() - n0 == 5, "expected 2 x (operand prep + tcgen05 launch) + scale"
+    assert_close(y.cpu(), ref.detach().numpy(), 2e-3, "attn fwd")
+    n0 = K.lib().launch_count()
+    gth, gph, gg = tape_grads(K, y, gy, [td, pd, gd])
+    assert_close(gth.cpu(), tt.grad.numpy(), 2e-3, "d theta (nn)")
+    assert_close(gph.cpu(), pt.grad.numpy(), 2e-3, "d phi (tn)")
+    assert_close(gg.cpu(), gt.grad.numpy(), 2e-3, "d g (tn)")
+  finally:
+    K.set_math_mode(0)
