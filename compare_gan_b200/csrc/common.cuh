@@ -15,6 +15,7 @@ struct cgan_ctx {
   int math_mode;
   int64_t launches;
   int num_sms;
+  int tc_mt_max;       // tcgen05 kernels: max tiles per CTA sharing one operand tile (tuning knob, env CGAN_TC_MT, default 2)
   char err[512];
 };
 
@@ -91,7 +92,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 // internal (C++ linkage) entry points shared between translation units
 int cgan_conv2d_fwd_simt(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const float* bias, float* y,
-                         int relu = 0);
+                         int relu, int ldy);
 int cgan_conv2d_dgrad_simt(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, float* dx);
 int cgan_upsample1x1_bias_phases(cgan_ctx* ctx, float* out, const float* bias, int n, int oh, int ow, int c);
 int cgan_gemm_batched_simt(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda,

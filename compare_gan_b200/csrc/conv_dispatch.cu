@@ -9,6 +9,9 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
                  const int* view_phase_of = nullptr, int wimg_stride = 0);
+bool cgan_fwd_thin_ok(const cgan_conv_desc* d);
+int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int relu,
+                  int ldy);
 int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
@@ -23,9 +26,19 @@ int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
 int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, int act,
                         float* y) {
   if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, d, "null pointer");
+  return cgan_conv2d_fwd_act_ld(ctx, d, x, w, bias, act, y, d->cout);
+}
+
+int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, int act,
+                           float* y, int ldy) {
+  if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
   CGAN_REQUIRE(ctx, act == 0 || act == CGAN_ACT_RELU, "act must be 0 or CGAN_ACT_RELU");
+  CGAN_REQUIRE(ctx, ldy >= d->cout, "ldy must be >= cout");
+  CGAN_REQUIRE(ctx, ldy == d->cout || !d->upsample, "strided output is not available with upsample");
   const int relu = act == CGAN_ACT_RELU;
+  const bool ld_ok = ldy == d->cout || ldy % 4 == 0;      // the tcgen05 epilogue stores float4
   // a 1x1 kernel over a zero-inserted input (BigGAN's up-sampling shortcut): phase (0,0) is a plain 1x1 conv written to the
   // even pixels, the other three phases are bias only
   if (ctx->math_mode == 1 && d->stride == 1 && d->upsample && d->kh == 1 && d->kw == 1 && d->oh == 2 * d->h &&
@@ -45,7 +58,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
       (!d->upsample || (d->oh == 2 * d->h && d->ow == 2 * d->w)) && d->oh <= (d->upsample ? 2 * d->h : d->h) &&
       d->ow <= (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0)) {
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0) && ld_ok) {
     int oh[32], ow[32], wt[32];
     const long long zero = 0;
     if (!d->upsample) {
@@ -56,7 +69,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
         }
       return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
                           d->w, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                          (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu);
+                          (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu);
     }
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
     // pixel (2i+a, 2j+b) only sees the taps whose virtual input coordinate 2i+a+kh-pad is even -> real pixel i+dh.
@@ -88,7 +101,7 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
   if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 32 && d->h >= 2 && d->w >= 2 &&
       (d->oh - 1) * 2 + d->kh - d->pad_t <= d->h + d->kh && cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cin, d->cout) &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && ld_ok) {
     int oh[32], ow[32], wt[32], am[32], nt = 0;
     const int hw[2] = {d->h, d->w};
     long long voff[4];
@@ -103,9 +116,10 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
     }
     return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
                         (d->h + 1) / 2, (d->w + 1) / 2, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am,
-                        bias, y, (long long)d->oh * d->ow * d->cout, (long long)d->ow * d->cout, d->cout, 0, relu, hw);
+                        bias, y, (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu, hw);
   }
-  return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu);
+  if (cgan_fwd_thin_ok(d)) return cgan_fwd_thin(ctx, d, x, w, bias, y, relu, ldy);
+  return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu, ldy);
 }
 
 int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, float* dx) {

@@ -29,7 +29,8 @@ constexpr int TC_BM = 128;          // output pixels per CTA tile (UMMA M)
 constexpr int TC_BK = 32;           // fp32 channels per k-block: 128 B = one swizzle row
 constexpr int TC_MAX_STAGES = 4;   // the pipeline depth is chosen per launch so that TWO CTAs fit an SM (see host code)
 constexpr int TC_MAX_TAPS = 32;
-constexpr int TC_THREADS = 192;
+constexpr int TC_RWARPS = 8;         // warps 2..9: operand rounding, then the epilogue (two warps per TMEM lane quarter)
+constexpr int TC_THREADS = 64 + 32 * TC_RWARPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB
 
 struct TcParams {
@@ -43,6 +44,8 @@ struct TcParams {
   int wimg_stride;                  // batched GEMM: weight slice = wtap + image * wimg_stride (tiles never span images)
   int bn;                           // UMMA N (multiple of 32, <= 256)
   int stages;                       // smem pipeline depth (2..4)
+  int mt;                           // pixel tiles per CTA sharing one weight tile (accumulators mt x bn TMEM columns)
+  int tiles_total;                  // tiles_w * tiles_h * tiles_n
   int tmem_cols;                    // power of two >= bn
   int cout;                         // valid output channels (row length of `out` pixels)
   long long s_n, s_h, s_w, base;    // output element strides / offset (floats)
@@ -69,10 +72,11 @@ struct AMaps { CUtensorMap m[4]; };
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16KB][B bn*128B] | barriers | tmem ptr
+  // carve: [stages][mt x A 16KB][B bn*128B] | barriers | tmem ptr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.bn * TC_BK * 4;
-  const int stage_bytes = TC_A_BYTES + b_bytes;
+  const int a_bytes = p.mt * TC_A_BYTES;
+  const int stage_bytes = a_bytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* ready_bar = full_bar + p.stages;
   uint64_t* empty_bar = ready_bar + p.stages;
@@ -82,12 +86,17 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.ntaps * p.kchunks;
 
-  // tile origin
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tn = t / p.tiles_h;
-  const int ow0 = tw * p.bw, oh0 = th * p.bh, n0 = tn * p.bni;
+  // this CTA's pixel tiles: [tile0, tile0 + nt_here).  They all multiply the same weight tile, which is therefore
+  // fetched from L2 once per k-block for mt*128 pixels: the kernel is bound by L2->SM bytes per MMA, not by HBM.
+  const int tile0 = blockIdx.x * p.mt;
+  const int nt_here = min(p.mt, p.tiles_total - tile0);
+  auto tile_origin = [&](int i, int& ow0, int& oh0, int& n0) {
+    int t = tile0 + i;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    ow0 = tw * p.bw; oh0 = th * p.bh; n0 = tn * p.bni;
+  };
   const int nb0 = blockIdx.y * p.bn;          // first output channel of this CTA
 
   if (warp == 0 && lane == 0) {
@@ -98,7 +107,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&ready_bar[s], 4);      // one arrive per rounding warp
+        mbar_init(&ready_bar[s], TC_RWARPS);      // one arrive per rounding warp
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(tmem_full_bar, 1);
@@ -123,9 +132,15 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
         const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + TC_A_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.rows_used * TC_BK * 4 + b_bytes));
-        tma_load_4d(sa, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap], oh0 + p.off_h[tap], n0);
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(nt_here * p.rows_used * TC_BK * 4 + b_bytes));
+        int ow0, oh0, n0;
+        for (int i = 0; i < nt_here; ++i) {
+          tile_origin(i, ow0, oh0, n0);
+          tma_load_4d(sa + i * TC_A_BYTES, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap],
+                      oh0 + p.off_h[tap], n0);
+        }
+        tile_origin(0, ow0, oh0, n0);           // batched GEMM: all tiles of a CTA lie in one image (host guarantees)
         tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0, p.wtap[tap] + n0 * p.wimg_stride);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -142,10 +157,13 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_addr = a_addr + TC_A_BYTES;
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int i = 0; i < nt_here; ++i) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {       // UMMA_K = 8 for tf32: 32 B per step inside the 128 B swizzle row
-          umma_tf32(tmem_base, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 8; ++k) {     // UMMA_K = 8 for tf32: 32 B per step inside the 128 B swizzle row
+            umma_tf32(tmem_base + (uint32_t)(i * p.bn), make_desc(a_addr + i * TC_A_BYTES + k * 32), make_desc(b_addr + k * 32),
+                      idesc, (kb | k) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -154,19 +172,23 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ===== warps 2..5: round A to nearest TF32 in smem, then epilogue =====
-    const int q = threadIdx.x - 64;                  // 0..127
+    // ===== warps 2..9: round A to nearest TF32 in smem, then epilogue =====
+    const int q = threadIdx.x - 64;                  // 0..255
     {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        float4* a4 = reinterpret_cast<float4*>(smem + stage * stage_bytes);
+        uint32_t a4 = smem_u32(smem + stage * stage_bytes) + q * 16;
+        for (int tl = 0; tl < nt_here; ++tl, a4 += TC_A_BYTES) {
+          float4 v[TC_A_BYTES / 16 / (32 * TC_RWARPS)];       // 1024 float4 / 256 threads = 4 each, loads first
 #pragma unroll
-        for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {   // 1024 float4 / 128 threads = 8 each
-          float4 v = a4[i * 128 + q];
-          v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
-          a4[i * 128 + q] = v;
+          for (int i = 0; i < TC_A_BYTES / 16 / (32 * TC_RWARPS); ++i) v[i] = lds128(a4 + i * (512 * TC_RWARPS));
+#pragma unroll
+          for (int i = 0; i < TC_A_BYTES / 16 / (32 * TC_RWARPS); ++i) {
+            v[i].x = rna_tf32(v[i].x); v[i].y = rna_tf32(v[i].y); v[i].z = rna_tf32(v[i].z); v[i].w = rna_tf32(v[i].w);
+            sts128(a4 + i * (512 * TC_RWARPS), v[i]);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA) reads
         __syncwarp();
@@ -182,12 +204,18 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     const int wi = m % p.bw;
     const int hi = (m / p.bw) % p.bh;
     const int ni = m / (p.bw * p.bh);
+    for (int tl = 0; tl < nt_here; ++tl) {
+    int ow0, oh0, n0;
+    tile_origin(tl, ow0, oh0, n0);
     // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
     const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
     float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
                   (long long)(ow0 + wi) * p.s_w + nb0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * p.bn);
+    // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
+    const int nchunks = p.bn / 32, csplit = (nchunks + 1) / 2;
+    const int cbeg = (warp - 2) < 4 ? 0 : csplit * 32, cend = (warp - 2) < 4 ? csplit * 32 : p.bn;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t r[32];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -224,6 +252,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
           }
         }
       }
+    }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -269,6 +298,21 @@ inline int tc_pick_bn(int ncols_pad) {     // largest UMMA N <= 256 (multiple of
   for (int b = 256; b >= 32; b -= 32)
     if (ncols_pad % b == 0) return b;
   return 0;
+}
+
+// Few pixel tiles (8x8 / 17x17 Inception stages at batch 64, the 4x4 GAN stages): the widest column tile would leave SMs
+// idle, so the columns are split further (>= 64) until there is at least one CTA per SM.  The K order is unchanged, so
+// the result is bit-identical to the wide tile's.
+inline int tc_pick_bn_occupancy(int ncols_pad, long long tiles_m, int sms) {
+  int best = tc_pick_bn(ncols_pad);
+  if (best == 0 || tiles_m * (ncols_pad / best) >= sms) return best;
+  int pick = best;
+  for (int b = best - 32; b >= 64; b -= 32) {
+    if (ncols_pad % b) continue;
+    pick = b;
+    if (tiles_m * (ncols_pad / b) >= sms) break;
+  }
+  return pick;
 }
 
 }  // namespace
@@ -318,7 +362,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   if (wimg_stride != 0 && p.bni != 1)
     return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: batched GEMM needs >= 128 rows per matrix%s", "cgan_conv_tc");
   const int ncols_pad = (ncols + 31) / 32 * 32;
-  p.bn = tc_pick_bn(ncols_pad);
+  p.bn = tc_pick_bn_occupancy(ncols_pad, (long long)p.tiles_w * p.tiles_h * tiles_n, ctx->num_sms);
   p.cout = ncols;
   p.s_n = s_n; p.s_h = s_h; p.s_w = s_w; p.base = base;
   p.out = out;
@@ -361,19 +405,30 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   }
   // Two CTAs per SM (each owns 256 of the 512 TMEM columns): one CTA's epilogue and prologue overlap the other's main
   // loop, which matters for the short-K convolutions (3x3x128: 36 k-blocks).  ~110 KB of smem each.
-  const size_t stage_bytes = TC_A_BYTES + (size_t)p.bn * TC_BK * 4;
-  p.stages = (int)((110 * 1024) / stage_bytes);
+  // Pixel tiles per CTA: with mt = 2 the weight tile is fetched once for 256 pixels, which cuts the L2->SM bytes per MMA by
+  // a third (bn = 256: 96 -> 64 B/clk/SM against a ~43 B/clk/SM L2 budget).  bn = 256 then fills the TMEM (one CTA per SM),
+  // bn <= 128 keeps two CTAs per SM.  Only when enough CTAs remain to fill the machine.
+  const long long tiles_total = (long long)p.tiles_w * p.tiles_h * tiles_n;
+  const int ncol_tiles = ncols_pad / p.bn;
+  p.tiles_total = (int)tiles_total;
+  p.mt = 1;
+  if (ctx->tc_mt_max >= 2 && tiles_total * ncol_tiles >= 4ll * ctx->num_sms &&
+      (wimg_stride == 0 || (p.tiles_w * p.tiles_h) % 2 == 0))
+    p.mt = 2;
+  const bool two_ctas = p.mt * p.bn <= 256;
+  const size_t stage_bytes = (size_t)p.mt * TC_A_BYTES + (size_t)p.bn * TC_BK * 4;
+  p.stages = (int)(((two_ctas ? 110 : 220) * 1024) / stage_bytes);
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  while (p.tmem_cols < p.mt * p.bn) p.tmem_cols *= 2;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * tiles_n), (unsigned)(ncols_pad / p.bn));
+  dim3 grid((unsigned)((tiles_total + p.mt - 1) / p.mt), (unsigned)ncol_tiles);
   conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_as, tm_b, p);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;

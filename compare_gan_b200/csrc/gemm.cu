@@ -368,7 +368,7 @@ GP conv_gp(const cgan_conv_desc* d) {
 }  // namespace
 
 int cgan_conv2d_fwd_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                         int relu) {
+                         int relu, int ldy) {
   int rc = check_desc(ctx, d);
   if (rc) return rc;
   GP p = conv_gp(d);
@@ -377,7 +377,7 @@ int cgan_conv2d_fwd_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x,
   p.K = d->kh * d->kw * d->cin;
   p.A = x; p.B = w; p.C = y; p.bias = bias;
   p.relu = relu;
-  p.ldc = d->cout;
+  p.ldc = ldy;
   p.vecA = (d->cin % 8 == 0) && al16(x);
   p.vecB = (d->cout % 8 == 0) && al16(w);
   return launch<M_FWD, true, false>(ctx, p, 1);

@@ -82,20 +82,33 @@ __global__ void colreduce_kernel(F f, float* __restrict__ partial, long long row
   }
 }
 
-// out_v[g*C + c] = scale * sum_chunk partial
+// out_v[g*C + c] = scale * sum_chunk partial.  Block = 32 columns x 8 chunk lanes: the (up to ~150) partials of a column
+// are summed by 8 threads in parallel and combined in a fixed order, instead of one long chain of dependent loads.
 template <int NV>
 __global__ void colreduce_final_kernel(const float* __restrict__ partial, int groups, int chunks, int C, float scale,
                                        float* out0, float* out1) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)groups * C) return;
-  int g = (int)(i / C), c = (int)(i % C);
+  __shared__ float red[NV][8][32];
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  const bool ok = i < (long long)groups * C;
+  const int g = ok ? (int)(i / C) : 0, c = ok ? (int)(i % C) : 0;
   float* outs[2] = {out0, out1};
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    if (!outs[v]) continue;
     float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(((long long)g * chunks + k) * NV + v) * C + c];
-    outs[v][i] = s * scale;
+    if (ok && outs[v])
+      for (int k = threadIdx.y; k < chunks; k += 8) s += partial[(((long long)g * chunks + k) * NV + v) * C + c];
+    red[v][threadIdx.y][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!outs[v]) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += red[v][y][threadIdx.x];
+      outs[v][i] = s * scale;
+    }
   }
 }
 
@@ -121,7 +134,7 @@ int colreduce(cgan_ctx* ctx, F f, int groups, long long rows_per_group, int C, f
   colreduce_kernel<F, NV><<<grid, block, 0, ctx->stream>>>(f, partial, rows_per_group, C, rpc, (int)chunks);
   CGAN_LAUNCHED(ctx);
   long long tot = (long long)groups * C;
-  colreduce_final_kernel<NV><<<cdiv(tot, 256), 256, 0, ctx->stream>>>(partial, groups, (int)chunks, C, scale, out0, out1);
+  colreduce_final_kernel<NV><<<cdiv(tot, 32), dim3(32, 8), 0, ctx->stream>>>(partial, groups, (int)chunks, C, scale, out0, out1);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

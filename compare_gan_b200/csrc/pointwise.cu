@@ -24,6 +24,8 @@ int cgan_ctx_create(cgan_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CGAN_ERR_CUDA; }
   c->num_sms = prop.multiProcessorCount;
+  c->tc_mt_max = 2;
+  if (const char* e = getenv("CGAN_TC_MT")) c->tc_mt_max = atoi(e) >= 2 ? 2 : 1;
   c->stream = 0;
   *out = c;
   return CGAN_OK;

@@ -33,7 +33,8 @@ __device__ __forceinline__ long long thin_in_offset(const ThinParams& p, int n, 
 template <int M>
 __global__ void wgrad_thin_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial,
                                       ThinParams p) {
-  __shared__ float xs[THIN_PB][M + 1];
+  constexpr int M4 = (M + 3) / 4 * 4;       // rows are read back as float4 broadcasts: 4x fewer LDS than FMAs
+  __shared__ __align__(16) float xs[THIN_PB][M4];
   const cgan_conv_desc& d = p.d;
   const int co = blockIdx.y * blockDim.x + threadIdx.x;
   const long long p0 = (long long)blockIdx.x * p.pix_per_block;
@@ -44,23 +45,26 @@ __global__ void wgrad_thin_cin_kernel(const float* __restrict__ x, const float* 
   for (long long pb = p0; pb < p1; pb += THIN_PB) {
     const int nb = (int)min((long long)THIN_PB, p1 - pb);
     __syncthreads();
-    for (int e = threadIdx.x; e < nb * M; e += blockDim.x) {
-      int pi = e / M, m = e % M;
+    for (int e = threadIdx.x; e < nb * M4; e += blockDim.x) {
+      int pi = e / M4, m = e % M4;
       long long pix = pb + pi;
       int ow = (int)(pix % d.ow);
       long long t = pix / d.ow;
       int oh = (int)(t % d.oh);
       int n = (int)(t / d.oh);
       int ci = m % d.cin, tap = m / d.cin;
-      long long off = thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw);
+      long long off = m < M ? thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw) : -1;
       xs[pi][m] = off < 0 ? 0.f : x[off + ci];
     }
     __syncthreads();
     if (co < d.cout) {
       for (int pi = 0; pi < nb; ++pi) {
         float g = dy[(pb + pi) * d.cout + co];
+        float xv[M4];
 #pragma unroll
-        for (int m = 0; m < M; ++m) acc[m] = fmaf(xs[pi][m], g, acc[m]);
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m] = fmaf(xv[m], g, acc[m]);
       }
     }
   }
@@ -123,6 +127,53 @@ __global__ void wgrad_thin_cout_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// Forward of the same image-side layers (3 input channels: the first conv of every discriminator and of Inception):
+// 27 x Cout per pixel is far below a tensor-core tile, so thread = output channel with the filter column in registers,
+// the receptive fields of THIN_PB pixels staged in smem and read back as float4 broadcasts; stores are 128-byte rows.
+template <int M4>
+__global__ void fwd_thin_cin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                    float* __restrict__ y, ThinParams p, int m_real, int relu, int ldy) {
+  __shared__ __align__(16) float xs[THIN_PB][M4];
+  const cgan_conv_desc& d = p.d;
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < d.cout;
+  float wr[M4];
+#pragma unroll
+  for (int m = 0; m < M4; ++m) wr[m] = (co_ok && m < m_real) ? w[(long long)m * d.cout + co] : 0.f;
+  const float b = (co_ok && bias) ? bias[co] : 0.f;
+  const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+  const long long p1 = min(p.npix, p0 + p.pix_per_block);
+  for (long long pb = p0; pb < p1; pb += THIN_PB) {
+    const int nb = (int)min((long long)THIN_PB, p1 - pb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * M4; e += blockDim.x) {
+      int pi = e / M4, m = e % M4;
+      long long pix = pb + pi;
+      int ow = (int)(pix % d.ow);
+      long long t = pix / d.ow;
+      int oh = (int)(t % d.oh);
+      int n = (int)(t / d.oh);
+      int ci = m % d.cin, tap = m / d.cin;
+      long long off = m < m_real ? thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw) : -1;
+      xs[pi][m] = off < 0 ? 0.f : x[off + ci];
+    }
+    __syncthreads();
+    if (co_ok) {
+      for (int pi = 0; pi < nb; ++pi) {
+        float xv[M4];
+#pragma unroll
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < M4; ++m) acc = fmaf(xv[m], wr[m], acc);
+        acc += b;
+        if (relu) acc = fmaxf(acc, 0.f);
+        y[(pb + pi) * ldy + co] = acc;
+      }
+    }
+  }
+}
+
 __global__ void thin_reduce_kernel(float* __restrict__ out, const float* __restrict__ part, long long n, int blocks) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -171,6 +222,35 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
   }
   CGAN_LAUNCHED(ctx);
   thin_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, blocks);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+
+bool cgan_fwd_thin_ok(const cgan_conv_desc* d) {
+  return d->cin <= 4 && d->kh * d->kw * d->cin <= THIN_MAX_M && d->cout >= 16;
+}
+
+int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int relu,
+                  int ldy) {
+  ThinParams p;
+  p.d = *d;
+  p.vh = d->upsample ? 2 * d->h : d->h;
+  p.vw = d->upsample ? 2 * d->w : d->w;
+  p.npix = (long long)d->n * d->oh * d->ow;
+  const int threads = d->cout >= 128 ? 128 : ((d->cout + 31) / 32 * 32);
+  const int co_blocks = (d->cout + threads - 1) / threads;
+  long long want_blocks = 16ll * ctx->num_sms * 128 / threads / co_blocks;     // ~16 resident warps' worth of CTAs per SM, x2 waves
+  if (want_blocks < 1) want_blocks = 1;
+  long long ppb = (p.npix + want_blocks - 1) / want_blocks;
+  ppb = (ppb + THIN_PB - 1) / THIN_PB * THIN_PB;
+  p.pix_per_block = ppb;
+  dim3 grid((unsigned)((p.npix + ppb - 1) / ppb), (unsigned)co_blocks);
+  const int m = d->kh * d->kw * d->cin;
+  if (m <= 12) fwd_thin_cin_kernel<12><<<grid, threads, 0, ctx->stream>>>(x, w, bias, y, p, m, relu, ldy);
+  else if (m <= 20) fwd_thin_cin_kernel<20><<<grid, threads, 0, ctx->stream>>>(x, w, bias, y, p, m, relu, ldy);
+  else if (m <= 28) fwd_thin_cin_kernel<28><<<grid, threads, 0, ctx->stream>>>(x, w, bias, y, p, m, relu, ldy);
+  else fwd_thin_cin_kernel<36><<<grid, threads, 0, ctx->stream>>>(x, w, bias, y, p, m, relu, ldy);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

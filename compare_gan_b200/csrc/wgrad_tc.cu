@@ -25,7 +25,8 @@ constexpr int WG_MAX_STAGES = 4;
 constexpr int WG_P = 32;                 // pixels per k-block
 constexpr int WG_BOX = WG_P * 128;       // 4 KB: 32 pixel rows x 32 channels fp32
 constexpr int WG_A_BYTES = 4 * WG_BOX;   // 128 input channels
-constexpr int WG_THREADS = 192;
+constexpr int WG_RWARPS = 8;         // warps 2..9: operand rounding, then the epilogue (two warps per TMEM lane quarter)
+constexpr int WG_THREADS = 64 + 32 * WG_RWARPS;
 constexpr int WG_MAX_TAPS = 16;
 
 struct WgParams {
@@ -35,7 +36,8 @@ struct WgParams {
   int kblocks, kb_per_split;
   int ci_tiles, co_tiles, bn;
   int cin, cout, taps_total;
-  int stages, tmem_cols;                 // pipeline depth chosen so that two CTAs share an SM; TMEM columns = pow2 >= bn
+  int stages, tmem_cols;                 // pipeline depth chosen so that two CTAs share an SM; TMEM columns = pow2 >= mt*bn
+  int mt;                                // (tap, ci-tile) units per CTA that share one dY tile (mt accumulators in TMEM)
   float* partial;                        // [split][taps_total][cin][cout]
 };
 
@@ -58,7 +60,8 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = (p.bn / 32) * WG_BOX;
-  const int stage_bytes = WG_A_BYTES + b_bytes;
+  const int a_bytes = p.mt * WG_A_BYTES;
+  const int stage_bytes = a_bytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* ready_bar = full_bar + p.stages;
   uint64_t* empty_bar = ready_bar + p.stages;
@@ -66,15 +69,18 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work units (tap, ci tile); this CTA owns units [u0, u0 + nu) — they all contract against the same dY tile, which is
+  // fetched from L2 once per k-block for all of them (the kernel is bound by L2->SM bytes per MMA)
   int t = blockIdx.x;
-  const int co_t = t % p.co_tiles; t /= p.co_tiles;
-  const int ci_t = t % p.ci_tiles;
-  const int tap = t / p.ci_tiles;
+  const int co_t = t % p.co_tiles;
+  const int u0 = (t / p.co_tiles) * p.mt;
+  const int nu = min(p.mt, p.ntaps * p.ci_tiles - u0);
+  const int tap = u0 / p.ci_tiles;               // unit 0's tap: selects the dY view (equal for all units, host-checked)
   const int split = blockIdx.y;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
   const int num_kb = kb1 - kb0;                 // >= 1 by construction
-  const int ci0 = ci_t * 128, co0 = co_t * p.bn;
+  const int co0 = co_t * p.bn;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x.m[p.amap[tap]]) : "memory");
@@ -84,7 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&ready_bar[s], 4);
+        mbar_init(&ready_bar[s], WG_RWARPS);
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(tmem_full_bar, 1);
@@ -102,8 +108,6 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
   if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* mb = &tm_dy.m[p.bmap[tap]];
-      const CUtensorMap* ma = &tm_x.m[p.amap[tap]];
-      const int dh = p.off_h[tap], dw = p.off_w[tap];
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -114,10 +118,16 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bni;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + WG_A_BYTES;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(nu * WG_A_BYTES + b_bytes));
+        for (int i = 0; i < nu; ++i) {
+          const int u = u0 + i, utap = u / p.ci_tiles, ci0 = (u % p.ci_tiles) * 128;
+          const CUtensorMap* ma = &tm_x.m[p.amap[utap]];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * WG_BOX, ma, &full_bar[stage], ci0 + g * 32, w0 + dw, h0 + dh, n0);
+          for (int g = 0; g < 4; ++g)
+            tma_load_4d(sa + i * WG_A_BYTES + g * WG_BOX, ma, &full_bar[stage], ci0 + g * 32, w0 + p.off_w[utap],
+                        h0 + p.off_h[utap], n0);
+        }
         for (int g = 0; g < p.bn / 32; ++g) tma_load_4d(sb + g * WG_BOX, mb, &full_bar[stage], co0 + g * 32, w0, h0, n0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -133,10 +143,13 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_addr = a_addr + WG_A_BYTES;
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int i = 0; i < nu; ++i) {
 #pragma unroll
-        for (int k = 0; k < WG_P / 8; ++k)          // 8 pixel rows (1024 B) per MMA
-          umma_tf32(tmem_base, make_desc_mn(a_addr + k * 1024), make_desc_mn(b_addr + k * 1024), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < WG_P / 8; ++k)          // 8 pixel rows (1024 B) per MMA
+            umma_tf32(tmem_base + (uint32_t)(i * p.bn), make_desc_mn(a_addr + i * WG_A_BYTES + k * 1024),
+                      make_desc_mn(b_addr + k * 1024), idesc, (kb | k) ? 1u : 0u);
+        }
         umma_commit(&empty_bar[stage]);
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }
@@ -151,11 +164,13 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
       const int n4 = stage_bytes / 16;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        float4* s4 = reinterpret_cast<float4*>(smem + stage * stage_bytes);
-        for (int i = q; i < n4; i += 128) {
-          float4 v = s4[i];
+        const uint32_t s4 = smem_u32(smem + stage * stage_bytes);
+        // stage_bytes is a multiple of 4 KB (32-pixel boxes of 128 B rows): 256 threads x 16 B per sweep
+#pragma unroll 4
+        for (int i = q; i < n4; i += 32 * WG_RWARPS) {
+          float4 v = lds128(s4 + i * 16);
           v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
-          s4[i] = v;
+          sts128(s4 + i * 16, v);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -167,10 +182,15 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // ci within the tile
-    float* orow = p.partial + (((long long)split * p.taps_total + p.wtap[tap]) * p.cin + ci0 + row) * p.cout + co0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int i = 0; i < nu; ++i) {
+    const int u = u0 + i, utap = u / p.ci_tiles, ci0 = (u % p.ci_tiles) * 128;
+    float* orow = p.partial + (((long long)split * p.taps_total + p.wtap[utap]) * p.cin + ci0 + row) * p.cout + co0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(i * p.bn);
     const bool row_ok = ci0 + row < p.cin;       // the last ci tile may hang over Cin (TMA zero-filled those channels)
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+    // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
+    const int nchunks = p.bn / 32, csplit = (nchunks + 1) / 2;
+    const int cbeg = (warp - 2) < 4 ? 0 : csplit * 32, cend = (warp - 2) < 4 ? csplit * 32 : p.bn;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + (uint32_t)c0, r);       // warp-collective: every lane takes part, stores are predicated
       if (row_ok) {
@@ -185,6 +205,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
             if (co0 + c0 + j < p.cout) orow[c0 + j] = __uint_as_float(r[j]);
         }
       }
+    }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -273,9 +294,15 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
       ++nt;
     }
   p.ntaps = nt;
-  long long tiles = (long long)p.ci_tiles * p.co_tiles * nt;
-  // two CTAs' worth of work per SM, rounded DOWN so the grid never spills a few CTAs into an extra wave
-  int splits = (int)((2ll * ctx->num_sms) / tiles);
+  // two (tap, ci-tile) units per CTA when they read the same dY view: dY is then fetched once per k-block for both
+  const int units = p.ci_tiles * nt;
+  bool same_b = true;
+  for (int i = 1; i < nt; ++i) same_b = same_b && p.bmap[i] == p.bmap[0];
+  p.mt = (ctx->tc_mt_max >= 2 && same_b && units >= 2) ? 2 : 1;
+  const bool two_ctas = p.mt * p.bn <= 256;      // TMEM: mt*bn accumulator columns per CTA, 512 per SM
+  long long tiles = (long long)p.co_tiles * ((units + p.mt - 1) / p.mt);
+  // one wave of CTAs, rounded DOWN so the grid never spills a few CTAs into an extra wave
+  int splits = (int)(((two_ctas ? 2ll : 1ll) * ctx->num_sms) / tiles);
   int max_splits = p.kblocks / 8 > 0 ? p.kblocks / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -321,12 +348,12 @@ int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
     }
     if (!ok) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(dy) failed%s", "cgan_wgrad_tc");
   }
-  const size_t stage_bytes = WG_A_BYTES + (size_t)(p.bn / 32) * WG_BOX;
-  p.stages = (int)((110 * 1024) / stage_bytes);
+  const size_t stage_bytes = (size_t)p.mt * WG_A_BYTES + (size_t)(p.bn / 32) * WG_BOX;
+  p.stages = (int)(((two_ctas ? 110 : 220) * 1024) / stage_bytes);
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.bn) p.tmem_cols *= 2;
+  while (p.tmem_cols < p.mt * p.bn) p.tmem_cols *= 2;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -361,6 +388,7 @@ int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* 
   p.co_tiles = (k2 + p.bn - 1) / p.bn;
   p.cin = k1; p.cout = k2; p.taps_total = 1;
   p.ntaps = 1;
+  p.mt = 1;
   p.partial = c;
   BMaps tm_x, tm_dy;
   memset(&tm_x, 0, sizeof(tm_x));

@@ -103,6 +103,18 @@ def walk_convs(spec=SPEC, cin=3, prefix=""):
   return out
 
 
+def _channels(items, c):
+  """Output channels of a branch given its input channels."""
+  for it in items:
+    if it[0] == "conv":
+      c = it[2]
+    elif it[0] == "split":
+      c = sum(_channels(br, c) for br in it[1])
+    elif it[0] == "block":
+      c = sum(_channels(br, c) for br in it[2])
+  return c
+
+
 def synthetic_weights(seed=0):
   """Deterministic He-normal weights (BN folded into a small bias) for the exact topology."""
   rng = np.random.RandomState(seed)
@@ -149,19 +161,30 @@ class InceptionV3(object):
     self.host_weights = weights
     self.w = {k: K.from_numpy(v) for k, v in weights.items()}
 
-  def _seq(self, items, x, pre):
-    for it in items:
+  def _seq(self, items, x, pre, sink=None, off=0):
+    """Runs `items` on x.  With `sink` the LAST item stores into channels [off, ...) of the sink (the enclosing concat):
+    convolutions write their slice directly (strided epilogue), pooling branches are copied in."""
+    for i, it in enumerate(items):
+      last = sink is not None and i == len(items) - 1
       if it[0] == "conv":
         _, name, _, _, _, stride, padding = it
         x = K.conv2d_relu(x, self.w["inception/%s%s/kernel" % (pre, name)], self.w["inception/%s%s/bias" % (pre, name)],
-                          stride=stride, padding=padding)
+                          stride=stride, padding=padding, sink=sink if last else None, sink_off=off)
       elif it[0] == "pool":
         _, mode, k, s, pad = it
         x = K.pool2d(x, k, s, pad, mode)
-      elif it[0] == "split":
-        x = K.concat_channels([self._seq(br, x, pre) for br in it[1]])
-      elif it[0] == "block":
-        x = K.concat_channels([self._seq(br, x, pre + it[1] + "/") for br in it[2]])
+        if last:
+          sink.put(x, off)
+          x = None
+      elif it[0] in ("split", "block"):
+        branches, bpre = (it[1], pre) if it[0] == "split" else (it[2], pre + it[1] + "/")
+        cin = x.shape[3]
+        widths = [_channels(br, cin) for br in branches]
+        tgt, base = (sink, off) if last else (K.ChannelSink(sum(widths)), 0)
+        for br, wd in zip(branches, widths):
+          self._seq(br, x, bpre, tgt, base)
+          base += wd
+        x = None if last else tgt.buf
     return x
 
   def __call__(self, images):

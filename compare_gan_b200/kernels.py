@@ -179,14 +179,41 @@ def _conv_fwd_raw(d, x, w, bias):
   return y
 
 
-def conv2d_relu(x, w, bias, stride=1, padding="SAME"):
-  """relu(conv2d(x, w) + bias) in one kernel; inference only (no tape)."""
+def conv2d_relu(x, w, bias, stride=1, padding="SAME", sink=None, sink_off=0):
+  """relu(conv2d(x, w) + bias) in one kernel; inference only (no tape).  With `sink` (a ChannelSink) the result is
+  stored straight into channels [sink_off, sink_off + cout) of the wider NHWC tensor (tf.concat(axis=3) without the
+  copy) and None is returned."""
   n, h, ww, cin = x.shape
   kh, kw, _, cout = w.shape
   d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, False, padding)
+  b = None if bias is None else bias.ptr
+  if sink is not None:
+    buf = sink.buffer(d.n, d.oh, d.ow)
+    _call("conv2d_fwd_act_ld", ctypes.byref(d), x.ptr, w.ptr, b, ACT_RELU, buf.ptr + 4 * sink_off, sink.channels)
+    return None
   y = empty(d.n, d.oh, d.ow, d.cout)
-  _call("conv2d_fwd_act", ctypes.byref(d), x.ptr, w.ptr, None if bias is None else bias.ptr, ACT_RELU, y.ptr)
+  _call("conv2d_fwd_act", ctypes.byref(d), x.ptr, w.ptr, b, ACT_RELU, y.ptr)
   return y
+
+
+class ChannelSink(object):
+  """The output of a channel concatenation, allocated when the first producer knows the spatial size."""
+
+  def __init__(self, channels):
+    self.channels, self.buf = channels, None
+
+  def buffer(self, n, h, w):
+    if self.buf is None:
+      self.buf = empty(n, h, w, self.channels)
+    elif self.buf.shape[:3] != (n, h, w):
+      raise ValueError("concat: branch output %s does not match %s" % ((n, h, w), self.buf.shape[:3]))
+    return self.buf
+
+  def put(self, t, off):
+    """Copies an already materialised branch (the pooling branches) into its slice."""
+    n, h, w, c = t.shape
+    buf = self.buffer(n, h, w)
+    _call("copy2d", buf.ptr, self.channels, off, t.ptr, c, 0, n * h * w, c)
 
 
 def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME"):

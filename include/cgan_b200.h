@@ -74,6 +74,11 @@ int cgan_conv2d_fwd(cgan_ctx*, const cgan_conv_desc*, const float* x, const floa
  * (tfgan.eval.run_inception, eval_utils.py:165-175); inference only. */
 int cgan_conv2d_fwd_act(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const float* bias, int act,
                         float* y);
+/* same, writing output pixel p's `cout` channels at y + p*ldy (ldy >= cout): the convolution stores straight into its
+ * channel slice of a wider NHWC tensor, which is tf.concat(axis=3) of the Inception "mixed" blocks without the copy
+ * (tfgan.eval.run_inception, eval_utils.py:165-175).  Not available with desc.upsample. */
+int cgan_conv2d_fwd_act_ld(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const float* bias, int act,
+                           float* y, int ldy);
 /* dx = d/dx of the above (TF Conv2DBackpropInput); this is also tf.nn.conv2d_transpose, arch_ops.py:588-589. */
 int cgan_conv2d_dgrad(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w_hwio, float* dx);
 /* dw = d/dw (TF Conv2DBackpropFilter); deterministic split-K. */

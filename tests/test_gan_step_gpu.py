@@ -44,9 +44,12 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
   for c in range(n_cycles):
     imgs, zs, labels, sampled, alphas = make_inputs(rng, k, batch, image_shape, z_dim, num_classes, z_normal, gp)
     eng.set_inputs(imgs, zs, labels, sampled, alphas)
-    eng.run_cycle()
-    dl, gl = eng.read_losses()
-    odl, ogl = orc.cycle(imgs, zs, labels, sampled, alphas)
+    with ReluSigns() as signs:      # (leaky-)ReLU inputs within rounding distance of zero: see ReluSigns
+      eng.run_cycle()
+      dl, gl = eng.read_losses()
+      signs.start_oracle()
+      odl, ogl = orc.cycle(imgs, zs, labels, sampled, alphas)
+      flips = signs.flips()
     tol = loss_tol * (1 + 2 * c)     # trajectories drift apart slowly through Adam's sign amplification
     for a, b in zip(dl, odl):
       assert abs(a - b) <= tol * max(1.0, abs(b)), ("d_loss", c, dl, odl)
@@ -54,7 +57,7 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
     if c == 0:
       # D gradients: identical weights on both sides -> tight.  G gradients are taken AFTER the D updates, whose
       # Adam sign-amplified rounding noise perturbs D slightly -> loose here, tight in _frozen_d_gradients().
-      compare_grads(eng, orc, grad_tol, g_tol=5e-2)
+      compare_grads(eng, orc, grad_tol, g_tol=5e-2, flips=flips)
   assert eng.global_step == n_cycles and eng.global_step_disc == n_cycles * k     # modular_gan_test.py:175-177
   return compare_states(eng, orc, {"generator": g_lr, "discriminator": d_lr},
                         {"generator": n_cycles, "discriminator": n_cycles * k})

@@ -3,6 +3,7 @@ Tolerances: fp32 SIMT path 2e-5 rel-L2 (reduction order only); stated per test o
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import gan as ogan
 from oracle import metrics as ometrics
@@ -555,3 +556,36 @@ def test_tc_batched_matmul_attention(K, bsz, m, kv, ca, cg):
     assert_close(gg.cpu(), gt.grad.numpy(), 2e-3, "d g (tn)")
   finally:
     K.set_math_mode(0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,h,cin,cout,k,stride,pad", [(64, 8, 64, 96, 3, 1, "SAME"), (8, 17, 32, 64, 3, 2, "VALID"),
+                                                       (4, 35, 48, 64, 5, 1, "SAME"), (64, 8, 128, 320, 1, 1, "SAME"),
+                                                       (4, 35, 3, 32, 3, 2, "VALID"), (16, 32, 3, 128, 3, 1, "SAME")])
+def test_conv_into_channel_slice(K, mode, n, h, cin, cout, k, stride, pad):
+  """cgan_conv2d_fwd_act_ld: the convolution stores into its channel slice of a wider NHWC tensor (the Inception
+  concat without the copy); the neighbouring channels stay untouched.  The 8x8 cases also take the narrow column tiles
+  the occupancy rule picks when there are fewer pixel tiles than SMs; the 3-channel cases run the thin-Cin kernel."""
+  rng = np.random.RandomState(n + h + cin)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+  if pad == "SAME":
+    ref = T.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), stride) + torch.from_numpy(b)
+  else:
+    ref = F.conv2d(xt, torch.from_numpy(w).permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1) + torch.from_numpy(b)
+  ref = torch.relu(ref).numpy()
+  K.set_math_mode(mode)
+  try:
+    sink = K.ChannelSink(cout + 40)
+    buf = sink.buffer(n, ref.shape[1], ref.shape[2])
+    K.fill_(buf, 7.0)
+    assert K.conv2d_relu(dev(K, x), dev(K, w), dev(K, b), stride=stride, padding=pad, sink=sink, sink_off=24) is None
+    whole = K.conv2d_relu(dev(K, x), dev(K, w), dev(K, b), stride=stride, padding=pad).cpu()
+  finally:
+    K.set_math_mode(0)
+  out = buf.cpu()
+  assert_close(out[..., 24:24 + cout], ref, 1e-3 if mode else TOL, "sliced conv")
+  np.testing.assert_array_equal(out[..., 24:24 + cout], whole)       # same kernel, same K order: bit-identical
+  assert (out[..., :24] == 7.0).all() and (out[..., 24 + cout:] == 7.0).all()
