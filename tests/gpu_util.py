@@ -190,7 +190,7 @@ def compare_grads(eng, orc, tol=1e-3, g_tol=None, orc64=None, flips=0):
   return worst
 
 
-def compare_states(eng, orc, lr, updates, frac=0.35, skip=()):
+def compare_states(eng, orc, lr, updates, frac=0.35, skip=(), state_tol=2e-3):
   """Weights after Adam.  Adam's first steps move every element by ~lr*sign(g): elements whose gradient is at the
   rounding-noise level flip sign in ANY two implementations, so the criterion is in units of the step size:
   rms(w - w_ref) <= frac * lr * updates per tensor; tensors whose reference gradient is pure noise are skipped."""

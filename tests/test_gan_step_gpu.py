@@ -41,6 +41,7 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
                  g_lr=2e-4, d_lr=None, grad_tol=1e-3, loss_tol=1e-3):
   rng = np.random.RandomState(5)
   d_lr = g_lr if d_lr is None else d_lr
+  total_flips = 0
   for c in range(n_cycles):
     imgs, zs, labels, sampled, alphas = make_inputs(rng, k, batch, image_shape, z_dim, num_classes, z_normal, gp)
     eng.set_inputs(imgs, zs, labels, sampled, alphas)
@@ -50,6 +51,7 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
       signs.start_oracle()
       odl, ogl = orc.cycle(imgs, zs, labels, sampled, alphas)
       flips = signs.flips()
+    total_flips += flips
     tol = loss_tol * (1 + 2 * c)     # trajectories drift apart slowly through Adam's sign amplification
     for a, b in zip(dl, odl):
       assert abs(a - b) <= tol * max(1.0, abs(b)), ("d_loss", c, dl, odl)
@@ -59,8 +61,10 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
       # Adam sign-amplified rounding noise perturbs D slightly -> loose here, tight in _frozen_d_gradients().
       compare_grads(eng, orc, grad_tol, g_tol=5e-2, flips=flips)
   assert eng.global_step == n_cycles and eng.global_step_disc == n_cycles * k     # modular_gan_test.py:175-177
+  # a flipped (leaky-)ReLU mask sends the two Adam trajectories apart by a fraction of the step size, which the BN
+  # moving statistics then see: the tight bound on the non-trainable state only holds when the masks agreed
   return compare_states(eng, orc, {"generator": g_lr, "discriminator": d_lr},
-                        {"generator": n_cycles, "discriminator": n_cycles * k})
+                        {"generator": n_cycles, "discriminator": n_cycles * k}, state_tol=2e-3 if total_flips == 0 else 2e-2)
 
 
 def _frozen_d_gradients(batch, image_shape, z_dim, k, num_classes=0, gp=False, z_normal=False, tol=1e-3, **pair_kw):
