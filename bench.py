@@ -236,8 +236,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": dom["tflops"] / pk["bf16_tflops"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full`
-                     # capture (profiles/r1_ncu_full_tc_kernels.csv): 271 MB + 220 MB vs 2 x 268 MB algorithmic
-                     "traffic": 4.91e8 if (mm and b == 256) else None,
+                     # capture (profiles/r1_ncu_full_tc_kernels.csv): 283 MB + 216 MB vs 2 x 268 MB algorithmic
+                     "traffic": 4.99e8 if (mm and b == 256) else None,
                      "kernel": dom["kernel"], "kernel_ms": dom["ms"],
                      "peak_kind": "%s dense bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 tensor peak is nominally half of it"
                                   % pk["source"],

@@ -18,6 +18,17 @@ struct ThinParams {
   long long pix_per_block;
 };
 
+// pixel index -> (image, row, column) of the output grid.  The hosts below only launch with npix < 2^31, so this is
+// 32-bit unsigned arithmetic (a 64-bit division costs ~10x as many instructions and dominated the staging loops).
+__device__ __forceinline__ void thin_pixel(long long pix64, const cgan_conv_desc& d, int& n, int& oh, int& ow) {
+  const unsigned pix = (unsigned)pix64;
+  const unsigned t = pix / (unsigned)d.ow;
+  ow = (int)(pix - t * (unsigned)d.ow);
+  const unsigned nn = t / (unsigned)d.oh;
+  oh = (int)(t - nn * (unsigned)d.oh);
+  n = (int)nn;
+}
+
 __device__ __forceinline__ long long thin_in_offset(const ThinParams& p, int n, int oh, int ow, int kh, int kw) {
   const cgan_conv_desc& d = p.d;
   int vh = oh * d.stride + kh - d.pad_t, vw = ow * d.stride + kw - d.pad_l;
@@ -47,11 +58,8 @@ __global__ void wgrad_thin_cin_kernel(const float* __restrict__ x, const float* 
     __syncthreads();
     for (int e = threadIdx.x; e < nb * M4; e += blockDim.x) {
       int pi = e / M4, m = e % M4;
-      long long pix = pb + pi;
-      int ow = (int)(pix % d.ow);
-      long long t = pix / d.ow;
-      int oh = (int)(t % d.oh);
-      int n = (int)(t / d.oh);
+      int n, oh, ow;
+      thin_pixel(pb + pi, d, n, oh, ow);
       int ci = m % d.cin, tap = m / d.cin;
       long long off = m < M ? thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw) : -1;
       xs[pi][m] = off < 0 ? 0.f : x[off + ci];
@@ -94,11 +102,8 @@ __global__ void wgrad_thin_cout_kernel(const float* __restrict__ x, const float*
     __syncthreads();
     for (int e = threadIdx.x; e < nb * TAPS; e += blockDim.x) {
       int pi = e / TAPS, tap = e % TAPS;
-      long long pix = pb + pi;
-      int ow = (int)(pix % d.ow);
-      long long t = pix / d.ow;
-      int oh = (int)(t % d.oh);
-      int n = (int)(t / d.oh);
+      int n, oh, ow;
+      thin_pixel(pb + pi, d, n, oh, ow);
       offs[pi][tap] = thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw);
     }
     for (int e = threadIdx.x; e < nb * CO; e += blockDim.x) gs[e / CO][e % CO] = dy[(pb + e / CO) * d.cout + e % CO];
@@ -148,11 +153,8 @@ __global__ void fwd_thin_cin_kernel(const float* __restrict__ x, const float* __
     __syncthreads();
     for (int e = threadIdx.x; e < nb * M4; e += blockDim.x) {
       int pi = e / M4, m = e % M4;
-      long long pix = pb + pi;
-      int ow = (int)(pix % d.ow);
-      long long t = pix / d.ow;
-      int oh = (int)(t % d.oh);
-      int n = (int)(t / d.oh);
+      int n, oh, ow;
+      thin_pixel(pb + pi, d, n, oh, ow);
       int ci = m % d.cin, tap = m / d.cin;
       long long off = m < m_real ? thin_in_offset(p, n, oh, ow, tap / d.kw, tap % d.kw) : -1;
       xs[pi][m] = off < 0 ? 0.f : x[off + ci];
@@ -185,6 +187,7 @@ __global__ void thin_reduce_kernel(float* __restrict__ out, const float* __restr
 }  // namespace
 
 bool cgan_wgrad_thin_ok(const cgan_conv_desc* d) {
+  if ((long long)d->n * d->oh * d->ow >= (1ll << 31)) return false;      // 32-bit pixel arithmetic in the kernels
   int m = d->kh * d->kw * d->cin;
   if (d->cin <= 4 && (m == 9 || m == 18 || m == 27 || m == 36) && d->kh == 3 && d->kw == 3) return true;
   if (d->cout <= 4 && d->cout == 3 && d->kh == 3 && d->kw == 3) return true;
@@ -197,6 +200,7 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
   p.vh = d->upsample ? 2 * d->h : d->h;
   p.vw = d->upsample ? 2 * d->w : d->w;
   p.npix = (long long)d->n * d->oh * d->ow;
+  if (p.npix >= (1ll << 31)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: more than 2^31 output pixels%s", "cgan_wgrad_thin");
   long long want_blocks = 4ll * ctx->num_sms;
   long long ppb = (p.npix + want_blocks - 1) / want_blocks;
   ppb = (ppb + THIN_PB - 1) / THIN_PB * THIN_PB;
@@ -228,6 +232,7 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
 
 
 bool cgan_fwd_thin_ok(const cgan_conv_desc* d) {
+  if ((long long)d->n * d->oh * d->ow >= (1ll << 31)) return false;
   return d->cin <= 4 && d->kh * d->kw * d->cin <= THIN_MAX_M && d->cout >= 16;
 }
 

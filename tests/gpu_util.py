@@ -216,5 +216,5 @@ def compare_states(eng, orc, lr, updates, frac=0.35, skip=(), state_tol=2e-3):
       assert rms <= lim, "%s: rms weight error %.3e > %.3e" % (k, rms, lim)
     else:
       e = rel_err(a, b)
-      assert e <= 2e-3, "%s (state): rel-L2 error %.3e" % (k, e)
+      assert e <= state_tol, "%s (state): rel-L2 error %.3e" % (k, e)
   return worst
