@@ -112,3 +112,41 @@ def test_is_and_kid_match_oracle():
   assert abs(inception_score.classifier_score_from_logits(logits) - ometrics.inception_score_from_logits(logits)) < 1e-12
   a, b = rng.randn(2100, 16), rng.randn(2500, 16) + 0.3
   assert abs(kid_score.kid(a, b, gram=lambda x, y: x @ y.T) - ometrics.kid(a, b)) < 1e-12
+
+
+def test_inception_topology_statics():
+  """The Inception-v3 layer table (2015 classify_image graph): 94 convolutions + logits, 2048-d pool_3, channel widths of
+  every concat, and the FLOP count that bench.py reports per FID sample.  Pure host logic, no kernels."""
+  from compare_gan_b200 import inception as inc
+  from oracle import inception as oinc
+  convs = inc.walk_convs()
+  assert len(convs) == 94
+  assert inc._channels(inc.SPEC, 3) == inc.POOL_DIM == 2048
+  widths = [inc._channels([it], c) for it, c in ((inc.SPEC[7], 192), (inc.SPEC[8], 256), (inc.SPEC[10], 288),
+                                                  (inc.SPEC[11], 768), (inc.SPEC[15], 768), (inc.SPEC[16], 1280))]
+  assert widths == [256, 288, 768, 768, 1280, 2048]
+  assert abs(inc.flops_per_image() / 1e9 - 11.43) < 0.01
+  w = inc.synthetic_weights(0)
+  assert len(w) == 2 * 94 + 2 and w["inception/logits/kernel"].shape == (2048, inc.NUM_CLASSES)
+  # the CPU oracle walks the same table: same variable names and shapes
+  assert sorted(w) == sorted(oinc.synthetic_weights(0)) if hasattr(oinc, "synthetic_weights") else True
+
+
+def test_reference_arm_prints_contract_line():
+  """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints one JSON line with the contract's
+  keys; runs a single bounded cycle here."""
+  import json
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+  assert out.returncode == 0, out.stderr[-2000:]
+  line = json.loads(out.stdout.strip().splitlines()[-1])
+  for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+    assert key in line, key
+  assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0
+  assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+  assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
