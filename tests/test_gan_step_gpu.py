@@ -241,3 +241,32 @@ def _forward_both_tol(eng, orc, batch, z_dim, tol):
   assert_close(h.cpu(), oh.numpy(), tol, "discriminator features")
   eng.restore(snap)
   orc.store.load_numpy(eng.state_numpy())
+
+
+def test_initialisation_rules_and_training_determinism():
+  """Mirrors runner_lib_test.py:44-104 (bias / beta / moving_mean start at 0, gamma / moving_variance at 1, equal seeds
+  give equal weights, different seeds different ones) and :107-147 (training is deterministic: two runs from the same
+  seed end in identical checkpoints)."""
+  def run(seed, cycles):
+    eng, _ = make_pair("resnet_cifar_arch", (32, 32, 3), 2, d_sn=True, disc_iters=1, seed=seed)
+    init = eng.state_numpy()
+    rng = np.random.RandomState(3)
+    for _ in range(cycles):
+      eng.set_inputs(*make_inputs(rng, 1, 2, (32, 32, 3), 128))
+      eng.run_cycle()
+      eng.read_losses()
+    return init, eng.state_numpy(), eng.global_step
+  init_a, final_a, steps_a = run(3, 3)
+  init_b, final_b, steps_b = run(3, 3)
+  init_c, _, _ = run(4, 0)
+  for name, t0 in init_a.items():
+    if any(name.endswith(e) for e in ("bias", "beta", "moving_mean")):
+      assert not t0.any(), name
+    elif any(name.endswith(e) for e in ("gamma", "moving_variance")):
+      assert (t0 == 1).all(), name
+    np.testing.assert_array_equal(t0, init_b[name], err_msg=name)                 # same seed
+    if name.endswith("kernel"):
+      assert not np.allclose(t0, init_c[name]), name                              # different seed
+  assert steps_a == steps_b == 3
+  for name, t0 in final_a.items():
+    np.testing.assert_array_equal(t0, final_b[name], err_msg=name)
