@@ -1,4 +1,4 @@
-"""Diagnostic (not a test): per-tensor gradient errors of the smoke configuration vs fp32 / fp64 oracles."""
+"""Diagnostic (not a test; run from the repo root: python -m profiles.diag_gradients): per-tensor gradient errors of the smoke configuration vs fp32 / fp64 oracles."""
 import sys
 import numpy as np
 import torch
