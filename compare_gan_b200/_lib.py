@@ -20,7 +20,7 @@ class ConvDesc(ctypes.Structure):
 
 
 _SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64,
-            "float": ctypes.c_float, "size_t": ctypes.c_size_t}
+            "float": ctypes.c_float, "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64}
 
 
 def parse_header(path=HEADER):
@@ -50,21 +50,33 @@ class CganError(RuntimeError):
   pass
 
 
+_DLL = {}
+
+
+def load_functions(so_path=SO_PATH):
+  """Loads the shared library and returns (dll, protos, {name: typed function}) without creating a device context —
+  all the host-side input pipeline (cgan_loader_*) needs."""
+  if so_path not in _DLL:
+    if not os.path.exists(so_path):
+      raise CganError("libcgan_b200.so not found at %s — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU / PyTorch fallback for the product path)" % so_path)
+    dll = ctypes.CDLL(so_path)
+    protos = parse_header()
+    fn = {}
+    for name, (restype, argtypes) in protos.items():
+      f = getattr(dll, name)       # AttributeError if the symbol is not exported
+      f.restype = restype
+      f.argtypes = argtypes
+      fn[name] = f
+    _DLL[so_path] = (dll, protos, fn)
+  return _DLL[so_path]
+
+
 class Lib(object):
   """Loaded library + one context bound to one CUDA device."""
 
   def __init__(self, device=0, so_path=SO_PATH):
-    if not os.path.exists(so_path):
-      raise CganError("libcgan_b200.so not found at %s — run `python -c 'import __graft_entry__ as g; g.build()'` "
-                      "(there is no CPU / PyTorch fallback for the product path)" % so_path)
-    self.dll = ctypes.CDLL(so_path)
-    self.protos = parse_header()
-    self.fn = {}
-    for name, (restype, argtypes) in self.protos.items():
-      f = getattr(self.dll, name)       # AttributeError if the symbol is not exported
-      f.restype = restype
-      f.argtypes = argtypes
-      self.fn[name] = f
+    self.dll, self.protos, self.fn = load_functions(so_path)
     self.ctx = ctypes.c_void_p()
     rc = self.fn["cgan_ctx_create"](ctypes.byref(self.ctx), device)
     if rc != 0:

@@ -3,6 +3,7 @@ training loop in place of TPUEstimator.train.  Checkpoint polling / CSV task man
 accelerated path."""
 import csv
 import glob
+import collections
 import os
 import re
 import time
@@ -54,18 +55,48 @@ gin.external_configurable(_normal, "tf.random.normal")
 gin.external_configurable(_uniform, "tf.random.uniform")
 
 
-def sample_cycle_inputs(gan, dataset, batch_size, rng):
-  """One unrolled cycle of synthetic inputs: disc_iters+1 sub-steps, fresh images/z each
-  (reference gans/modular_gan.py:218-223, 410-426)."""
+def sample_cycle_inputs(gan, dataset, batch_size, rng, real=None):
+  """One unrolled cycle of inputs: disc_iters+1 sub-steps, fresh images/z each (reference
+  gans/modular_gan.py:218-223, 410-426).  Images/labels are synthetic unless `real` = (images, labels) lists from the
+  input pipeline are given."""
   k = gan._disc_iters
-  images = [dataset.sample_images(batch_size) for _ in range(k + 1)]
+  images = real[0] if real is not None else [dataset.sample_images(batch_size) for _ in range(k + 1)]
   z = [z_generator((batch_size, gan._z_dim), rng=rng) for _ in range(k + 1)]
   labels = sampled = None
   if gan.conditional:
-    labels = [dataset.sample_labels(batch_size) for _ in range(k + 1)]
+    labels = real[1] if real is not None else [dataset.sample_labels(batch_size) for _ in range(k + 1)]
     sampled = [rng.randint(0, dataset.num_classes, batch_size).astype(np.int32) for _ in range(k + 1)]
   alphas = [rng.rand(batch_size, 1, 1, 1).astype(np.float32) for _ in range(k + 1)]
   return images, z, labels, sampled, alphas
+
+
+class PipelineFeeder(object):
+  """Feeds training cycles from `dataset.train_input_fn` (reference datasets.py:261-291 + the TPUEstimator infeed):
+  each cycle takes disc_iters+1 page-locked batches from the native loader, `set_inputs` copies them asynchronously, and
+  the ring slots of a cycle are handed back once a CUDA event recorded behind its copies has completed — checked two
+  cycles later, so the host never waits on the copies it has just issued."""
+
+  def __init__(self, gan, dataset, batch_size, rank=0):
+    self.k1 = gan._disc_iters + 1
+    self.it = dataset.train_input_fn({"batch_size": batch_size}, rank=rank, ring=3 * self.k1 + 1)
+    self.pending = collections.deque()
+
+  def feed(self, gan, dataset, batch_size, rng):
+    import torch
+    while len(self.pending) >= 2:
+      self.pending.popleft().synchronize()
+      self.it.release(self.k1)
+    batches = [next(self.it) for _ in range(self.k1)]
+    real = ([b[0] for b in batches], [b[1] for b in batches])
+    gan.set_inputs(*sample_cycle_inputs(gan, dataset, batch_size, rng, real=real))
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    self.pending.append(ev)
+
+  def close(self):
+    while self.pending:
+      self.pending.popleft().synchronize()
+    self.it.close()
 
 
 class TaskManager(object):
@@ -180,9 +211,10 @@ def _run_eval(gan, task_manager, eval_tasks=None, num_averaging_runs=1, num_samp
 
 
 def run_with_schedule(schedule, options=None, model_dir="/tmp/compare_gan_b200", num_cycles=None, use_graph=True,
-                      seed=0, task_manager=None, save_every_cycles=None, eval_kwargs=None):
-  """Run the schedule `train` / `eval_after_train` / `continuous_eval` on synthetic data (reference
-  runner_lib.py:280-354)."""
+                      seed=0, task_manager=None, save_every_cycles=None, eval_kwargs=None, input_pipeline=False):
+  """Run the schedule `train` / `eval_after_train` / `continuous_eval` (reference runner_lib.py:280-354).  Training
+  images are synthetic draws by default; with `input_pipeline` they come from `dataset.train_input_fn` (the reference's
+  fake data set or on-disk shards) through the native prefetching loader."""
   if schedule not in ("train", "eval_after_train", "continuous_eval"):
     raise ValueError("Schedule {} not supported.".format(schedule))
   options = options or get_options_dict()
@@ -203,12 +235,21 @@ def run_with_schedule(schedule, options=None, model_dir="/tmp/compare_gan_b200",
   rng = np.random.RandomState(seed)
   cycles = num_cycles if num_cycles is not None else options["training_steps"] // max(1, options["disc_iters"])
   t0 = time.time()
+  feeder = None
+  if input_pipeline:
+    import torch.distributed as dist
+    feeder = PipelineFeeder(gan, dataset, per_replica, rank=dist.get_rank() if tpu_ops.num_replicas() > 1 else 0)
   for _ in range(cycles):
-    gan.set_inputs(*sample_cycle_inputs(gan, dataset, per_replica, rng))
+    if feeder is not None:
+      feeder.feed(gan, dataset, per_replica, rng)
+    else:
+      gan.set_inputs(*sample_cycle_inputs(gan, dataset, per_replica, rng))
     gan.run_cycle()
     if save_every_cycles and (_ + 1) % save_every_cycles == 0:
       gan.save_checkpoint(model_dir)
   d_losses, g_loss = gan.read_losses()
+  if feeder is not None:
+    feeder.close()
   os.makedirs(model_dir, exist_ok=True)
   with open(os.path.join(model_dir, "operative_config-0.gin"), "w") as f:     # GinConfigSaverHook, runner_lib.py:319
     f.write(gin.operative_config_str())

@@ -183,6 +183,27 @@ int cgan_cov_accumulate(cgan_ctx*, const float* act, int n, int d, double* sum, 
  * when `inception_scale` (eval_utils.py:157-175). */
 int cgan_resize_bilinear(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c, int oh, int ow, int inception_scale);
 
+/* ---- input pipeline (ImageDatasetV2.train_input_fn, datasets.py:261-291; host side, no GPU work) ---- */
+/* The tf.data chain of the reference: repeat() -> shuffle(buffer, seed) -> batch(drop_remainder=True) -> prefetch, with
+ * _parse_fn's uint8 -> float32 / 255 (datasets.py:225-227), run by a producer thread into a ring of `ring` batch buffers
+ * (page-locked when a CUDA device is present, so the caller's cudaMemcpyAsync overlaps the previous step).
+ * Source: `n` images NHWC contiguous in host memory, uint8 (src_dtype 0, scaled by 1/255) or float32 (src_dtype 1, copied;
+ * the reference's fake data set, datasets.py:136-145), and optional int32 labels; caller-owned, must outlive the loader
+ * (e.g. an mmap of a shard file).  shuffle_buffer <= 1 disables shuffling.  The shuffle is tf.data's algorithm (a buffer
+ * of `shuffle_buffer` elements, each output drawn uniformly from it and replaced by the next input) on a SplitMix64
+ * stream; the element ORDER is therefore not TF's (its Philox stream is not restated). */
+typedef struct cgan_loader cgan_loader;
+int cgan_loader_create(cgan_loader** out, const void* images, int src_dtype, const int32_t* labels, int64_t n, int h, int w,
+                       int c, int batch, int shuffle_buffer, uint64_t seed, int ring);
+/* Blocks until the next batch is ready: images float32 [batch,h,w,c], labels int32 [batch] (zeros without source
+ * labels).  The buffers stay untouched until released; with every ring slot outstanding the call fails instead of
+ * dead-locking. */
+int cgan_loader_next(cgan_loader*, const float** images, const int32_t** labels);
+/* Hands the `count` oldest outstanding batches back to the producer (call once their host->device copies finished). */
+int cgan_loader_release(cgan_loader*, int count);
+int cgan_loader_destroy(cgan_loader*);
+const char* cgan_loader_last_error(cgan_loader*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,3 +149,27 @@ def test_eval_after_train_schedule_and_checkpoint_roundtrip(K, tmp_path):
   after = gan.checkpoint_dict()
   for k in before:
     np.testing.assert_array_equal(before[k], after[k], err_msg=k)
+
+
+def test_train_from_input_pipeline(K, tmp_path):
+  """run_with_schedule("train", input_pipeline=True): every cycle takes disc_iters+1 batches from
+  dataset.train_input_fn (the reference's fake data set through the native prefetching loader, datasets.py:136-145,
+  261-291).  The images resident on the device after the last cycle are exactly the batches the tf.data model of the
+  shuffle stream predicts for that cycle."""
+  from compare_gan_b200 import configs, datasets, gin_lite as gin, runner_lib
+  from compare_gan_b200.gans import modular_gan  # noqa: F401
+  from tests.test_input_pipeline import model_stream
+  gin.clear_config()
+  gin.parse_config(configs.RESNET_CIFAR10)
+  gin.parse_config("options.batch_size = 8")
+  out = runner_lib.run_with_schedule("train", model_dir=str(tmp_path / "run"), num_cycles=3, use_graph=False,
+                                     input_pipeline=True)
+  gan = out["gan"]
+  assert np.isfinite(out["g_loss"]) and all(np.isfinite(v) for v in out["d_loss"])
+  k1 = gan._disc_iters + 1
+  ds = datasets.get_dataset()
+  fake, _ = ds._make_fake_dataset("train")
+  ids = model_stream(len(fake), 10000, 547, 3 * k1 * 8)
+  for i in range(k1):
+    want = fake[ids[(2 * k1 + i) * 8:(2 * k1 + i + 1) * 8]]
+    np.testing.assert_array_equal(gan.inputs[i]["images"].cpu(), want)
