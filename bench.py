@@ -213,7 +213,18 @@ def run_ours(args):
   if rank == 0:
     pk = peaks()
     dom = time_dominant_kernel(b, math_mode=mm)
-    ev = eval_leg(eng, args, wl) if not args.no_eval else None
+    ev = None
+    if not args.no_eval:
+      # The FID leg is timed on rank 0 alone as a single replica (no collective can be left waiting on ranks that have
+      # already finished).  eval_gan_lib.evaluate itself shards the samples over ranks and all-reduces (n, sum, sum xx^T)
+      # when every rank calls it; that path is not timed by this bench.
+      from compare_gan_b200.tpu import tpu_ops
+      tpu_ops.force_local(world > 1)
+      try:
+        ev = eval_leg(eng, args, wl)
+        ev["n_gpus"] = 1
+      finally:
+        tpu_ops.force_local(False)
     cyc_tflop = wl["gflop_per_slot_image"] * b / 1e3          # useful TFLOP per cycle per GPU
     cpu = cpu_baseline_leg(args, sample_cycles=2) if not args.no_cpu_baseline else None
     out = {
