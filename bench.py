@@ -226,7 +226,7 @@ def run_ours(args):
       finally:
         tpu_ops.force_local(False)
     cyc_tflop = wl["gflop_per_slot_image"] * b / 1e3          # useful TFLOP per cycle per GPU
-    cpu = cpu_baseline_leg(args, sample_cycles=2) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline_leg(args, sample_cycles=2) if (not args.no_cpu_baseline and world == 1) else None    # N=1 only
     out = {
         "metric": "images/sec G+D step (%s)" % args.workload, "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
