@@ -307,7 +307,35 @@ def cpu_baseline_leg(args, sample_cycles=2, batch=64):
   return {"value": batch * (k + 1) / dt, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
           "sample": "%d full cycles (5 D + 1 G) of resnet_cifar10 at batch %d per sub-step on the host cores, "
                     "PyTorch-CPU fp32 oracle (CPU restatement of the reference; TF unavailable)" % (sample_cycles, batch),
-          "seconds_per_cycle": dt, "host_cpus": os.cpu_count()}
+          "seconds_per_cycle": dt, "host_cpus": os.cpu_count(), "fid_path": cpu_eval_leg(o, cfg, rng)}
+
+
+def cpu_eval_leg(o, cfg, rng, batch=64, batches=2):
+  """The FID path of the CPU restatement beside it: inference-mode G -> bilinear 299x299 -> Inception-v3
+  -> float64 (sum, sum xx^T), batch 64 as the reference evaluates (eval_gan_lib.py:95-212, eval_utils.py:165-175)."""
+  import torch
+  from oracle import inception as oinc, nets as onets
+  w = {k: torch.from_numpy(v) for k, v in oinc.synthetic_weights(0).items()} if hasattr(oinc, "synthetic_weights") else None
+  if w is None:
+    from compare_gan_b200 import inception as inc
+    w = {k: torch.from_numpy(v) for k, v in inc.synthetic_weights(0).items()}
+  s, sxx = np.zeros(2048), np.zeros((2048, 2048))
+
+  def one():
+    nonlocal s, sxx
+    with torch.no_grad():
+      z = torch.from_numpy(rng.uniform(-1, 1, (batch, 128)).astype(np.float32))
+      imgs = onets.generator(o.store, cfg, z, None, False)
+      pool, _ = oinc.inception_v3(oinc.preprocess(imgs), w)
+    a = pool.numpy().astype(np.float64)
+    s += a.sum(0)
+    sxx += a.T @ a
+  one()   # warm-up
+  t0 = time.time()
+  for _ in range(batches):
+    one()
+  dt = (time.time() - t0) / batches
+  return {"fid_samples_per_sec": batch / dt, "unit": "samples/sec", "sample": "%d evaluation batches of %d" % (batches, batch)}
 
 
 def run_reference(args):
