@@ -1,6 +1,6 @@
 """Per-kernel timing table on one B200 (no profiler): the convolution shapes of the resnet_cifar10 B=256 cycle and a few
 BigGAN-128 ones (forward / input gradient / filter gradient, tcgen05 path) as TFLOP/s, and the memory-bound kernel
-families (BN, ReLU, add, pooling, column sums, Adam) as algorithmic GB/s against the measured HBM peak.  CUDA events on
+families (BN forward / backward, ReLU, add, pooling, column sums) as algorithmic GB/s against the measured HBM peak.  CUDA events on
 the launching stream, 3 warm-ups + 10 timed launches per entry; every operand set is larger than the 126 MB L2 or is
 re-streamed between launches by the other operands of the same entry.
 
