@@ -190,3 +190,58 @@ def test_conv_transpose_is_adjoint_of_conv():
     lhs = (T.conv2d_same(x, w, s) * y).sum()
     rhs = (x * T.conv2d_transpose_same(y, w, (n, n), s)).sum()
     assert abs(float(lhs - rhs)) < 1e-9 * max(1.0, abs(float(lhs)))
+
+
+def _naive_conv2d_same(x, w, s):
+  """tf.nn.conv2d(padding="SAME") written out from its definition (TF docs "convolution" / nn_ops padding notes):
+  out = ceil(in / s); pad_total = max((out-1)*s + k - in, 0); pad_before = pad_total // 2 (the extra pixel goes AFTER);
+  out[b,i,j,o] = sum_{di,dj,c} x[b, s*i+di-pad_top, s*j+dj-pad_left, c] * w[di,dj,c,o]."""
+  b, h, wd, c = x.shape
+  kh, kw, _, o = w.shape
+  oh, ow = -(-h // s), -(-wd // s)
+  pt = max((oh - 1) * s + kh - h, 0) // 2
+  pl = max((ow - 1) * s + kw - wd, 0) // 2
+  y = np.zeros((b, oh, ow, o), np.float64)
+  for i in range(oh):
+    for j in range(ow):
+      for di in range(kh):
+        for dj in range(kw):
+          r, q = s * i + di - pt, s * j + dj - pl
+          if 0 <= r < h and 0 <= q < wd:
+            y[:, i, j, :] += x[:, r, q, :].astype(np.float64) @ w[di, dj].astype(np.float64)
+  return y
+
+
+def test_conv2d_same_matches_the_written_out_definition():
+  """The oracle's conv2d_same (explicit asymmetric padding + torch conv) against plain loops over TF's definition:
+  odd and even sizes, strides 1/2, kernels 1/3/4/5 (the 4x4 and 5x5 stride-2 cases put the extra padding pixel after,
+  SURVEY App. A)."""
+  rng = np.random.RandomState(0)
+  for (h, w_, k, s) in [(5, 5, 3, 1), (6, 4, 3, 2), (7, 7, 5, 2), (8, 8, 4, 2), (5, 6, 1, 1), (9, 9, 5, 1), (4, 4, 4, 2), (7, 5, 3, 2)]:
+    x = rng.randn(2, h, w_, 3).astype(np.float32)
+    w = rng.randn(k, k, 3, 4).astype(np.float32)
+    got = T.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), s).numpy()
+    want = _naive_conv2d_same(x, w, s)
+    assert got.shape == want.shape, (h, w_, k, s)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5, err_msg=str((h, w_, k, s)))
+
+
+def test_conv2d_transpose_matches_scatter_definition():
+  """tf.nn.conv2d_transpose(..., "SAME") is the gradient of conv2d_same w.r.t. its input: every input pixel scatters
+  its value times the kernel into the output window the forward conv would have read (arch_ops.py:588-589)."""
+  rng = np.random.RandomState(1)
+  for (oh, k, s) in [(8, 4, 2), (8, 5, 2), (6, 3, 1), (10, 4, 2)]:
+    ih = -(-oh // s)
+    x = rng.randn(2, ih, ih, 3).astype(np.float32)
+    w = rng.randn(k, k, 5, 3).astype(np.float32)              # [kh, kw, out_channels, in_channels]
+    got = T.conv2d_transpose_same(torch.from_numpy(x), torch.from_numpy(w), (oh, oh), s).numpy()
+    pt = max((ih - 1) * s + k - oh, 0) // 2
+    want = np.zeros((2, oh, oh, 5), np.float64)
+    for i in range(ih):
+      for j in range(ih):
+        for di in range(k):
+          for dj in range(k):
+            r, q = s * i + di - pt, s * j + dj - pt
+            if 0 <= r < oh and 0 <= q < oh:
+              want[:, r, q, :] += x[:, i, j, :].astype(np.float64) @ w[di, dj].astype(np.float64).T
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5, err_msg=str((oh, k, s)))
