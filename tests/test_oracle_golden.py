@@ -245,3 +245,71 @@ def test_conv2d_transpose_matches_scatter_definition():
             if 0 <= r < oh and 0 <= q < oh:
               want[:, r, q, :] += x[:, i, j, :].astype(np.float64) @ w[di, dj].astype(np.float64).T
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5, err_msg=str((oh, k, s)))
+
+
+def test_losses_match_their_mathematical_definitions():
+  """loss_lib.py:53-148 against float64 numpy from the textbook forms: -log sigma(x) / -log(1 - sigma(x)) for the
+  non-saturating loss (TF evaluates them through the stable max(x,0) - x z + log1p(exp(-|x|)) form), hinge,
+  Wasserstein and least squares.  Includes logits of +-30 where the naive fp32 form would overflow."""
+  from oracle import gan as ogan
+  rng = np.random.RandomState(0)
+  real = np.concatenate([rng.randn(30, 1) * 3, [[30.0], [-30.0]]]).astype(np.float32)
+  fake = np.concatenate([rng.randn(30, 1) * 3, [[-30.0], [30.0]]]).astype(np.float32)
+  r64, f64 = real.astype(np.float64), fake.astype(np.float64)
+  sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+  want = {
+      # -log sigma(x) = log(1 + e^-x), -log(1 - sigma(x)) = log(1 + e^x): evaluated with logaddexp, exact in float64
+      "non_saturating": (np.mean(np.logaddexp(0, -r64)) + np.mean(np.logaddexp(0, f64)), np.mean(np.logaddexp(0, -r64)),
+                         np.mean(np.logaddexp(0, f64)), np.mean(np.logaddexp(0, -f64))),
+      "hinge": (np.mean(np.maximum(0, 1 - r64)) + np.mean(np.maximum(0, 1 + f64)), np.mean(np.maximum(0, 1 - r64)),
+                np.mean(np.maximum(0, 1 + f64)), -np.mean(f64)),
+      "wasserstein": (-np.mean(r64) + np.mean(f64), -np.mean(r64), np.mean(f64), -np.mean(f64)),
+      "least_squares": (0.5 * (np.mean((sig(r64) - 1) ** 2) + np.mean(sig(f64) ** 2)), np.mean((sig(r64) - 1) ** 2),
+                        np.mean(sig(f64) ** 2), 0.5 * np.mean((sig(f64) - 1) ** 2)),
+  }
+  tr, tf_ = torch.from_numpy(real), torch.from_numpy(fake)
+  for fn, expect in want.items():
+    got = ogan.get_losses(fn, torch.sigmoid(tr), torch.sigmoid(tf_), tr, tf_)
+    np.testing.assert_allclose([float(v) for v in got], expect, rtol=2e-6, atol=1e-6, err_msg=fn)
+
+
+def test_spectral_norm_is_one_power_iteration_and_converges_to_the_top_singular_value():
+  """arch_ops.py:503-531: v = normalize(W^T u), u' = normalize(W v), sigma = u'^T W v, W / sigma; iterating the stored u
+  drives sigma to the largest singular value (numpy SVD), for both the left and the right variant."""
+  rng = np.random.RandomState(0)
+  w = rng.randn(12, 7).astype(np.float32)
+  smax = np.linalg.svd(w.astype(np.float64), compute_uv=False)[0]
+  for mode, ushape in (("left", (12, 1)), ("right", (1, 7))):
+    u = rng.randn(*ushape).astype(np.float32)
+    u64 = u.astype(np.float64)
+    w64 = w.astype(np.float64)
+    # one step, written out in float64
+    if mode == "left":
+      v = w64.T @ u64; v /= np.sqrt((v ** 2).sum() + 1e-12)
+      un = w64 @ v; un /= np.sqrt((un ** 2).sum() + 1e-12)
+      s_ref = float((un.T @ w64 @ v).item())
+    else:
+      v = u64 @ w64.T; v /= np.sqrt((v ** 2).sum() + 1e-12)
+      un = v @ w64; un /= np.sqrt((un ** 2).sum() + 1e-12)
+      s_ref = float((v @ w64 @ un.T).item())
+    sigma, u_new, _ = T.spectral_sigma(torch.from_numpy(w), torch.from_numpy(u), mode)
+    np.testing.assert_allclose(float(sigma), s_ref, rtol=1e-5)
+    np.testing.assert_allclose(u_new.numpy(), un, rtol=1e-4, atol=1e-6)
+    ut = torch.from_numpy(u)
+    for _ in range(200):
+      sigma, ut, _ = T.spectral_sigma(torch.from_numpy(w), ut, mode)
+    np.testing.assert_allclose(float(sigma), smax, rtol=1e-4)
+
+
+def test_unpool_and_pools_match_definitions():
+  """resnet_ops.unpool (resnet_ops.py:35-56): value at the even position of each 2x2 cell, zeros elsewhere;
+  tf.nn.pool AVG 2x2 stride 2 (resnet_ops.py:131) and the 2x2 max pool of the attention block (arch_ops.py:741)."""
+  rng = np.random.RandomState(0)
+  x = rng.randn(2, 4, 6, 3).astype(np.float32)
+  up = T.unpool(torch.from_numpy(x)).numpy()
+  want = np.zeros((2, 8, 12, 3), np.float32)
+  want[:, ::2, ::2, :] = x
+  np.testing.assert_array_equal(up, want)
+  cells = x.reshape(2, 2, 2, 3, 2, 3)
+  np.testing.assert_allclose(T.avg_pool2(torch.from_numpy(x)).numpy(), cells.mean(axis=(2, 4)), rtol=1e-6, atol=1e-7)
+  np.testing.assert_array_equal(T.max_pool2(torch.from_numpy(x)).numpy(), cells.max(axis=(2, 4)))
