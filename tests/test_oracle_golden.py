@@ -313,3 +313,53 @@ def test_unpool_and_pools_match_definitions():
   cells = x.reshape(2, 2, 2, 3, 2, 3)
   np.testing.assert_allclose(T.avg_pool2(torch.from_numpy(x)).numpy(), cells.mean(axis=(2, 4)), rtol=1e-6, atol=1e-7)
   np.testing.assert_array_equal(T.max_pool2(torch.from_numpy(x)).numpy(), cells.max(axis=(2, 4)))
+
+
+def test_non_local_block_matches_written_out_attention():
+  """arch_ops.py:709-758 from its definition in float64 numpy: theta = x W_t [hw, c/8]; phi, g = 2x2-max-pooled
+  x W_p, x W_g [hw/4, .]; beta = softmax(theta phi^T) over the hw/4 keys; out = x + sigma * (beta g) W_o."""
+  from oracle import nets as onets
+  cfg = onets.Cfg(architecture="resnet_biggan_arch", image_shape=(32, 32, 3))
+  store = onets.VarStore(seed=3)
+  rng = np.random.RandomState(0)
+  x = rng.randn(2, 4, 4, 16).astype(np.float32)
+  with torch.no_grad():
+    onets.non_local_block(store, cfg, torch.from_numpy(x), "nl", False)          # creates the variables
+    store.vars["nl/sigma"].fill_(0.7)
+    for k in ("conv2d_theta", "conv2d_phi", "conv2d_g", "conv2d_attn_g"):
+      store.vars["nl/%s/kernel" % k].mul_(20.0)                                   # away from a uniform softmax
+    got = onets.non_local_block(store, cfg, torch.from_numpy(x), "nl", False).numpy()
+  w = {k: store.vars["nl/%s/kernel" % k].detach().numpy().astype(np.float64)[0, 0] for k in ("conv2d_theta", "conv2d_phi", "conv2d_g", "conv2d_attn_g")}
+  x64 = x.astype(np.float64)
+
+  def pool(t):          # [n,4,4,c] -> [n,4,c]: 2x2 max over each cell, row-major cells
+    n, h, w_, c = t.shape
+    return t.reshape(n, h // 2, 2, w_ // 2, 2, c).max(axis=(2, 4)).reshape(n, -1, c)
+  theta = (x64 @ w["conv2d_theta"]).reshape(2, 16, -1)
+  phi = pool(x64 @ w["conv2d_phi"])
+  g = pool(x64 @ w["conv2d_g"])
+  logits = theta @ phi.transpose(0, 2, 1)
+  beta = np.exp(logits - logits.max(-1, keepdims=True))
+  beta /= beta.sum(-1, keepdims=True)
+  want = x64 + 0.7 * ((beta @ g).reshape(2, 4, 4, -1) @ w["conv2d_attn_g"])
+  np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_tf_adam_matches_the_update_rule():
+  """tf.train.AdamOptimizer (modular_gan.py:606-616 via the optimizer fn): t += 1; lr_t = lr sqrt(1-b2^t)/(1-b1^t);
+  m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr_t m / (sqrt(v) + eps) — epsilon OUTSIDE the bias-corrected
+  root, unlike the paper's form."""
+  from collections import OrderedDict
+  from oracle import gan as ogan
+  rng = np.random.RandomState(0)
+  p0 = rng.randn(5, 3).astype(np.float32)
+  params = OrderedDict(w=torch.from_numpy(p0.copy()))
+  opt = ogan.TFAdam(params, lr=2e-4, beta1=0.5, beta2=0.999)
+  theta, m, v = p0.astype(np.float64), 0.0, 0.0
+  for t in range(1, 6):
+    g = rng.randn(5, 3).astype(np.float32)
+    opt.step({"w": torch.from_numpy(g)})
+    m = 0.5 * m + 0.5 * g.astype(np.float64)
+    v = 0.999 * v + 0.001 * g.astype(np.float64) ** 2
+    theta = theta - 2e-4 * np.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t) * m / (np.sqrt(v) + 1e-8)
+    np.testing.assert_allclose(params["w"].numpy(), theta, rtol=1e-5, atol=1e-7, err_msg="step %d" % t)
