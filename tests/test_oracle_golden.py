@@ -363,3 +363,23 @@ def test_tf_adam_matches_the_update_rule():
     v = 0.999 * v + 0.001 * g.astype(np.float64) ** 2
     theta = theta - 2e-4 * np.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t) * m / (np.sqrt(v) + 1e-8)
     np.testing.assert_allclose(params["w"].numpy(), theta, rtol=1e-5, atol=1e-7, err_msg="step %d" % t)
+
+
+def test_inception_score_and_kid_match_their_estimators():
+  """IS = exp(E_x KL(p(y|x) || p(y))) (tfgan classifier_score_from_logits, inception_score.py:44) and KID = the unbiased
+  MMD^2 with k(a,b) = (a.b/d + 1)^3 (kid_score.py:44-149), both as explicit double loops in float64 for a single block
+  with equally many real and generated samples (where the reference's `n = r_e - r_s` quirk is immaterial)."""
+  rng = np.random.RandomState(0)
+  logits = rng.randn(17, 9) * 2
+  p = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
+  marg = p.mean(0)
+  kl = [sum(p[i, j] * (np.log(p[i, j]) - np.log(marg[j])) for j in range(9)) for i in range(17)]
+  np.testing.assert_allclose(metrics.inception_score_from_logits(logits), np.exp(np.mean(kl)), rtol=1e-10)
+
+  real, fake = rng.randn(12, 6), rng.randn(12, 6) + 0.3
+  k = lambda a, b: (a @ b / 6.0 + 1.0) ** 3
+  m = 12
+  rr = sum(k(real[i], real[j]) for i in range(m) for j in range(m) if i != j) / (m * (m - 1))
+  gg = sum(k(fake[i], fake[j]) for i in range(m) for j in range(m) if i != j) / (m * (m - 1))
+  rg = sum(k(real[i], fake[j]) for i in range(m) for j in range(m)) / (m * m)
+  np.testing.assert_allclose(metrics.kid(fake, real), rr + gg - 2 * rg, rtol=1e-10)
