@@ -150,3 +150,37 @@ def test_reference_arm_prints_contract_line():
   assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0
   assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
   assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_task_manager_checkpoint_polling_and_csv(tmp_path):
+  """TaskManager / TaskManagerWithCsvResults (reference runner_lib.py:114-232): unevaluated checkpoints come in step
+  order, `eval_every_steps` keeps the positive multiples only, results land in scores.csv as checkpoint_path, step,
+  sorted result keys, sorted operative-config keys (floats with three decimals), evaluated checkpoints are not offered
+  again, and the config of a step is the latest operative_config saved at or before it."""
+  import csv
+  import os
+  from compare_gan_b200 import runner_lib
+  md = str(tmp_path)
+  for step in (0, 5000, 10000, 12500):
+    open(os.path.join(md, "model.ckpt-%d.npz" % step), "w").close()
+  open(os.path.join(md, "operative_config-0.gin"), "w").write("options.batch_size = 64\nloss.fn = @hinge\n")
+  open(os.path.join(md, "operative_config-10000.gin"), "w").write("options.batch_size = 128\nloss.fn = @hinge\n")
+  tm = runner_lib.TaskManagerWithCsvResults(md)
+  assert not tm.is_training_done()
+  tm.mark_training_done()
+  assert tm.is_training_done() and os.path.exists(os.path.join(md, "TRAIN_DONE"))
+  todo = list(tm.unevaluated_checkpoints(timeout=0))
+  assert [os.path.basename(c) for c in todo] == ["model.ckpt-0.npz", "model.ckpt-5000.npz", "model.ckpt-10000.npz",
+                                                  "model.ckpt-12500.npz"]
+  assert [os.path.basename(c) for c in tm.unevaluated_checkpoints(timeout=0, eval_every_steps=5000)] == [
+      "model.ckpt-5000.npz", "model.ckpt-10000.npz"]
+  tm.add_eval_result(todo[1], {"fid_score_mean": 12.34567, "inception_score_mean": 7.0, "note": "ok"}, -1.0)
+  tm.add_eval_result(todo[2], {"fid_score_mean": 11.0, "inception_score_mean": 7.5, "note": "ok"}, -1.0)
+  rows = list(csv.reader(open(os.path.join(md, "scores.csv"))))
+  assert rows[0] == ["checkpoint_path", "step", "fid_score_mean", "inception_score_mean", "note", "loss.fn", "options.batch_size"]
+  assert rows[1][1:] == ["5000", "12.346", "7.000", "ok", "@hinge", "64"]
+  assert rows[2][1:] == ["10000", "11.000", "7.500", "ok", "@hinge", "128"]
+  assert tm.get_checkpoints_with_results() == {todo[1], todo[2]}
+  assert [os.path.basename(c) for c in tm.unevaluated_checkpoints(timeout=0)] == ["model.ckpt-0.npz", "model.ckpt-12500.npz"]
+  # the base class keeps no results: everything stays unevaluated
+  assert len(list(runner_lib.TaskManager(md).unevaluated_checkpoints(timeout=0))) == 4
