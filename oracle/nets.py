@@ -531,10 +531,117 @@ def _disc_biggan(store, cfg, x, y, is_training):
   return torch.sigmoid(logit), logit, feat
 
 
+# --------------------------------------------------------------------------- resnet_biggan_deep
+
+def biggan_deep_block(store, cfg, x, name, cin, cout, scale, y, is_training, bn, use_sn):
+  """resnet_biggan_deep.BigGanDeepResNetBlock — resnet_biggan_deep.py:61-177: bottleneck (1x1 -> 3x3 -> 3x3 -> 1x1 at
+  max(cin, cout) / 4 channels) with an identity-preserving skip: channels are DROPPED on the way up and ADDED by a 1x1
+  conv on the way down."""
+  if x.shape[-1] != cin:
+    raise ValueError("Unexpected number of input channels (expected {}, got {}).".format(cin, x.shape[-1]))
+  mid = max(cin, cout) // 4
+  with store.scope(name):
+    h = x
+    with store.scope("conv1"):
+      h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "bn", use_sn))
+      h = conv2d(store, cfg, h, mid, 1, 1, 1, "1x1_conv", use_sn)
+    with store.scope("conv2"):
+      h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "bn", use_sn))
+      if scale == "up":
+        h = T.unpool(h)
+      h = conv2d(store, cfg, h, mid, 3, 3, 1, "3x3_conv", use_sn)
+    with store.scope("conv3"):
+      h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "bn", use_sn))
+      h = conv2d(store, cfg, h, mid, 3, 3, 1, "3x3_conv", use_sn)
+    with store.scope("conv4"):
+      h = torch.relu(apply_bn(store, cfg, bn, h, y, is_training, "bn", use_sn))
+      if scale == "down":
+        h = T.avg_pool2(h)
+      h = conv2d(store, cfg, h, cout, 1, 1, 1, "1x1_conv", use_sn)
+    with store.scope("shortcut"):                                   # :94-117
+      sc = x
+      if cin > cout:
+        assert scale == "up"
+        sc = sc[..., :cout]
+      if scale == "up":
+        sc = T.unpool(sc)
+      if scale == "down":
+        sc = T.avg_pool2(sc)
+      if cin < cout:
+        assert scale == "down"
+        sc = torch.cat([sc, conv2d(store, cfg, sc, cout - cin, 1, 1, 1, "add_channels", use_sn)], dim=-1)
+    return h + sc
+
+
+_DEEP_G = {512: 4 * [16] + 4 * [8] + [4, 4, 2, 2, 1, 1, 1], 256: 4 * [16] + 4 * [8] + [4, 4, 2, 2, 1],
+           128: 4 * [16] + 2 * [8] + [4, 4, 2, 2, 1], 64: 4 * [16] + 2 * [8] + [4, 4, 2], 32: 8 * [4]}
+_DEEP_D = {512: [1, 1, 1, 2, 2, 4, 4] + 4 * [8] + 4 * [16], 256: [1, 2, 2, 4, 4] + 4 * [8] + 4 * [16],
+           128: [1, 2, 2, 4, 4] + 2 * [8] + 4 * [16], 64: [2, 4, 4] + 2 * [8] + 4 * [16], 32: 8 * [2]}
+
+
+def _gen_biggan_deep(store, cfg, z, y, is_training):
+  """resnet_biggan_deep.Generator.apply — resnet_biggan_deep.py:243-311: z is not chunked, every BN sees [z, embed(y)];
+  blocks alternate none / up; attention after the up block that reaches 64x64."""
+  sn, bn = cfg.g_sn, cfg.g_bn
+  res = cfg.image_shape[0]
+  if res not in _DEEP_G:
+    raise ValueError("Unsupported resolution: {}".format(res))
+  mult = _DEEP_G[res]
+  cin = [cfg.ch * c for c in mult[:-1]]
+  cout = [cfg.ch * c for c in mult[1:]]
+  if cfg.embed_y:
+    y = linear(store, cfg, y, cfg.embed_y_dim, "embed_y", use_sn=False, use_bias=False)
+  if y is not None:
+    y = torch.cat([z, y], dim=1)
+    z = y
+  h = linear(store, cfg, z, cin[0] * 16, "fc_noise", use_sn=sn).reshape(-1, 4, 4, cin[0])
+  for i in range(len(cin)):
+    scale = "none" if i % 2 == 0 else "up"
+    h = biggan_deep_block(store, cfg, h, "B%d" % (i + 1), cin[i], cout[i], scale, y, is_training, bn, sn)
+    if scale == "up" and h.shape[1] == 64:
+      h = non_local_block(store, cfg, h, "non_local_block", sn)
+  h = torch.relu(batch_norm(store, cfg, h, is_training, name="final_norm"))
+  h = conv2d(store, cfg, h, cfg.image_shape[2], 3, 3, 1, "final_conv", use_sn=sn)
+  return (torch.tanh(h) + 1.0) / 2.0
+
+
+def _disc_biggan_deep(store, cfg, x, y, is_training):
+  """resnet_biggan_deep.Discriminator.apply — resnet_biggan_deep.py:373-434: initial 3x3 conv, blocks alternate
+  down / none, attention after the none block at 64x64, relu, SUM over space, final_fc (+ projection)."""
+  sn, bn = cfg.d_sn, cfg.d_bn
+  colors, res = x.shape[-1], x.shape[1]
+  if colors not in (1, 3):
+    raise ValueError("Unsupported color channels: {}".format(colors))
+  if res not in _DEEP_D:
+    raise ValueError("Unsupported resolution: {}".format(res))
+  mult = _DEEP_D[res]
+  cin = [cfg.ch * c for c in mult[:-1]]
+  cout = [cfg.ch * c for c in mult[1:]]
+  h = conv2d(store, cfg, x, cin[0], 3, 3, 1, "initial_conv", use_sn=sn)
+  for i in range(len(cin)):
+    scale = "down" if i % 2 == 0 else "none"
+    h = biggan_deep_block(store, cfg, h, "B%d" % (i + 1), cin[i], cout[i], scale, y, is_training, bn, sn)
+    if scale == "none" and h.shape[1] == 64:
+      h = non_local_block(store, cfg, h, "non_local_block", sn)
+  h = torch.relu(h)
+  feat = h.sum(dim=(1, 2))
+  logit = linear(store, cfg, feat, 1, "final_fc", use_sn=sn)
+  if cfg.project_y:
+    if y is None:
+      raise ValueError("You must provide class information y to project.")
+    with store.scope("embedding_fc"):
+      k = store.get("kernel", (y.shape[1], cout[-1]), ("glorot_normal",))
+      if sn:
+        k = spectral_norm(store, cfg, k)
+      emb = y @ k
+    logit = logit + (emb * feat).sum(dim=1, keepdim=True)
+  return torch.sigmoid(logit), logit, feat
+
+
 _GENS = {"dcgan_arch": _gen_dcgan, "resnet_cifar_arch": _gen_resnet_cifar, "sndcgan_arch": _gen_sndcgan,
-         "resnet5_arch": _gen_resnet5, "resnet_biggan_arch": _gen_biggan}
+         "resnet5_arch": _gen_resnet5, "resnet_biggan_arch": _gen_biggan, "resnet_biggan_deep_arch": _gen_biggan_deep}
 _DISCS = {"dcgan_arch": _disc_dcgan, "resnet_cifar_arch": _disc_resnet_cifar, "sndcgan_arch": _disc_sndcgan,
-          "resnet5_arch": _disc_resnet5, "resnet_biggan_arch": _disc_biggan}
+          "resnet5_arch": _disc_resnet5, "resnet_biggan_arch": _disc_biggan, "resnet_biggan_deep_arch": _disc_biggan_deep}
 
 
 def generator(store, cfg, z, y, is_training):

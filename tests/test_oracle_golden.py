@@ -383,3 +383,27 @@ def test_inception_score_and_kid_match_their_estimators():
   gg = sum(k(fake[i], fake[j]) for i in range(m) for j in range(m) if i != j) / (m * (m - 1))
   rg = sum(k(real[i], fake[j]) for i in range(m) for j in range(m)) / (m * m)
   np.testing.assert_allclose(metrics.kid(fake, real), rr + gg - 2 * rg, rtol=1e-10)
+
+
+def test_biggan_deep128_parameter_counts():
+  # architectures/resnet_biggan_deep_test.py:30-60
+  cfg = nets.Cfg(architecture="resnet_biggan_deep_arch", image_shape=(128, 128, 3), g_bn="conditional_batch_norm",
+                 embed_y=True, project_y=True, num_classes=1000, ch=128)
+  store = nets.VarStore()
+  with torch.no_grad():
+    z = torch.zeros(2, 128)
+    y = torch.zeros(2, 1000); y[:, 1] = 1
+    x = nets.generator(store, cfg, z, y, True)
+    assert list(x.shape) == [2, 128, 128, 3]
+    out = nets.discriminator(store, cfg, x, y, True)
+    assert len(out) == 3 and list(out[1].shape) == [2, 1]
+  ng = sum(v.numel() for k, v in store.trainable.items() if k.startswith("generator/"))
+  nd = sum(v.numel() for k, v in store.trainable.items() if k.startswith("discriminator/"))
+  assert ng == G["biggan_deep128_params"]["generator"]
+  assert nd == G["biggan_deep128_params"]["discriminator"]
+  # structure: every BN is conditioned on [z, embed(y)] = 256 wide; the first G block keeps 2048 channels through a
+  # 512-wide bottleneck; D grows channels through `add_channels`; attention sits at 64x64 in both networks
+  assert list(store.vars["generator/B1/conv1/bn/condition/gamma/kernel"].shape) == [256, 2048]
+  assert list(store.vars["generator/B1/conv2/3x3_conv/kernel"].shape) == [3, 3, 512, 512]
+  assert list(store.vars["discriminator/B1/shortcut/add_channels/kernel"].shape) == [1, 1, 128, 128]
+  assert "generator/non_local_block/sigma" in store.vars and "discriminator/non_local_block/sigma" in store.vars
