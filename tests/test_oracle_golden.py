@@ -407,3 +407,32 @@ def test_biggan_deep128_parameter_counts():
   assert list(store.vars["generator/B1/conv2/3x3_conv/kernel"].shape) == [3, 3, 512, 512]
   assert list(store.vars["discriminator/B1/shortcut/add_channels/kernel"].shape) == [1, 1, 128, 128]
   assert "generator/non_local_block/sigma" in store.vars and "discriminator/non_local_block/sigma" in store.vars
+
+
+def test_single_training_step_over_losses_penalties_and_architectures():
+  """modular_gan_test.py:65-97 (testSingleTrainingStepArchitectures / Losses / Penalties): one cycle at batch 2 for
+  every loss, for WGAN-GP, and for every restated architecture, with finite losses and the step-counter rule."""
+  rng = np.random.RandomState(0)
+
+  def one(arch, loss, penalty, conditional=False, **cfg_kw):
+    shape = (32, 32, 3)
+    cfg = nets.Cfg(architecture=arch, image_shape=shape, num_classes=10 if conditional else 0, **cfg_kw)
+    o = gan.GanOracle(cfg, loss=loss, penalty=penalty, lamba=1.0, disc_iters=1, g_lr=2e-4, beta1=0.5, beta2=0.999,
+                      conditional=conditional, z_dim=120 if conditional else 128).build(2)
+    imgs = [rng.rand(2, *shape).astype(np.float32) for _ in range(2)]
+    zs = [rng.uniform(-1, 1, (2, 120 if conditional else 128)).astype(np.float32) for _ in range(2)]
+    labels = [rng.randint(0, 10, 2).astype(np.int32) for _ in range(2)] if conditional else None
+    alphas = [rng.rand(2, 1, 1, 1).astype(np.float32) for _ in range(2)] if penalty == "wgangp_penalty" else None
+    d_losses, g_loss = o.cycle(imgs, zs, labels, labels, alphas)
+    assert np.isfinite(g_loss) and all(np.isfinite(v) for v in d_losses), (arch, loss, penalty)
+    assert o.global_step == 1 and o.global_step_disc == 1
+
+  for loss in ("non_saturating", "hinge", "wasserstein", "least_squares"):
+    one("resnet_cifar_arch", loss, "no_penalty")
+  one("resnet_cifar_arch", "hinge", "wgangp_penalty")
+  for arch in ("sndcgan_arch", "dcgan_arch", "resnet5_arch"):
+    one(arch, "hinge", "no_penalty")
+  one("resnet_biggan_arch", "hinge", "no_penalty", conditional=True, g_bn="conditional_batch_norm", g_sn=True, d_sn=True,
+      hierarchical_z=True, embed_y=True, project_y=True, ch=8, g_attention="B2", d_attention="B1")
+  one("resnet_biggan_deep_arch", "hinge", "no_penalty", conditional=True, g_bn="conditional_batch_norm", g_sn=True,
+      d_sn=True, embed_y=True, project_y=True, ch=8)
