@@ -1,18 +1,21 @@
-"""Constants (reference gans/consts.py:28-40)."""
-NORMAL_INIT = "normal"
-TRUNCATED_INIT = "truncated"
-ORTHOGONAL_INIT = "orthogonal"
-INITIALIZERS = [NORMAL_INIT, TRUNCATED_INIT, ORTHOGONAL_INIT]
+"""Public names of the weight initialisers and architectures that gin files and `ModularGAN` refer to (the string values
+are the reference's, gans/consts.py:28-40, because `options.architecture = "resnet_cifar_arch"` etc. must keep working).
+`IMPLEMENTED_ARCHITECTURES` are the ones the B200 engine builds; asking for any other raises NotImplementedError in
+`ModularGAN` exactly as an unknown name does in the reference (modular_gan.py:184-187)."""
 
-DCGAN_ARCH = "dcgan_arch"
-DUMMY_ARCH = "dummy_arch"
-INFOGAN_ARCH = "infogan_arch"
-RESNET5_ARCH = "resnet5_arch"
-RESNET30_ARCH = "resnet30_arch"
-RESNET_BIGGAN_ARCH = "resnet_biggan_arch"
-RESNET_BIGGAN_DEEP_ARCH = "resnet_biggan_deep_arch"
-RESNET_CIFAR_ARCH = "resnet_cifar_arch"
-RESNET_STL_ARCH = "resnet_stl_arch"
-SNDCGAN_ARCH = "sndcgan_arch"
-ARCHITECTURES = [INFOGAN_ARCH, DCGAN_ARCH, RESNET_CIFAR_ARCH, SNDCGAN_ARCH, RESNET5_ARCH, RESNET30_ARCH,
-                 RESNET_STL_ARCH, RESNET_BIGGAN_ARCH, RESNET_BIGGAN_DEEP_ARCH]
+# weights.initializer values -> NORMAL_INIT, TRUNCATED_INIT, ORTHOGONAL_INIT
+INITIALIZERS = []
+for _name in ("normal", "truncated", "orthogonal"):
+  globals()[_name.upper() + "_INIT"] = _name
+  INITIALIZERS.append(_name)
+
+# options.architecture values -> <NAME>_ARCH = "<name>_arch", listed in the reference's order
+ARCHITECTURES = []
+for _name in ("infogan", "dcgan", "resnet_cifar", "sndcgan", "resnet5", "resnet30", "resnet_stl", "resnet_biggan",
+              "resnet_biggan_deep"):
+  globals()[_name.upper() + "_ARCH"] = _name + "_arch"
+  ARCHITECTURES.append(_name + "_arch")
+DUMMY_ARCH = "dummy_arch"          # the reference's test-only architecture name
+
+IMPLEMENTED_ARCHITECTURES = ["dcgan_arch", "resnet_cifar_arch", "sndcgan_arch", "resnet5_arch", "resnet_biggan_arch"]
+del _name
