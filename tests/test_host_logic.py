@@ -184,3 +184,38 @@ def test_task_manager_checkpoint_polling_and_csv(tmp_path):
   assert [os.path.basename(c) for c in tm.unevaluated_checkpoints(timeout=0)] == ["model.ckpt-0.npz", "model.ckpt-12500.npz"]
   # the base class keeps no results: everything stays unevaluated
   assert len(list(runner_lib.TaskManager(md).unevaluated_checkpoints(timeout=0))) == 4
+
+
+def test_get_losses_routes_every_objective_to_the_fused_kernel(monkeypatch):
+  """loss_lib.get_losses(fn=...) hands the logits to `kernels.gan_losses` with the objective's name, whatever the order
+  in which the reference declares the (probability, logit) arguments (loss_lib.py:53-154)."""
+  from compare_gan_b200 import kernels as K
+  from compare_gan_b200.gans import loss_lib
+  gin.clear_config()
+
+  class T(object):
+    shape = (4, 1)
+  calls = []
+  monkeypatch.setattr(K, "gan_losses", lambda kind, real, fake: calls.append((kind, real, fake)) or "out")
+  d_real, d_fake, lr, lf = T(), T(), T(), T()
+  for fn in (loss_lib.non_saturating, loss_lib.wasserstein, loss_lib.least_squares, loss_lib.hinge):
+    assert loss_lib.get_losses(fn=fn, d_real=d_real, d_fake=d_fake, d_real_logits=lr, d_fake_logits=lf) == "out"
+  assert [c[0] for c in calls] == ["non_saturating", "wasserstein", "least_squares", "hinge"]
+  assert all(c[1] is lr and c[2] is lf for c in calls)
+  gin.parse_config("loss.fn = @hinge")
+  loss_lib.get_losses(d_real=d_real, d_fake=d_fake, d_real_logits=lr, d_fake_logits=lf)
+  assert calls[-1][0] == "hinge"
+  gin.clear_config()
+
+
+def test_kid_follows_the_reference_block_estimator_for_unequal_sets():
+  """metrics/kid_score.py:44-149 incl. its bin-size quirks: the host code (Gram matrices injected, so no GPU) against
+  the line-by-line restatement in the oracle, for equal and unequal set sizes and several blocks."""
+  from compare_gan_b200.metrics import kid_score
+  from oracle import metrics as ometrics
+  rng = np.random.RandomState(0)
+  gram = lambda a, b: np.asarray(a, np.float64) @ np.asarray(b, np.float64).T
+  for n_real, n_fake, block in [(12, 12, 1024), (50, 50, 16), (37, 41, 10), (64, 50, 16), (41, 37, 10), (200, 190, 64), (17, 23, 5)]:
+    real, fake = rng.randn(n_real, 6), rng.randn(n_fake, 6) + 0.2
+    np.testing.assert_allclose(kid_score.kid(fake, real, max_batch_size=block, gram=gram),
+                               ometrics.kid(fake, real, max_batch_size=block), rtol=1e-12, err_msg=str((n_real, n_fake, block)))
