@@ -1,0 +1,39 @@
+"""The package's REAL host code — taped ops and their vector-Jacobian products (kernels.py), the tape, flat variable
+packing, ModularGAN's unrolled cycle with Adam / EMA / step counters, checkpoints, the schedules of runner_lib — executed
+on the CPU against `tests/abi_emulator.py` (a numpy restatement of the C-ABI contract) and compared with the oracle.
+No GPU and no CUDA library involved: what is checked here is everything ABOVE the C-ABI; the kernels BELOW it are
+checked against the same oracle by the `-m gpu` tests."""
+import pytest
+
+from tests.abi_emulator import emulated_library
+
+
+# The GPU parity tests whose bodies are pure host code + C-ABI calls: the same functions, run against the emulator.
+STEP_TESTS = ["test_resnet_cifar_forward", "test_resnet_cifar_cycle_sn_bn", "test_resnet_cifar_cycle_hinge_gsn_ema",
+              "test_sndcgan_forward_and_cycle", "test_dcgan_forward_and_cycle", "test_resnet5_wgangp_cycle",
+              "test_biggan_forward_and_cycle", "test_initialisation_rules_and_training_determinism"]
+EVAL_TESTS = ["test_resize_bilinear_matches_tf_semantics", "test_pool2d_tf_semantics", "test_inception_v3_features",
+              "test_train_from_input_pipeline", "test_eval_after_train_schedule_and_checkpoint_roundtrip"]
+
+
+@pytest.mark.parametrize("name", STEP_TESTS)
+def test_training_step_suite_on_the_emulator(name):
+  """Forward passes, full cycles (losses, gradients incl. the WGAN-GP double backward, post-Adam weights, EMA, BN state,
+  step counters) of every architecture, engine vs oracle — tests/test_gan_step_gpu.py executed above the emulated ABI."""
+  import tests.test_gan_step_gpu as gpu_tests
+  with emulated_library() as lib:
+    getattr(gpu_tests, name)()
+    assert lib.launches > 0
+
+
+@pytest.mark.parametrize("name", EVAL_TESTS)
+def test_evaluation_and_schedule_suite_on_the_emulator(name, tmp_path):
+  """Resize / pooling semantics, the concat-free Inception-v3 graph, pipeline-fed training, and the eval_after_train
+  schedule (training, checkpoint in the reference's key space, FID / IS evaluation of the checkpoint, scores.csv,
+  bit-exact checkpoint reload) — tests/test_eval_gpu.py executed above the emulated ABI."""
+  import inspect
+  import tests.test_eval_gpu as gpu_tests
+  from compare_gan_b200 import kernels as K
+  fn = getattr(gpu_tests, name)
+  with emulated_library():
+    fn(K, tmp_path) if "tmp_path" in inspect.signature(fn).parameters else fn(K)

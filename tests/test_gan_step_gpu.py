@@ -21,7 +21,7 @@ def _forward_both(eng, orc, batch, z_dim, num_classes=0, z_normal=False):
   labels = rng.randint(0, num_classes, batch).astype(np.int32) if num_classes else None
   snap = eng.snapshot()
   with V.use(eng.store), tape.no_record():
-    y = K.one_hot(tape.DT(torch.from_numpy(labels).cuda()), num_classes) if num_classes else None
+    y = K.one_hot(tape.DT(torch.from_numpy(labels).to(K._RT["device"])), num_classes) if num_classes else None
     img = eng.generator(K.from_numpy(z), y=y, is_training=True)
     d, logit, h = eng.discriminator(img, y=y, is_training=True)
   with torch.no_grad():
