@@ -17,5 +17,6 @@ for _name in ("infogan", "dcgan", "resnet_cifar", "sndcgan", "resnet5", "resnet3
   ARCHITECTURES.append(_name + "_arch")
 DUMMY_ARCH = "dummy_arch"          # the reference's test-only architecture name
 
-IMPLEMENTED_ARCHITECTURES = ["dcgan_arch", "resnet_cifar_arch", "sndcgan_arch", "resnet5_arch", "resnet_biggan_arch"]
+IMPLEMENTED_ARCHITECTURES = ["dcgan_arch", "resnet_cifar_arch", "sndcgan_arch", "resnet5_arch", "resnet_biggan_arch",
+                             "resnet_biggan_deep_arch"]
 del _name

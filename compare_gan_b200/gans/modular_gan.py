@@ -16,7 +16,7 @@ from .. import gin_lite as gin
 from .. import kernels as K
 from .. import tape
 from .. import variables as V
-from ..architectures import dcgan, resnet5, resnet_biggan, resnet_cifar, sndcgan
+from ..architectures import dcgan, resnet5, resnet_biggan, resnet_biggan_deep, resnet_cifar, sndcgan
 from ..tpu import tpu_ops
 from . import consts, loss_lib, penalty_lib
 from .abstract_gan import AbstractGAN
@@ -96,6 +96,7 @@ class ModularGAN(AbstractGAN):
   def generator(self):
     if self._generator is None:
       module = {consts.RESNET5_ARCH: resnet5, consts.RESNET_BIGGAN_ARCH: resnet_biggan, consts.DCGAN_ARCH: dcgan,
+                consts.RESNET_BIGGAN_DEEP_ARCH: resnet_biggan_deep,
                 consts.RESNET_CIFAR_ARCH: resnet_cifar, consts.SNDCGAN_ARCH: sndcgan}.get(self._architecture)
       if module is None:
         raise NotImplementedError("Architecture {} not implemented.".format(self._architecture))
@@ -106,6 +107,7 @@ class ModularGAN(AbstractGAN):
   def discriminator(self):
     if self._discriminator is None:
       module = {consts.RESNET5_ARCH: resnet5, consts.RESNET_BIGGAN_ARCH: resnet_biggan, consts.DCGAN_ARCH: dcgan,
+                consts.RESNET_BIGGAN_DEEP_ARCH: resnet_biggan_deep,
                 consts.RESNET_CIFAR_ARCH: resnet_cifar, consts.SNDCGAN_ARCH: sndcgan}.get(self._architecture)
       if module is None:
         raise NotImplementedError("Architecture {} not implemented.".format(self._architecture))

@@ -396,6 +396,26 @@ def avgpool2_bwd(g, h, w):
   return attach("avgpool2_bwd", dx, [g], lambda gg, needs: [avgpool2(gg)])
 
 
+_UNPOOL_MASKS = {}
+
+
+def unpool(x):
+  """resnet_ops.unpool materialised (resnet_ops.py:35-56): zero insertion to twice the size, x at the even positions.
+  Only the identity shortcut of resnet_biggan_deep's up blocks needs the tensor itself (convolutions over an unpooled
+  input use conv2d(upsample=True) and never build it).  Composed of two existing kernels: avgpool2's adjoint spreads
+  x / 4 over each 2x2 cell, a per-pixel scale (4 at the even-even pixel, 0 elsewhere) keeps the corner — exact in fp32,
+  and differentiable to any order because both parts are taped ops."""
+  import numpy as np
+  n, h, w, c = x.shape
+  key = (n, h, w, str(_RT["device"]))
+  if key not in _UNPOOL_MASKS:          # built once per shape, i.e. during the eager warm-up that precedes graph capture
+    cell = np.zeros((2 * h, 2 * w), np.float32)
+    cell[::2, ::2] = 4.0
+    _UNPOOL_MASKS[key] = from_numpy(np.tile(cell.reshape(1, -1), (n, 1)).reshape(-1))
+  spread = avgpool2_bwd(x, 2 * h, 2 * w)
+  return reshape(rowscale(reshape(spread, -1, c), _UNPOOL_MASKS[key]), n, 2 * h, 2 * w, c)
+
+
 def maxpool2(x):
   """tf.layers.max_pooling2d(2, 2) (arch_ops.py:741, 750)."""
   n, h, w, c = x.shape

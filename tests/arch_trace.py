@@ -125,6 +125,7 @@ SHAPE_RULES = {
     "rowdot": lambda a, b: (a.shape[0], 1),
     "maxpool2": lambda x: (x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]),
     "avgpool2": lambda x: (x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]),
+    "unpool": lambda x: (x.shape[0], 2 * x.shape[1], 2 * x.shape[2], x.shape[3]),
     "matmul": _matmul, "bmm": _bmm, "conv2d": _conv2d, "deconv2d": _deconv2d,
     "one_hot": lambda labels, classes: (labels.shape[0], classes),
 }
@@ -238,6 +239,12 @@ CASES = {
                                 "resnet_biggan.Discriminator.ch = 8\nresnet_biggan.Discriminator.project_y = True",
                        architecture="resnet_biggan_arch", image_shape=(128, 128, 3), z_dim=120, num_classes=1000,
                        conditional=True),
+    "biggan_deep_64": dict(gin_text="G.batch_norm_fn = @conditional_batch_norm\nG.spectral_norm = True\nD.spectral_norm = True\n"
+                                    "spectral_norm.singular_value = 'auto'\nweights.initializer = 'orthogonal'\n"
+                                    "standardize_batch.use_moving_averages = False\nresnet_biggan_deep.Generator.ch = 4\n"
+                                    "resnet_biggan_deep.Discriminator.ch = 4",
+                           architecture="resnet_biggan_deep_arch", image_shape=(64, 64, 3), z_dim=128, num_classes=10,
+                           conditional=True),
     "biggan_128_unconditional_plain": dict(gin_text="G.batch_norm_fn = @batch_norm\nresnet_biggan.Generator.ch = 8\n"
                                                     "resnet_biggan.Discriminator.ch = 8\n"
                                                     "resnet_biggan.Generator.hierarchical_z = False\n"

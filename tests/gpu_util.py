@@ -58,6 +58,9 @@ def make_pair(arch, image_shape, batch, loss="non_saturating", penalty="no_penal
       "resnet_biggan.Generator.ch = %d" % ch,
       "resnet_biggan.Discriminator.ch = %d" % ch,
       "resnet_biggan.Discriminator.project_y = %s" % project_y,
+      "resnet_biggan_deep.Generator.ch = %d" % ch,
+      "resnet_biggan_deep.Discriminator.ch = %d" % ch,
+      "resnet_biggan_deep.Discriminator.project_y = %s" % project_y,
       "resnet_cifar.Discriminator.project_y = %s" % project_y,
       "ModularGAN.math_mode = %d" % math_mode,
   ]
@@ -74,7 +77,7 @@ def make_pair(arch, image_shape, batch, loss="non_saturating", penalty="no_penal
   ocfg = onets.Cfg(architecture=arch, image_shape=tuple(image_shape), g_bn=g_bn, g_sn=g_sn, d_sn=d_sn,
                    sn_singular=sn_singular, bn_decay=bn_decay, bn_eps=bn_eps,
                    use_moving_averages=use_moving_averages, initializer=initializer, ch=ch, project_y=project_y,
-                   hierarchical_z=hier, embed_y=hier, num_classes=num_classes)
+                   hierarchical_z=hier, embed_y=hier or arch == "resnet_biggan_deep_arch", num_classes=num_classes)
   for b in extra_bindings:
     if "Generator.blocks_with_attention" in b:
       ocfg.g_attention = b.split("=")[1].strip().strip("'\"")

@@ -11,7 +11,8 @@ from tests.abi_emulator import emulated_library
 # The GPU parity tests whose bodies are pure host code + C-ABI calls: the same functions, run against the emulator.
 STEP_TESTS = ["test_resnet_cifar_forward", "test_resnet_cifar_cycle_sn_bn", "test_resnet_cifar_cycle_hinge_gsn_ema",
               "test_sndcgan_forward_and_cycle", "test_dcgan_forward_and_cycle", "test_resnet5_wgangp_cycle",
-              "test_biggan_forward_and_cycle", "test_initialisation_rules_and_training_determinism"]
+              "test_biggan_forward_and_cycle", "test_biggan_deep_forward_and_cycle",
+              "test_initialisation_rules_and_training_determinism"]
 EVAL_TESTS = ["test_resize_bilinear_matches_tf_semantics", "test_pool2d_tf_semantics", "test_inception_v3_features",
               "test_train_from_input_pipeline", "test_eval_after_train_schedule_and_checkpoint_roundtrip"]
 

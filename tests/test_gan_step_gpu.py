@@ -270,3 +270,17 @@ def test_initialisation_rules_and_training_determinism():
   assert steps_a == steps_b == 3
   for name, t0 in final_a.items():
     np.testing.assert_array_equal(t0, final_b[name], err_msg=name)
+
+
+def test_biggan_deep_forward_and_cycle():
+  # resnet_biggan_deep: bottleneck blocks, channel-dropping / channel-appending identity shortcuts
+  # (the up-sampling one through kernels.unpool), un-chunked z, attention at 64x64
+  kw = dict(loss="hinge", g_bn="conditional_batch_norm", g_sn=True, d_sn=True, sn_singular="auto", conditional=True,
+            num_classes=10, initializer="orthogonal", use_moving_averages=False, g_lr=1e-4, d_lr=5e-4, beta1=0.0,
+            beta2=0.999, z_dim=128, ch=4, project_y=True)
+  eng, orc = make_pair("resnet_biggan_deep_arch", (64, 64, 3), 2, disc_iters=1, **kw)
+  eng.store.vars["generator/non_local_block/sigma"].t.fill_(0.5)
+  orc.store.load_numpy(eng.state_numpy())
+  _forward_both(eng, orc, 2, 128, num_classes=10, z_normal=True)
+  _cycles_both(eng, orc, 2, (64, 64, 3), 128, 1, num_classes=10, z_normal=True, g_lr=1e-4, d_lr=5e-4, grad_tol=2e-3,
+               loss_tol=3e-3)
