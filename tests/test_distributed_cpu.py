@@ -66,3 +66,68 @@ def test_two_replica_exchange_logic():
     np.testing.assert_allclose(res[r]["mean"], G["cross_replica_mean"]["expected"], atol=1e-6)
     np.testing.assert_allclose(res[r]["bn"], exp_bn[2 * r:2 * r + 2], rtol=1e-5, atol=1e-5)
     assert abs(res[r]["grad"] - 1.5) < 1e-6
+
+
+def _engine_worker(rank, world, port, q):
+  """One data-parallel rank of the whole training cycle: the engine's host code above the emulated C-ABI
+  (tests/abi_emulator.py), collectives over gloo."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  torch.set_num_threads(2)
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  from tests.abi_emulator import emulated_library
+  from tests.dist_gpu_check import build
+  from compare_gan_b200.tpu import tpu_ops
+  per = 2
+  rng = np.random.RandomState(0)
+  imgs = [rng.rand(per * world, 32, 32, 3).astype(np.float32) for _ in range(2)]
+  zs = [rng.uniform(-1, 1, (per * world, 128)).astype(np.float32) for _ in range(2)]
+  out = {}
+  with emulated_library():
+    eng = build(per)
+    sl = slice(rank * per, (rank + 1) * per)
+    eng.set_inputs([a[sl] for a in imgs], [a[sl] for a in zs])
+    eng.run_cycle()
+    out["d_grad"] = eng.flat_d["grad"].cpu() / world          # all-reduced sums -> means
+    out["g_grad"] = eng.flat_g["grad"].cpu() / world
+    out["state"] = {k: v for k, v in eng.state_numpy().items() if "moving_" in k or k.endswith("u_var")}
+    dist.barrier()
+    if rank == 0:                                              # the same cycle alone on the concatenated batch
+      tpu_ops.force_local(True)
+      ref = build(per * world)
+      ref.set_inputs(imgs, zs)
+      ref.run_cycle()
+      out["ref_d_grad"], out["ref_g_grad"] = ref.flat_d["grad"].cpu(), ref.flat_g["grad"].cpu()
+      out["ref_state"] = {k: v for k, v in ref.state_numpy().items() if k in out["state"]}
+      tpu_ops.force_local(False)
+  q.put((rank, out))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_rank_training_cycle_equals_one_rank_on_the_concatenated_batch():
+  """SURVEY §8e acceptance, on the CPU: two ranks, each on its shard, with the flat-gradient all-reduce after the D and
+  the G update and cross-replica BN moments (forward) / sums (backward), reproduce the single-rank cycle on the whole
+  batch — the analogue of arch_ops_tpu_test.py:112-133 for the full step (tests/dist_gpu_check.py is the NCCL twin)."""
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = dict(q.get(timeout=600) for _ in range(2))
+  for p in procs:
+    p.join(60)
+    assert p.exitcode == 0
+
+  def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+  r0 = res[0]
+  np.testing.assert_array_equal(res[0]["d_grad"], res[1]["d_grad"])      # both ranks hold the same reduced gradients
+  np.testing.assert_array_equal(res[0]["g_grad"], res[1]["g_grad"])
+  assert rel(r0["d_grad"], r0["ref_d_grad"]) < 1e-4 and rel(r0["g_grad"], r0["ref_g_grad"]) < 2e-3
+  for k, v in r0["ref_state"].items():
+    assert rel(r0["state"][k], v) < 1e-5, k                               # BN moving stats (sync-BN) and SN u vectors
+    np.testing.assert_array_equal(res[0]["state"][k], res[1]["state"][k], err_msg=k)
