@@ -102,6 +102,15 @@ def _engine_worker(rank, world, port, q):
       out["ref_d_grad"], out["ref_g_grad"] = ref.flat_d["grad"].cpu(), ref.flat_g["grad"].cpu()
       out["ref_state"] = {k: v for k, v in ref.state_numpy().items() if k in out["state"]}
       tpu_ops.force_local(False)
+    # sharded evaluation statistics: every rank streams its shard of the activations into float64
+    # (n, sum x, sum x x^T); FeatureAccumulator.finish all-reduces them -> moments of the whole set on every rank
+    from compare_gan_b200 import eval_utils, kernels as K
+    acts = np.random.RandomState(7).randn(12, 16).astype(np.float32)
+    acc = eval_utils.FeatureAccumulator(dim=16, keep_features=False)
+    mine = acts[rank::world]
+    acc.add(K.from_numpy(mine), K.from_numpy(np.zeros((len(mine), 4), np.float32)), len(mine))
+    sample = acc.finish(eval_utils.EvalDataSample())
+    out["eval_n"], out["eval_mu"], out["eval_sigma"] = acc.n, sample.moments[0], sample.moments[1]
   q.put((rank, out))
   dist.barrier()
   dist.destroy_process_group()
@@ -131,3 +140,8 @@ def test_two_rank_training_cycle_equals_one_rank_on_the_concatenated_batch():
   for k, v in r0["ref_state"].items():
     assert rel(r0["state"][k], v) < 1e-5, k                               # BN moving stats (sync-BN) and SN u vectors
     np.testing.assert_array_equal(res[0]["state"][k], res[1]["state"][k], err_msg=k)
+  acts = np.random.RandomState(7).randn(12, 16).astype(np.float32).astype(np.float64)
+  for r in (0, 1):
+    assert res[r]["eval_n"] == 12
+    np.testing.assert_allclose(res[r]["eval_mu"], acts.mean(0), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(res[r]["eval_sigma"], np.cov(acts, rowvar=False, ddof=1), rtol=1e-10, atol=1e-12)
