@@ -38,3 +38,45 @@ def test_evaluation_and_schedule_suite_on_the_emulator(name, tmp_path):
   fn = getattr(gpu_tests, name)
   with emulated_library():
     fn(K, tmp_path) if "tmp_path" in inspect.signature(fn).parameters else fn(K)
+
+
+def _kernel_test_cases():
+  """Every case of tests/test_kernels_gpu.py (parametrisations expanded by hand: the functions are called directly)."""
+  import inspect
+  import itertools
+  import tests.test_kernels_gpu as kt
+  for name, fn in inspect.getmembers(kt, inspect.isfunction):
+    if not name.startswith("test_"):
+      continue
+    grids = []
+    for mark in [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]:
+      names = [n.strip() for n in mark.args[0].split(",")]
+      grids.append([dict(zip(names, v if len(names) > 1 else (v,))) for v in mark.args[1]])
+    for combo in itertools.product(*grids):
+      kw = {}
+      for part in combo:
+        kw.update(part)
+      yield name, fn, kw
+
+
+def test_emulator_conforms_to_the_kernel_parity_suite():
+  """The per-op parity tests define what each C-ABI entry must compute (against the oracle).  Running them against the
+  emulator shows that the emulator — on which the host-code tests above rest — honours the same contract.  Only the
+  assertions that the tcgen05 path was TAKEN (launch counts of the tensor-core kernels) are specific to the real
+  library and are skipped."""
+  import inspect
+  from compare_gan_b200 import kernels as K
+  ran = 0
+  for name, fn, kw in _kernel_test_cases():
+    if "K" in inspect.signature(fn).parameters:
+      kw["K"] = K
+    try:
+      with emulated_library():
+        fn(**kw)
+    except AssertionError as e:
+      msg = str(e)
+      path_assertion = ("tcgen05" in name or "tc_" in name) and "rel-L2" not in msg      # "which kernels ran", not numerics
+      if not path_assertion:
+        raise AssertionError("%s %s: %s" % (name, kw, msg))
+    ran += 1
+  assert ran > 100

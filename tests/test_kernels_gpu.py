@@ -260,7 +260,7 @@ def test_concat_slice_onehot_rowdot(K):
   assert_close(gs.cpu(), full, 0, "slice grad")
   labels = np.array([1, 0, 3, 2], np.int32)
   from compare_gan_b200.tape import DT
-  oh = K.one_hot(DT(torch.from_numpy(labels).cuda()), 5)
+  oh = K.one_hot(DT(torch.from_numpy(labels).to(K._RT["device"])), 5)
   assert_close(oh.cpu(), np.eye(5, dtype=np.float32)[labels], 0, "one_hot")
   c = rng.randn(4, 6).astype(np.float32)
   cd = dev(K, c, True)
@@ -326,11 +326,12 @@ def test_adam_and_ema(K):
   pd = dev(K, p0)
   m, v = K.zeros(n), K.zeros(n)
   ema = dev(K, p0)
-  step = torch.zeros(1, dtype=torch.int32, device="cuda")
+  step = torch.zeros(1, dtype=torch.int32, device=K._RT["device"])
   ema_ref = p0.copy()
   for i, g in enumerate((g1, g2)):
     opt.step({"p": torch.from_numpy(g)})
-    K._call("adam_step", pd.ptr, dev(K, g * 2).ptr, m.ptr, v.ptr, n, 2e-4, 0.5, 0.999, 1e-8, 0.5, step.data_ptr(),
+    gd = dev(K, g * 2)          # held until the call returns (a temporary's storage may be recycled)
+    K._call("adam_step", pd.ptr, gd.ptr, m.ptr, v.ptr, n, 2e-4, 0.5, 0.999, 1e-8, 0.5, step.data_ptr(),
             ema.ptr, 0.9, 1)
     decay = 0.9 * float(i >= 1)
     ema_ref = ema_ref - (ema_ref - pt.numpy()) * (1 - decay)
@@ -354,10 +355,11 @@ def test_cov_accumulate_and_fid(K):
   rng = np.random.RandomState(7)
   n, d = 300, 70
   acts = [rng.randn(n, d).astype(np.float32) + 0.3 * i for i in range(2)]
-  s = torch.zeros(d, dtype=torch.float64, device="cuda")
-  sxx = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+  s = torch.zeros(d, dtype=torch.float64, device=K._RT["device"])
+  sxx = torch.zeros(d, d, dtype=torch.float64, device=K._RT["device"])
   for a in acts:
-    K._call("cov_accumulate", dev(K, a).ptr, n, d, s.data_ptr(), sxx.data_ptr())
+    ad = dev(K, a)              # held until the call returns
+    K._call("cov_accumulate", ad.ptr, n, d, s.data_ptr(), sxx.data_ptr())
   allact = np.concatenate(acts).astype(np.float64)
   np.testing.assert_allclose(s.cpu().numpy(), allact.sum(0), rtol=1e-12)
   np.testing.assert_allclose(sxx.cpu().numpy(), allact.T @ allact, rtol=1e-11, atol=1e-9)
