@@ -80,3 +80,20 @@ def test_emulator_conforms_to_the_kernel_parity_suite():
         raise AssertionError("%s %s: %s" % (name, kw, msg))
     ran += 1
   assert ran > 100
+
+
+@pytest.mark.parametrize("loss", ["non_saturating", "hinge", "wasserstein", "least_squares"])
+def test_every_objective_through_a_full_cycle(loss):
+  """modular_gan_test.py:77-80 (testSingleTrainingStepLosses), with numbers: one resnet_cifar cycle per objective, engine
+  (loss_lib routing -> fused loss op -> tape) against the oracle."""
+  import numpy as np
+  from tests.gpu_util import compare_grads, make_inputs, make_pair
+  with emulated_library():
+    eng, orc = make_pair("resnet_cifar_arch", (32, 32, 3), 2, d_sn=True, disc_iters=1, loss=loss)
+    inputs = make_inputs(np.random.RandomState(11), 1, 2, (32, 32, 3), 128)
+    eng.set_inputs(*inputs)
+    eng.run_cycle()
+    d_losses, g_loss = eng.read_losses()
+    ref_d, ref_g = orc.cycle(*inputs)
+    assert abs(d_losses[0] - ref_d[0]) <= 1e-4 * max(1.0, abs(ref_d[0])) and abs(g_loss - ref_g) <= 1e-4 * max(1.0, abs(ref_g))
+    compare_grads(eng, orc, 2e-3, g_tol=5e-2)
