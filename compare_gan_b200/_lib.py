@@ -19,6 +19,17 @@ class ConvDesc(ctypes.Structure):
               ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "upsample", "oh", "ow", "pad_t", "pad_l")]
 
 
+class ConvEpilogue(ctypes.Structure):
+  """cgan_conv_epilogue (include/cgan_b200.h)."""
+  _fields_ = [("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("mask", ctypes.c_void_p),
+              ("mask_leak", ctypes.c_float), ("flags", ctypes.c_int32), ("ldy", ctypes.c_int32)]
+
+
+CONV_RELU, CONV_ROUND_OUT, CONV_IN_TF32, CONV_IN2_TF32 = 1, 2, 4, 8
+ACT_ROUND_TF32 = 0x100
+OPT_TC_MT, OPT_LAST_PATH = 1, 2
+PATH_NAMES = {0: "simt_fp32", 1: "tcgen05_tf32", 2: "thin_fp32"}
+
 _SCALARS = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64,
             "float": ctypes.c_float, "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64}
 
@@ -93,6 +104,14 @@ class Lib(object):
 
   def launch_count(self):
     return int(self.fn["cgan_launch_count"](self.ctx))
+
+  def set_option(self, key, value):
+    self.call("ctx_set_option", int(key), int(value))
+
+  def get_option(self, key):
+    v = ctypes.c_int64(0)
+    self.call("ctx_get_option", int(key), ctypes.byref(v))
+    return int(v.value)
 
   def close(self):
     if self.ctx:

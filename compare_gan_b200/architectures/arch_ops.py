@@ -13,6 +13,19 @@ from ..gans import consts
 from ..tpu import tpu_ops
 
 
+# test hook: callables fn(scope_name, tensor) receiving the output of every linear / un-fused conv2d / deconv2d /
+# non_local_block / residual block, keyed by the variable scope it ran in (the oracle has the same hook)
+ACT_OBSERVERS = []
+
+
+def observe(y, suffix=None):
+  if ACT_OBSERVERS:
+    name = "/".join(V.current()._scope + ([suffix] if suffix else []))
+    for fn in ACT_OBSERVERS:
+      fn(name, y)
+  return y
+
+
 # ----------------------------------------------------------------------------- initializers
 
 def _normal(stddev):
@@ -90,9 +103,10 @@ def _bn_state(c, use_moving_averages):
 @gin.configurable(whitelist=["decay", "epsilon", "use_cross_replica_mean", "use_moving_averages"])
 def standardize_batch(inputs, is_training, decay=0.999, epsilon=1e-3, data_format="NHWC",
                       use_moving_averages=True, use_cross_replica_mean=None,
-                      _gamma=None, _beta=None, _cond=False, _relu=False):
+                      _gamma=None, _beta=None, _cond=False, _relu=False, _tf32=False):
   """Batch standardisation (reference arch_ops.py:194-319).  The private `_gamma/_beta` arguments let
-  batch_norm / conditional_batch_norm fuse their scale+offset into the same kernel."""
+  batch_norm / conditional_batch_norm fuse their scale+offset (and a following ReLU) into the same kernel; `_tf32`
+  says that the result only feeds tensor-core contractions (it is then stored TF32-rounded in math_mode 1)."""
   if data_format not in {"NCHW", "NHWC"}:
     raise ValueError("Invalid data_format {}. Allowed: NCHW, NHWC.".format(data_format))
   if data_format != "NHWC":
@@ -107,8 +121,9 @@ def standardize_batch(inputs, is_training, decay=0.999, epsilon=1e-3, data_forma
   if is_training:
     return K.bn_train(inputs, _gamma, _beta, epsilon, st if use_moving_averages else None, decay, cond=_cond,
                       relu_after=_relu, allreduce=tpu_ops.cross_replica_sum_ if use_cross_replica_mean else None,
-                      world=tpu_ops.num_replicas() if use_cross_replica_mean else 1)
-  return K.bn_infer(inputs, _gamma, _beta, epsilon, st, use_moving_averages, cond=_cond, relu_after=_relu)
+                      world=tpu_ops.num_replicas() if use_cross_replica_mean else 1, round_out=_tf32)
+  return K.bn_infer(inputs, _gamma, _beta, epsilon, st, use_moving_averages, cond=_cond, relu_after=_relu,
+                    round_out=_tf32)
 
 
 @gin.configurable(blacklist=["inputs"])
@@ -117,7 +132,7 @@ def no_batch_norm(inputs):
 
 
 @gin.configurable(blacklist=["inputs", "is_training", "center", "scale", "name"])
-def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm", _relu=False):
+def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm", _relu=False, _tf32=False):
   """Vanilla batch norm with trainable gamma/beta (reference arch_ops.py:327-367)."""
   with V.variable_scope(name):
     c = inputs.shape[-1]
@@ -125,7 +140,7 @@ def batch_norm(inputs, is_training, center=True, scale=True, name="batch_norm", 
     _bn_state_peek(c)
     gamma = V.get_variable("gamma", (c,), ones_init) if scale else None
     beta = V.get_variable("beta", (c,), zeros_init) if center else None
-    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _relu=_relu)
+    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _relu=_relu, _tf32=_tf32)
 
 
 def _bn_state_peek(c):
@@ -136,7 +151,7 @@ def _bn_state_peek(c):
 
 @gin.configurable(whitelist=["use_bias"])
 def conditional_batch_norm(inputs, y, is_training, use_sn, center=True, scale=True, name="batch_norm",
-                           use_bias=False, _relu=False):
+                           use_bias=False, _relu=False, _tf32=False):
   """Conditional batch normalization (reference arch_ops.py:423-445): gamma(y), beta(y) = linear(y)."""
   if y is None:
     raise ValueError("You must provide y for conditional batch normalization.")
@@ -151,17 +166,24 @@ def conditional_batch_norm(inputs, y, is_training, use_sn, center=True, scale=Tr
         gamma = linear(y, c, scope="gamma", use_sn=use_sn, use_bias=use_bias)
       if center:
         beta = linear(y, c, scope="beta", use_sn=use_sn, use_bias=use_bias)
-    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _cond=True, _relu=_relu)
+    return standardize_batch(inputs, is_training=is_training, _gamma=gamma, _beta=beta, _cond=True, _relu=_relu,
+                             _tf32=_tf32)
 
 
-def norm_relu(norm_fn, inputs, **kwargs):
+def configured_norm(norm_fn):
+  """The gin-configured normaliser behind a network's `batch_norm` method (None when it is the identity)."""
+  net = getattr(norm_fn, "__self__", None)
+  fn = getattr(net, "_batch_norm_fn", None) if net is not None else None
+  return None if fn is no_batch_norm else fn
+
+
+def norm_relu(norm_fn, inputs, _tf32=False, **kwargs):
   """relu(norm_fn(inputs)): when the configured normaliser is one of the BN kernels above, the ReLU is fused into the
-  BN-apply kernel (one pass over the activation instead of two); any other normaliser is followed by a plain ReLU."""
-  fn = getattr(norm_fn, "__self__", None)
-  bn_fn = getattr(fn, "_batch_norm_fn", None) if fn is not None else None
-  if bn_fn in (batch_norm, conditional_batch_norm):
-    return norm_fn(inputs, _relu=True, **kwargs)
-  return K.relu(norm_fn(inputs, **kwargs))
+  BN-apply kernel (one pass over the activation instead of two); any other normaliser is followed by a plain ReLU.
+  `_tf32`: the result only feeds tensor-core contractions (stored TF32-rounded in math_mode 1)."""
+  if configured_norm(norm_fn) in (batch_norm, conditional_batch_norm):
+    return norm_fn(inputs, _relu=True, _tf32=_tf32, **kwargs)
+  return K.relu(norm_fn(inputs, **kwargs), round_tf32=_tf32)
 
 
 # ----------------------------------------------------------------------------- spectral norm
@@ -194,13 +216,13 @@ def linear(inputs, output_size, scope=None, stddev=0.02, bias_start=0.0, use_sn=
     if use_bias:
       bias = V.get_variable("bias", (output_size,), constant_init(bias_start))
       outputs = K.bias_add(outputs, bias)
-    return outputs
+    return observe(outputs)
 
 
 def conv2d(inputs, output_dim, k_h, k_w, d_h, d_w, stddev=0.02, name="conv2d", use_sn=False, use_bias=True,
-           _upsample=False):
+           _upsample=False, _relu=False, _residual=None, _tf32=False):
   """2-D convolution, SAME padding (reference arch_ops.py:559-573).  `_upsample` fuses the preceding
-  resnet_ops.unpool."""
+  resnet_ops.unpool; `_residual` / `_relu` / `_tf32` are the epilogue fusions of kernels.conv2d."""
   if d_h != d_w:
     raise ValueError("Only square strides are supported.")
   with V.variable_scope(name):
@@ -208,7 +230,8 @@ def conv2d(inputs, output_dim, k_h, k_w, d_h, d_w, stddev=0.02, name="conv2d", u
     if use_sn:
       w = spectral_norm(w)
     bias = V.get_variable("bias", (output_dim,), zeros_init) if use_bias else None
-    return K.conv2d(inputs, w, bias, stride=d_h, upsample=_upsample)
+    y = K.conv2d(inputs, w, bias, stride=d_h, upsample=_upsample, relu=_relu, residual=_residual, round_out=_tf32)
+    return y if (_relu or _residual is not None) else observe(y)
 
 
 conv1x1 = functools.partial(conv2d, k_h=1, k_w=1, d_h=1, d_w=1)
@@ -222,12 +245,12 @@ def deconv2d(inputs, output_shape, k_h, k_w, d_h, d_w, stddev=0.02, name="deconv
     if use_sn:
       w = spectral_norm(w)
     bias = V.get_variable("bias", (output_shape[-1],), zeros_init)
-    return K.deconv2d(inputs, w, bias, (output_shape[1], output_shape[2]), d_h)
+    return observe(K.deconv2d(inputs, w, bias, (output_shape[1], output_shape[2]), d_h))
 
 
-def lrelu(inputs, leak=0.2, name="lrelu"):
+def lrelu(inputs, leak=0.2, name="lrelu", _tf32=False):
   """Leaky ReLU max(x, leak*x) (reference arch_ops.py:595-597)."""
-  return K.lrelu(inputs, leak)
+  return K.lrelu(inputs, leak, round_tf32=_tf32)
 
 
 def non_local_block(x, name, use_sn):
@@ -250,4 +273,4 @@ def non_local_block(x, name, use_sn):
     attn_g = K.reshape(attn_g, n, h, w, num_channels_g)
     sigma = V.get_variable("sigma", (), zeros_init)
     attn_g = conv1x1(attn_g, num_channels, name="conv2d_attn_g", use_sn=use_sn, use_bias=False)
-    return K.add(x, K.scale_by_param(attn_g, sigma))
+    return observe(K.add(x, K.scale_by_param(attn_g, sigma)))

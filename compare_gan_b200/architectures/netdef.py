@@ -71,13 +71,14 @@ class Flow(object):
     self.x = self.net.batch_norm(self.x, name=name, **self._norm_kw)
     return self
 
-  def norm_relu(self, name):
-    self.x = ops.norm_relu(self.net.batch_norm, self.x, name=name, **self._norm_kw)
+  def norm_relu(self, name, tf32=False):
+    """`tf32`: the next layer is a (transposed) convolution, see arch_ops.norm_relu."""
+    self.x = ops.norm_relu(self.net.batch_norm, self.x, name=name, _tf32=tf32, **self._norm_kw)
     return self
 
   # -- pointwise / shape --
-  def relu(self):
-    self.x = K.relu(self.x)
+  def relu(self, tf32=False):
+    self.x = K.relu(self.x, round_tf32=tf32)
     return self
 
   def lrelu(self, **kw):
@@ -97,20 +98,30 @@ BlockPlan = collections.namedtuple("BlockPlan", "name cin cout scale generator_s
 # shortcut: "conv3x3_first" (resnet_ops.ResNetBlock), "conv1x1_last" (BigGAN), None (BigGAN block with equal widths)
 
 
-def _block_conv(x, plan, cin, cout, scale, suffix, kernel, use_sn):
+def _block_conv(x, plan, cin, cout, scale, suffix, kernel, use_sn, pool=True, **fused):
+  """One convolution of a residual block.  `pool=False` leaves the 2x2 average pool of a down-sampling convolution to the
+  caller (who applies it once to the sum of both branches); `fused` are arch_ops.conv2d's epilogue arguments."""
   if x.shape[-1] != cin:
     raise ValueError("Unexpected number of input channels.")
   if scale not in SCALES:
     raise ValueError("Scale: got {}, expected 'up', 'down', or 'none'.".format(scale))
   prefix = "same" if scale == "none" else scale
   y = ops.conv2d(x, output_dim=cout, k_h=kernel, k_w=kernel, d_h=1, d_w=1, use_sn=use_sn,
-                 name="{}_{}".format(prefix, suffix), _upsample=(scale == "up"))
-  return K.avgpool2(y) if scale == "down" else y
+                 name="{}_{}".format(prefix, suffix), _upsample=(scale == "up"), **fused)
+  return K.avgpool2(y) if (scale == "down" and pool) else y
 
 
 def residual_block(inputs, plan, batch_norm, z, y, is_training, use_sn):
   """norm-relu-conv, norm-relu-conv plus the plan's shortcut.  A generator block resamples in its FIRST convolution, a
-  discriminator block in its SECOND (reference resnet_ops.py:93-102)."""
+  discriminator block in its SECOND (reference resnet_ops.py:93-102).
+
+  What the reference runs as separate TF ops is folded into the convolutions' epilogues where that is exact:
+  * the residual add is done by the LAST convolution evaluated (conv2 for the 3x3-shortcut family, the 1x1 shortcut for
+    BigGAN's) — `_residual`;
+  * a down-sampling block pools ONCE: avgpool(a) + avgpool(b) == avgpool(a + b), so both branches stay at full
+    resolution until their sum;
+  * without a normaliser between the two convolutions (every discriminator here) the second ReLU is conv1's epilogue;
+  * every tensor whose only consumer is a tensor-core convolution is stored TF32-rounded (`_tf32`)."""
   if inputs.shape[-1] != plan.cin:
     if plan.shortcut == "conv3x3_first":
       raise ValueError("Unexpected number of input channels.")
@@ -118,17 +129,29 @@ def residual_block(inputs, plan, batch_norm, z, y, is_training, use_sn):
   first = plan.scale if plan.generator_side else "none"
   second = "none" if plan.generator_side else plan.scale
   norm_kw = dict(z=z, y=y, is_training=is_training)
+  plain = ops.configured_norm(batch_norm) is None          # no normaliser: bn1 / bn2 are the identity
   with V.variable_scope(plan.name):
     skip = None
     if plan.shortcut == "conv3x3_first":
-      skip = _block_conv(inputs, plan, plan.cin, plan.cout, plan.scale, "conv_shortcut", 3, use_sn)
-    h = ops.norm_relu(batch_norm, inputs, name="bn1", **norm_kw)
-    h = _block_conv(h, plan, plan.cin, plan.cout, first, "conv1", 3, use_sn)
-    h = ops.norm_relu(batch_norm, h, name="bn2", **norm_kw)
+      skip = _block_conv(inputs, plan, plan.cin, plan.cout, plan.scale, "conv_shortcut", 3, use_sn, pool=False)
+    # (a block fed by the 3-channel image runs its first convolutions in the exact-fp32 streaming kernels: no rounding)
+    h = ops.norm_relu(batch_norm, inputs, name="bn1", _tf32=plan.cin > 4, **norm_kw)
+    if plain and first != "down":
+      h = _block_conv(h, plan, plan.cin, plan.cout, first, "conv1", 3, use_sn, _relu=True, _tf32=True)
+    else:
+      h = _block_conv(h, plan, plan.cin, plan.cout, first, "conv1", 3, use_sn)
+      h = ops.norm_relu(batch_norm, h, name="bn2", _tf32=True, **norm_kw)
+    if plan.shortcut == "conv3x3_first":
+      h = _block_conv(h, plan, plan.cout, plan.cout, second, "conv2", 3, use_sn, pool=False, _residual=skip)
+      return ops.observe(K.avgpool2(h) if plan.scale == "down" else h)
+    if plan.shortcut == "conv1x1_last" and plan.scale != "up":
+      h = _block_conv(h, plan, plan.cout, plan.cout, second, "conv2", 3, use_sn, pool=False)
+      h = _block_conv(inputs, plan, plan.cin, plan.cout, plan.scale, "conv_shortcut", 1, use_sn, pool=False, _residual=h)
+      return ops.observe(K.avgpool2(h) if plan.scale == "down" else h)
     h = _block_conv(h, plan, plan.cout, plan.cout, second, "conv2", 3, use_sn)
-    if plan.shortcut == "conv1x1_last":
+    if plan.shortcut == "conv1x1_last":                      # 1x1 over a zero-inserted input: bias-only phases, plain add
       skip = _block_conv(inputs, plan, plan.cin, plan.cout, plan.scale, "conv_shortcut", 1, use_sn)
-    return h if skip is None else K.add(h, skip)
+    return ops.observe(h if skip is None else K.add(h, skip))
 
 
 def split_latent(z, y, num_blocks, hierarchical):

@@ -77,7 +77,7 @@ class Generator(_AttentionMixin, abstract_arch.AbstractGenerator):
       name = "B%d" % (i + 1)
       block = self._resnet_block(name, a, b, "up")
       flow.x = self._after_block(name, block(flow.x, z=z_blocks[i], y=y_blocks[i], is_training=is_training))
-    flow.through(ops.batch_norm, is_training=is_training, name="final_norm").relu()
+    flow.through(ops.batch_norm, is_training=is_training, name="final_norm", _relu=True, _tf32=True)
     flow.conv(self._image_shape[2], 3, 1, "final_conv", use_sn=self._spectral_norm)
     return K.tanh01(flow.x)
 

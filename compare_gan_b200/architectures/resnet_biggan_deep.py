@@ -72,7 +72,8 @@ class BigGanDeepResNetBlock(object):
       for scope, kernel, width, resample in BOTTLENECK:
         active = resample == self._scale
         with V.variable_scope(scope):
-          h = ops.norm_relu(self.batch_norm, h, z=z, y=y, is_training=is_training, name="bn")
+          h = ops.norm_relu(self.batch_norm, h, z=z, y=y, is_training=is_training, name="bn",
+                            _tf32=not (active and resample == "down"))
           if active and resample == "down":
             h = K.avgpool2(h)                                 # pooling precedes the closing 1x1 convolution
           h = ops.conv2d(h, widths[width], kernel, kernel, 1, 1, name="%dx%d_conv" % (kernel, kernel),
@@ -119,7 +120,7 @@ class Generator(abstract_arch.AbstractGenerator):
       flow.x = self._resnet_block("B%d" % (i + 1), cin, cout, scale)(flow.x, z=z, y=y, is_training=is_training)
       if scale == "up" and flow.x.shape[1] == ATTENTION_RESOLUTION:
         flow.through(ops.non_local_block, "non_local_block", use_sn=self._spectral_norm)
-    flow.through(ops.batch_norm, is_training=is_training, name="final_norm").relu()
+    flow.through(ops.batch_norm, is_training=is_training, name="final_norm", _relu=True, _tf32=True)
     flow.conv(self._image_shape[2], 3, 1, "final_conv", use_sn=self._spectral_norm)
     return K.tanh01(flow.x)
 

@@ -38,7 +38,7 @@ class PlainResNetGenerator(resnet_ops.ResNetGenerator):
     for i, scale in enumerate(plan.scales):
       block = self._resnet_block("B%d" % (i + 1), plan.widths[i], plan.widths[i + 1], scale)
       flow.x = block(flow.x, z=z_blocks[i], y=y_blocks[i], is_training=is_training)
-    flow.norm("final_norm").relu().conv(self._image_shape[2], 3, 1, "final_conv", use_sn=sn)
+    flow.norm_relu("final_norm", tf32=True).conv(self._image_shape[2], 3, 1, "final_conv", use_sn=sn)
     return K.sigmoid(flow.x)
 
 

@@ -21,10 +21,10 @@ class Generator(abstract_arch.AbstractGenerator):
     pyramid = netdef.halvings(height, width, len(G_STAGES))       # [full, 1/2, 1/4, 1/8]
     seed_h, seed_w = pyramid[-1]
     flow = netdef.Flow(self, z, z=z, y=y, is_training=is_training)
-    flow.linear(seed_h * seed_w * 512, "g_fc1").norm("g_bn1").relu().reshape(z.shape[0], seed_h, seed_w, 512)
+    flow.linear(seed_h * seed_w * 512, "g_fc1").norm_relu("g_bn1", tf32=True).reshape(z.shape[0], seed_h, seed_w, 512)
     for i, (channels, kernel, stride) in enumerate(G_STAGES):
       flow.deconv(pyramid[len(G_STAGES) - 1 - i], channels, kernel, stride, "g_dc%d" % (i + 2))
-      flow.norm("g_bn%d" % (i + 2)).relu()
+      flow.norm_relu("g_bn%d" % (i + 2), tf32=True)
     flow.deconv(pyramid[0], colors, 3, 1, "g_dc5")
     return K.tanh01(flow.x)
 
@@ -36,7 +36,7 @@ class Discriminator(abstract_arch.AbstractDiscriminator):
     sn = self._spectral_norm
     flow = netdef.Flow(self, K.affine(x, 2.0, -1.0))               # [0, 1] -> [-1, 1]
     for i, (channels, kernel, stride) in enumerate(D_STAGES):
-      flow.conv(channels, kernel, stride, "d_conv%d" % (i + 1), use_sn=sn).lrelu(leak=0.1)
+      flow.conv(channels, kernel, stride, "d_conv%d" % (i + 1), use_sn=sn).lrelu(leak=0.1, _tf32=i + 1 < len(D_STAGES))
     features = flow.reshape(x.shape[0], -1).x
     logit = flow.linear(1, "d_fc1", use_sn=sn).x
     return K.sigmoid(logit), logit, features

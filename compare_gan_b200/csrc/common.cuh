@@ -15,7 +15,8 @@ struct cgan_ctx {
   int math_mode;
   int64_t launches;
   int num_sms;
-  int tc_mt_max;       // tcgen05 kernels: max tiles per CTA sharing one operand tile (tuning knob, env CGAN_TC_MT, default 2)
+  int tc_mt_max;       // tcgen05 kernels: max tiles per CTA sharing one operand tile (CGAN_OPT_TC_MT / env CGAN_TC_MT, default 2)
+  int last_path;       // CGAN_PATH_* of the most recent contraction (cgan_ctx_get_option(CGAN_OPT_LAST_PATH))
   char err[512];
 };
 
@@ -90,10 +91,22 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return r;
 }
 
+// Optional arguments of the tcgen05 convolution launcher cgan_conv_tc (all zero = the plain convolution)
+struct TcExtra {
+  const float* wprep;       // weights already prepared by cgan_tc_prep_weights (shared by several launches)
+  int a_prerounded;         // the activation operand already holds TF32-representable values: skip the in-smem rounding
+  int round_out;            // store TF32-rounded outputs
+  const float* residual;    // + residual (output geometry), before the activation
+  const float* mask;        // (leaky-)ReLU backward fused into the epilogue: out = mask > 0 ? v : mask_leak * v
+  float mask_leak;
+};
+
 // internal (C++ linkage) entry points shared between translation units
 int cgan_conv2d_fwd_simt(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const float* bias, float* y,
                          int relu, int ldy);
 int cgan_conv2d_dgrad_simt(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, float* dx);
+int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld, const float* residual, const float* mask,
+                            float mask_leak, int relu, int round_out);
 int cgan_upsample1x1_bias_phases(cgan_ctx* ctx, float* out, const float* bias, int n, int oh, int ow, int c);
 int cgan_gemm_batched_simt(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, int lda,
                            int64_t sa, const float* b, int ldb, int64_t sb, float beta, float* c, int ldc, int64_t sc, int batch);

@@ -8,16 +8,38 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
-                 const int* view_phase_of = nullptr, int wimg_stride = 0);
+                 const int* view_phase_of = nullptr, int wimg_stride = 0, const TcExtra* ex = nullptr);
+int cgan_tc_prep_weights(cgan_ctx* ctx, const float* wsrc, int taps_total, int transpose_w, int ncols, int kdim, float** out);
+int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld, const float* residual, const float* mask,
+                            float mask_leak, int relu, int round_out);
 bool cgan_fwd_thin_ok(const cgan_conv_desc* d);
 int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int relu,
                   int ldy);
 int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
-int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
+int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw, int x_tf32, int dy_tf32);
 int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 bool cgan_wgrad_thin_ok(const cgan_conv_desc* d);
 int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
+
+namespace {
+
+inline TcExtra tc_extra(const cgan_conv_epilogue* ep, bool tf32_in) {
+  TcExtra ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.a_prerounded = tf32_in ? 1 : 0;
+  if (ep) {
+    ex.round_out = (ep->flags & CGAN_CONV_ROUND_OUT) ? 1 : 0;
+    ex.residual = ep->residual; ex.mask = ep->mask; ex.mask_leak = ep->mask_leak;
+  }
+  return ex;
+}
+inline bool ep_has_post(const cgan_conv_epilogue* ep) {
+  return ep && (ep->residual || ep->mask || (ep->flags & (CGAN_CONV_RELU | CGAN_CONV_ROUND_OUT)));
+}
+inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
 
 int cgan_conv2d_fwd(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y) {
   return cgan_conv2d_fwd_act(ctx, d, x, w, bias, 0, y);
@@ -33,34 +55,58 @@ int cgan_conv2d_fwd_act(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, 
 int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, int act,
                            float* y, int ldy) {
   if (!ctx) return CGAN_ERR_ARG;
-  CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
   CGAN_REQUIRE(ctx, act == 0 || act == CGAN_ACT_RELU, "act must be 0 or CGAN_ACT_RELU");
+  cgan_conv_epilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias;
+  ep.flags = act == CGAN_ACT_RELU ? CGAN_CONV_RELU : 0;
+  ep.ldy = ldy;
+  return cgan_conv2d_fwd_ex(ctx, d, x, w, &ep, y);
+}
+
+int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const cgan_conv_epilogue* ep,
+                       float* y) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, d && x && w && y, "null pointer");
+  const float* bias = ep ? ep->bias : nullptr;
+  const int ldy = (ep && ep->ldy) ? ep->ldy : d->cout;
+  const int relu = (ep && (ep->flags & CGAN_CONV_RELU)) ? 1 : 0;
+  const bool x_tf32 = ep && (ep->flags & CGAN_CONV_IN_TF32);
   CGAN_REQUIRE(ctx, ldy >= d->cout, "ldy must be >= cout");
   CGAN_REQUIRE(ctx, ldy == d->cout || !d->upsample, "strided output is not available with upsample");
-  const int relu = act == CGAN_ACT_RELU;
   const bool ld_ok = ldy == d->cout || ldy % 4 == 0;      // the tcgen05 epilogue stores float4
+  const bool ptr_ok = al16p(x) && al16p(y) && (!bias || al16p(bias)) && (!ep || ((!ep->residual || al16p(ep->residual)) &&
+                                                                                  (!ep->mask || al16p(ep->mask))));
+  TcExtra ex = tc_extra(ep, x_tf32);
   // a 1x1 kernel over a zero-inserted input (BigGAN's up-sampling shortcut): phase (0,0) is a plain 1x1 conv written to the
   // even pixels, the other three phases are bias only
   if (ctx->math_mode == 1 && d->stride == 1 && d->upsample && d->kh == 1 && d->kw == 1 && d->oh == 2 * d->h &&
       d->ow == 2 * d->w && d->pad_t == 0 && d->pad_l == 0 && d->cout % 4 == 0 &&
-      cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) {
+      cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) && ptr_ok) {
     const long long zero = 0;
     const int o0 = 0, t0 = 0;
+    TcExtra ex0;
+    memset(&ex0, 0, sizeof(ex0));
+    ex0.a_prerounded = ex.a_prerounded;
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
                           d->w, d->h, d->w, d->cin, w, 1, 1, d->cout, 1, &o0, &o0, &t0, nullptr, bias, y,
-                          (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, 0, relu);
+                          (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, 0, 0, nullptr, 0, &ex0);
     if (rc) return rc;
-    if (relu && bias) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: fused relu on bias-only phases%s", "cgan_conv2d_fwd");
-    return cgan_upsample1x1_bias_phases(ctx, y, bias, d->n, d->oh, d->ow, d->cout);
+    rc = cgan_upsample1x1_bias_phases(ctx, y, bias, d->n, d->oh, d->ow, d->cout);
+    if (rc) return rc;
+    if (ep_has_post(ep))
+      return cgan_conv_post_epilogue(ctx, y, (int64_t)d->n * d->oh * d->ow, d->cout, d->cout, ep->residual, ep->mask,
+                                     ep->mask_leak, relu, ex.round_out);
+    return CGAN_OK;
   }
   if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && !(d->upsample && (d->kh < 2 || d->kw < 2)) &&
       (!d->upsample || (d->oh == 2 * d->h && d->ow == 2 * d->w)) && d->oh <= (d->upsample ? 2 * d->h : d->h) &&
-      d->ow <= (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) &&
-      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && !(d->upsample && d->cout % 4 != 0) && ld_ok) {
+      d->ow <= (d->upsample ? 2 * d->w : d->w) && cgan_tc_shape_ok(d->n, d->h, d->w, d->cin, d->cout) && ptr_ok &&
+      !(d->upsample && d->cout % 4 != 0) && ld_ok) {
     int oh[32], ow[32], wt[32];
     const long long zero = 0;
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     if (!d->upsample) {
       int nt = 0;
       for (int kh = 0; kh < d->kh; ++kh)
@@ -69,10 +115,15 @@ int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
         }
       return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n, d->h,
                           d->w, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                          (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu);
+                          (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu, nullptr, 0, &ex);
     }
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
     // pixel (2i+a, 2j+b) only sees the taps whose virtual input coordinate 2i+a+kh-pad is even -> real pixel i+dh.
+    // The weights are prepared once for the four launches.
+    float* wprep = nullptr;
+    int rc = cgan_tc_prep_weights(ctx, w, d->kh * d->kw, 1, d->cout, d->cin, &wprep);
+    if (rc) return rc;
+    ex.wprep = wprep;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         int nt = 0;
@@ -88,9 +139,10 @@ int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
         }
         long long base = ((long long)a * d->ow + b) * d->cout;
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
-        int rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
-                              d->h, d->w, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                              (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base, relu);
+        rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
+                          d->h, d->w, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
+                          (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base, relu, nullptr, 0,
+                          &ex);
         if (rc) return rc;
       }
     return CGAN_OK;
@@ -100,8 +152,7 @@ int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
   // Any size / SAME or VALID: phase a holds the rows 2r+a < H, i.e. (H-a+1)/2 of them (Inception's 35->17, 17->8).
   if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 32 && d->h >= 2 && d->w >= 2 &&
       (d->oh - 1) * 2 + d->kh - d->pad_t <= d->h + d->kh && cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cin, d->cout) &&
-      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-      (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) && ld_ok) {
+      ptr_ok && ld_ok) {
     int oh[32], ow[32], wt[32], am[32], nt = 0;
     const int hw[2] = {d->h, d->w};
     long long voff[4];
@@ -114,25 +165,49 @@ int cgan_conv2d_fwd_act_ld(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
         oh[nt] = (th - a) / 2; ow[nt] = (tw - b) / 2; wt[nt] = kh * d->kw + kw; am[nt] = a * 2 + b; ++nt;
       }
     }
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     return cgan_conv_tc(ctx, x, 4, voff, 2ll * d->cin, 2ll * d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
                         (d->h + 1) / 2, (d->w + 1) / 2, d->oh, d->ow, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, am,
-                        bias, y, (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu, hw);
+                        bias, y, (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu, hw, 0, &ex);
   }
-  if (cgan_fwd_thin_ok(d)) return cgan_fwd_thin(ctx, d, x, w, bias, y, relu, ldy);
-  return cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, relu, ldy);
+  // exact-fp32 paths: residual / mask / rounding are applied by one extra pointwise pass
+  const bool post = ep && (ep->residual || ep->mask || (ep->flags & CGAN_CONV_ROUND_OUT));
+  int rc;
+  if (cgan_fwd_thin_ok(d)) {
+    ctx->last_path = CGAN_PATH_THIN_FP32;
+    rc = cgan_fwd_thin(ctx, d, x, w, bias, y, post ? 0 : relu, ldy);
+  } else {
+    ctx->last_path = CGAN_PATH_SIMT_FP32;
+    rc = cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, post ? 0 : relu, ldy);
+  }
+  if (rc || !post) return rc;
+  return cgan_conv_post_epilogue(ctx, y, (int64_t)d->n * d->oh * d->ow, d->cout, ldy, ep->residual, ep->mask, ep->mask_leak,
+                                 relu, (ep->flags & CGAN_CONV_ROUND_OUT) ? 1 : 0);
 }
 
 int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, float* dx) {
+  return cgan_conv2d_dgrad_ex(ctx, d, dy, w, nullptr, dx);
+}
+
+int cgan_conv2d_dgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, const float* w, const cgan_conv_epilogue* ep,
+                         float* dx) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && dy && w && dx, "null pointer");
+  CGAN_REQUIRE(ctx, !ep || (!ep->ldy || ep->ldy == d->cin), "dgrad output is dense");
+  const float* bias = ep ? ep->bias : nullptr;          // tf.nn.conv2d_transpose + bias (arch_ops.py:588-592)
+  const int relu = (ep && (ep->flags & CGAN_CONV_RELU)) ? 1 : 0;
+  const bool dy_tf32 = ep && (ep->flags & CGAN_CONV_IN_TF32);
+  const bool ptr_ok = al16p(dy) && al16p(dx) && (!bias || al16p(bias)) &&
+                      (!ep || ((!ep->residual || al16p(ep->residual)) && (!ep->mask || al16p(ep->mask))));
+  TcExtra ex = tc_extra(ep, dy_tf32);
   const bool geom = d->oh == (d->upsample ? 2 * d->h : d->h) && d->ow == (d->upsample ? 2 * d->w : d->w);
   if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && geom &&
-      cgan_tc_shape_ok(d->n, d->h, d->w, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+      cgan_tc_shape_ok(d->n, d->h, d->w, d->cout, d->cin) && ptr_ok) {
     // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, oh, ow, co] * w[kh,kw,ci,co]: HWIO is already [tap][row=ci][k=co], i.e.
     // K-major for this contraction (no transpose).
     int oh[32], ow[32], wt[32], am[32], nt = 0;
     long long voff[4] = {0, 0, 0, 0};
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     if (!d->upsample) {
       // oh = ih + pad_t - kh
       for (int kh = 0; kh < d->kh; ++kh)
@@ -140,8 +215,8 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
           oh[nt] = d->pad_t - kh; ow[nt] = d->pad_l - kw; wt[nt] = kh * d->kw + kw; am[nt] = 0; ++nt;
         }
       return cgan_conv_tc(ctx, dy, 1, voff, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
-                          d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
-                          (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
+                          d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, bias, dx,
+                          (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, relu, nullptr, 0, &ex);
     }
     // zero-inserted input: the real pixel ih sits at virtual row 2*ih; tap kh reaches output row oh = 2*ih + pad_t - kh,
     // i.e. sub-pixel phase a = (pad_t - kh) & 1 of dy at phase-row ih + (pad_t - kh - a)/2.  The four phases are four
@@ -156,17 +231,21 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
       }
     }
     return cgan_conv_tc(ctx, dy, 4, voff, 2ll * d->cout, 2ll * d->ow * d->cout, (long long)d->oh * d->ow * d->cout, d->n,
-                        d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, nullptr, dx,
-                        (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, 0);
+                        d->h, d->w, d->h, d->w, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, am, bias, dx,
+                        (long long)d->h * d->w * d->cin, (long long)d->w * d->cin, d->cin, 0, relu, nullptr, 0, &ex);
   }
   // stride 2 (also tf.nn.conv2d_transpose of SNDCGAN's generator, arch_ops.py:588-589): input pixel 2i+a only receives
   // the taps with kh = a + pad_t (mod 2), from output row i + (a + pad_t - kh)/2 -> four launches, one per input phase,
-  // each writing a strided quarter of dx.
+  // each writing a strided quarter of dx; the weights are prepared once.
   if (ctx->math_mode == 1 && d->stride == 2 && !d->upsample && d->kh * d->kw <= 16 && !(d->h & 1) && !(d->w & 1) &&
       d->oh == d->h / 2 && d->ow == d->w / 2 && d->kh >= 2 && d->kw >= 2 &&
-      cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && d->cin % 4 == 0) {
+      cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && ptr_ok && d->cin % 4 == 0) {
     const long long zero = 0;
+    float* wprep = nullptr;
+    int rc = cgan_tc_prep_weights(ctx, w, d->kh * d->kw, 0, d->cin, d->cout, &wprep);
+    if (rc) return rc;
+    ex.wprep = wprep;
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
         int oh[16], ow[16], wt[16], nt = 0;
@@ -180,26 +259,46 @@ int cgan_conv2d_dgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy, c
           }
         }
         if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty phase%s", "cgan_conv2d_dgrad");
-        int rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
-                              d->n, d->oh, d->ow, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr,
-                              nullptr,
-                              dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
-                              ((long long)a * d->w + b) * d->cin, 0);
+        rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
+                          d->n, d->oh, d->ow, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr,
+                          bias,
+                          dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
+                          ((long long)a * d->w + b) * d->cin, relu, nullptr, 0, &ex);
         if (rc) return rc;
       }
     return CGAN_OK;
   }
-  return cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);
+  ctx->last_path = CGAN_PATH_SIMT_FP32;
+  int rc = cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);
+  if (rc) return rc;
+  if (bias || ep_has_post(ep)) {
+    if (bias) {
+      rc = cgan_bias_add(ctx, dx, dx, bias, (int64_t)d->n * d->h * d->w, d->cin);
+      if (rc) return rc;
+    }
+    if (ep_has_post(ep))
+      return cgan_conv_post_epilogue(ctx, dx, (int64_t)d->n * d->h * d->w, d->cin, d->cin, ep->residual, ep->mask,
+                                     ep->mask_leak, relu, (ep->flags & CGAN_CONV_ROUND_OUT) ? 1 : 0);
+  }
+  return CGAN_OK;
 }
 
 int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
+  return cgan_conv2d_wgrad_ex(ctx, d, x, dy, 0, dw);
+}
+
+int cgan_conv2d_wgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, int flags, float* dw) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && dy && dw, "null pointer");
-  if (d->n > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0 && cgan_wgrad_thin_ok(d))
+  if (d->n > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0 && cgan_wgrad_thin_ok(d)) {
+    ctx->last_path = CGAN_PATH_THIN_FP32;
     return cgan_wgrad_thin(ctx, d, x, dy, dw);      // exact fp32 streaming kernels for 3-channel image-side layers
-  if (ctx->math_mode == 1 && cgan_wgrad_tc_ok(d) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0)
-    return cgan_wgrad_tc(ctx, d, x, dy, dw);
+  }
+  if (ctx->math_mode == 1 && cgan_wgrad_tc_ok(d) && al16p(x) && al16p(dy) && al16p(dw)) {
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+    return cgan_wgrad_tc(ctx, d, x, dy, dw, (flags & CGAN_CONV_IN_TF32) ? 1 : 0, (flags & CGAN_CONV_IN2_TF32) ? 1 : 0);
+  }
+  ctx->last_path = CGAN_PATH_SIMT_FP32;
   return cgan_conv2d_wgrad_simt(ctx, d, x, dy, dw);
 }
 
@@ -227,6 +326,7 @@ int cgan_gemm_batched(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float 
     if (nt || nn) {
       const long long zero = 0;
       const int o0 = 0;
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
       return cgan_conv_tc(ctx, a, 1, &zero, k, (long long)w * k, (long long)m * k, batch, h, w, h, w, k, b, batch, nn ? 1 : 0, n,
                           1, &o0, &o0, &o0, nullptr, nullptr, c, (long long)m * n, (long long)w * n, n, 0, 0, nullptr, 1);
     }
@@ -234,8 +334,10 @@ int cgan_gemm_batched(cgan_ctx* ctx, int ta, int tb, int m, int n, int k, float 
   if (ctx->math_mode == 1 && plain && ta && !tb && rows_as_grid(k, &h, &w) && lda == m && sa == (int64_t)k * m && ldb == n &&
       sb == (int64_t)k * n && ldc == n && sc == (int64_t)m * n && m % 32 == 0 && m >= 64 && n % 4 == 0 && n <= 256 && k % 32 == 0) {
     // C[i] = A[i]^T * B[i]: the reduction runs over the rows (pixels) -> the filter-gradient kernel, one image per CTA row
+    ctx->last_path = CGAN_PATH_TCGEN05_TF32;
     return cgan_wgrad_tc_batched(ctx, a, b, c, batch, h, w, m, n);
   }
+  ctx->last_path = CGAN_PATH_SIMT_FP32;
   return cgan_gemm_batched_simt(ctx, ta, tb, m, n, k, alpha, a, lda, sa, b, ldb, sb, beta, c, ldc, sc, batch);
 }
 

@@ -40,7 +40,12 @@ struct TcParams {
   int tiles_w, tiles_h;             // tiles per image row / column
   int rows_used;                    // bw*bh*bni <= 128 pixel rows actually filled by the TMA box
   int img_n, img_h, img_w;          // extent of the pixel grid (tiles at the border hang over; those rows are not stored)
-  int relu;                         // fused ReLU in the epilogue (inference-only callers)
+  int relu;                         // fused ReLU in the epilogue
+  int round_a;                      // 1: round the activation tiles to nearest TF32 in shared memory (operand not pre-rounded)
+  int round_out;                    // 1: store TF32-rounded outputs (the consumer is another tensor-core contraction)
+  float mask_leak;                  // with `mask`: out = ref > 0 ? v : mask_leak * v  ((leaky-)ReLU backward fused into a dgrad)
+  const float* residual;            // optional tensor of the output's geometry added before the activation (residual blocks)
+  const float* mask;                // optional tensor of the output's geometry: the (leaky-)ReLU input/output whose sign gates v
   int wimg_stride;                  // batched GEMM: weight slice = wtap + image * wimg_stride (tiles never span images)
   int bn;                           // UMMA N (multiple of 32, <= 256)
   int stages;                       // smem pipeline depth (2..4)
@@ -68,6 +73,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 
 // up to four views of the input tensor (the sub-pixel phases of a 2x-upsampled gradient); plain convs use view 0
 struct AMaps { CUtensorMap m[4]; };
+
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
@@ -153,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&ready_bar[stage], phase);
+      mbar_wait(p.round_a ? &ready_bar[stage] : &full_bar[stage], phase);   // pre-rounded operands: straight from TMA
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -174,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   } else {
     // ===== warps 2..9: round A to nearest TF32 in smem, then epilogue =====
     const int q = threadIdx.x - 64;                  // 0..255
-    {
+    if (p.round_a) {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -228,6 +234,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
           : "r"(taddr + (uint32_t)c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (!row_ok) continue;                 // (the tcgen05.ld above is warp-collective; only the stores are predicated)
+      const long long roff = orow - p.out;   // residual / mask share the output's geometry
       if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -238,7 +245,17 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
             const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
           }
+          if (p.residual) {
+            const float4 rv = *reinterpret_cast<const float4*>(p.residual + roff + c0 + j);
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
           if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (p.mask) {
+            const float4 mv = *reinterpret_cast<const float4*>(p.mask + roff + c0 + j);
+            v.x = mv.x > 0.f ? v.x : p.mask_leak * v.x; v.y = mv.y > 0.f ? v.y : p.mask_leak * v.y;
+            v.z = mv.z > 0.f ? v.z : p.mask_leak * v.z; v.w = mv.w > 0.f ? v.w : p.mask_leak * v.w;
+          }
+          if (p.round_out) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
           *reinterpret_cast<float4*>(orow + c0 + j) = v;
         }
       } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
@@ -247,7 +264,10 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
           if (nb0 + c0 + j < p.cout) {
             float v = __uint_as_float(r[j]);
             if (p.bias) v += p.bias[nb0 + c0 + j];
+            if (p.residual) v += p.residual[roff + c0 + j];
             if (p.relu) v = fmaxf(v, 0.f);
+            if (p.mask) v = p.mask[roff + c0 + j] > 0.f ? v : p.mask_leak * v;
+            if (p.round_out) v = rna_tf32(v);
             orow[c0 + j] = v;
           }
         }
@@ -326,10 +346,30 @@ bool cgan_tc_shape_ok(int n, int h, int w, int kdim, int ncols) {
   return bn != 0 && bn % 32 == 0;
 }
 
+// Weights -> TF32-rounded (nearest) K-major [taps_total][ncols_pad][kdim_pad] in the context workspace.  Split from the
+// launch so that a convolution over a zero-inserted input prepares its weights ONCE for its four sub-pixel phases.
+int cgan_tc_prep_weights(cgan_ctx* ctx, const float* wsrc, int taps_total, int transpose_w, int ncols, int kdim, float** out) {
+  const int kdim_pad = (kdim + TC_BK - 1) / TC_BK * TC_BK;
+  const int ncols_pad = (ncols + 31) / 32 * 32;
+  void* ws = nullptr;
+  size_t wbytes = (size_t)taps_total * ncols_pad * kdim_pad * sizeof(float);
+  int rc = cgan_ws(ctx, wbytes, &ws);
+  if (rc) return rc;
+  float* wt = reinterpret_cast<float*>(ws);
+  long long tot = (long long)taps_total * ncols_pad * kdim_pad;
+  long long blocks = (tot + 255) / 256, cap = (long long)ctx->num_sms * 8;
+  wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, ncols_pad, kdim,
+                                                                             kdim_pad, transpose_w);
+  CGAN_LAUNCHED(ctx);
+  *out = wt;
+  return CGAN_OK;
+}
+
 // in: fp32 NHWC activations seen through `nviews` views of logical size [n, h, w, kdim] (view v starts at
 // in + view_off[v], pixel strides sw/sh/sn floats) — one view for ordinary convs, the four sub-pixel phases of a
 // 2x-upsampled gradient for the input gradient of a conv over a zero-inserted input.
-// wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim] (transpose_w=0).
+// wsrc: weights [taps_total][kdim][ncols] (transpose_w=1) or [taps_total][ncols][kdim] (transpose_w=0); ignored when
+// ex->wprep holds the output of cgan_tc_prep_weights for the same weights.
 // taps: `ntaps` entries (off_h, off_w, weight slice, view).  Output pixel (n, y, x), y < gh, x < gw, is written at
 // out + base + n*s_n + y*s_h + x*s_w (+ channel).
 int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* view_off, long long in_sw, long long in_sh,
@@ -337,7 +377,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int transpose_w,
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
-                 const int* view_phase_of, int wimg_stride) {
+                 const int* view_phase_of, int wimg_stride, const TcExtra* ex) {
   // wimg_stride != 0: batched GEMM — image i multiplies weight slice wtap + i*wimg_stride (needs one image per tile)
   // view_phase_of: {H, W} of the tensor whose four stride-2 parity phases the views are (nullptr: all views h x w)
   EncodeTiledFn enc = get_encode();
@@ -358,6 +398,10 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   p.rows_used = p.bw * p.bh * p.bni;
   p.img_n = n; p.img_h = gh; p.img_w = gw;
   p.relu = relu;
+  p.round_a = (ex && ex->a_prerounded) ? 0 : 1;
+  if (ex) {
+    p.round_out = ex->round_out; p.residual = ex->residual; p.mask = ex->mask; p.mask_leak = ex->mask_leak;
+  }
   p.wimg_stride = wimg_stride;
   if (wimg_stride != 0 && p.bni != 1)
     return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: batched GEMM needs >= 128 rows per matrix%s", "cgan_conv_tc");
@@ -368,18 +412,10 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   p.out = out;
   p.bias = bias;
 
-  // weights -> tf32-rounded K-major [taps_total][ncols][kdim] in the workspace
-  void* ws = nullptr;
-  size_t wbytes = (size_t)taps_total * ncols_pad * kdim_pad * sizeof(float);
-  int rc = cgan_ws(ctx, wbytes, &ws);
-  if (rc) return rc;
-  float* wt = reinterpret_cast<float*>(ws);
-  {
-    long long tot = (long long)taps_total * ncols_pad * kdim_pad;
-    long long blocks = (tot + 255) / 256, cap = (long long)ctx->num_sms * 8;
-    wprep_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, ctx->stream>>>(wt, wsrc, taps_total, ncols, ncols_pad, kdim,
-                                                                               kdim_pad, transpose_w);
-    CGAN_LAUNCHED(ctx);
+  float* wt = (ex && ex->wprep) ? const_cast<float*>(ex->wprep) : nullptr;
+  if (!wt) {
+    int rc = cgan_tc_prep_weights(ctx, wsrc, taps_total, transpose_w, ncols, kdim, &wt);
+    if (rc) return rc;
   }
 
   AMaps tm_as;

@@ -173,9 +173,17 @@ __global__ void bn_accu_counter_kernel(float* ac, const float* upd) {
   if (*upd == 1.0f) *ac += 1.0f;
 }
 
+__device__ __forceinline__ float rna_tf32n(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// act: bit 0 = ReLU, CGAN_ACT_ROUND_TF32 = store TF32-rounded values
 __global__ void bn_apply_kernel(float* __restrict__ y, const float* __restrict__ x, long long total, int C,
                                 long long rows_per_sample, const float* __restrict__ mean_var, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int cond, int act) {
+  const int relu = act & 1, rnd = (act & CGAN_ACT_ROUND_TF32) ? 1 : 0;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int c = (int)(i % C);
@@ -185,7 +193,31 @@ __global__ void bn_apply_kernel(float* __restrict__ y, const float* __restrict__
     float v = (x[i] - mean_var[c]) * inv;
     if (gamma) v *= gamma[pidx];
     if (beta) v += beta[pidx];
-    if (act == 1) v = fmaxf(v, 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    y[i] = rnd ? rna_tf32n(v) : v;
+  }
+}
+
+// float4 form (C % 4 == 0, fewer than 2^31 vectors, 16-byte aligned tensors): one 32-bit division per four elements, the
+// per-channel parameters come in as float4s from L1
+__global__ void bn_apply_v4_kernel(float4* __restrict__ y, const float4* __restrict__ x, unsigned total4, unsigned lanes,
+                                   unsigned rows_per_sample, const float* __restrict__ mean_var, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int cond, int act) {
+  const int relu = act & 1, rnd = (act & CGAN_ACT_ROUND_TF32) ? 1 : 0;
+  const unsigned C = lanes * 4;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const unsigned r = i / lanes, c = (i - r * lanes) * 4;
+    const float4 m = *reinterpret_cast<const float4*>(mean_var + c);
+    const float4 vv = *reinterpret_cast<const float4*>(mean_var + C + c);
+    float4 v = x[i];
+    v.x = (v.x - m.x) * (1.0f / sqrtf(vv.x + eps)); v.y = (v.y - m.y) * (1.0f / sqrtf(vv.y + eps));
+    v.z = (v.z - m.z) * (1.0f / sqrtf(vv.z + eps)); v.w = (v.w - m.w) * (1.0f / sqrtf(vv.w + eps));
+    const size_t pidx = cond ? (size_t)(r / rows_per_sample) * C + c : c;
+    if (gamma) { const float4 g = *reinterpret_cast<const float4*>(gamma + pidx); v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w; }
+    if (beta) { const float4 b = *reinterpret_cast<const float4*>(beta + pidx); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (rnd) { v.x = rna_tf32n(v.x); v.y = rna_tf32n(v.y); v.z = rna_tf32n(v.z); v.w = rna_tf32n(v.w); }
     y[i] = v;
   }
 }
@@ -208,7 +240,7 @@ __global__ void bn_bwd_sums_kernel(float* sums, const float* A, const float* Bv,
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ x,
                                     long long total, int C, long long rows_per_sample,
                                     const float* __restrict__ mean_var, float eps, const float* __restrict__ gamma,
-                                    int cond, const float* __restrict__ sums, float inv_count) {
+                                    int cond, const float* __restrict__ sums, float inv_count, int rnd) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int c = (int)(i % C);
@@ -217,7 +249,45 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dx, const float* __restr
     float xh = (x[i] - mean_var[c]) * inv;
     float g = gamma ? gamma[cond ? (r / rows_per_sample) * C + c : c] : 1.0f;
     float dxh = dy[i] * g;
-    dx[i] = inv * (dxh - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+    float v = inv * (dxh - sums[c] * inv_count - xh * sums[C + c] * inv_count);
+    dx[i] = rnd ? rna_tf32n(v) : v;
+  }
+}
+
+__global__ void bn_bwd_apply_v4_kernel(float4* __restrict__ dx, const float4* __restrict__ dy, const float4* __restrict__ x,
+                                       unsigned total4, unsigned lanes, unsigned rows_per_sample,
+                                       const float* __restrict__ mean_var, float eps, const float* __restrict__ gamma,
+                                       int cond, const float* __restrict__ sums, float inv_count, int rnd) {
+  const unsigned C = lanes * 4;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const unsigned r = i / lanes, c = (i - r * lanes) * 4;
+    const float4 m = *reinterpret_cast<const float4*>(mean_var + c);
+    const float4 vv = *reinterpret_cast<const float4*>(mean_var + C + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(sums + c);
+    const float4 s2 = *reinterpret_cast<const float4*>(sums + C + c);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gamma) g = *reinterpret_cast<const float4*>(gamma + (cond ? (size_t)(r / rows_per_sample) * C + c : c));
+    const float4 xv = x[i], gy = dy[i];
+    float4 o;
+    {
+      const float inv = 1.0f / sqrtf(vv.x + eps), xh = (xv.x - m.x) * inv;
+      o.x = inv * (gy.x * g.x - s1.x * inv_count - xh * s2.x * inv_count);
+    }
+    {
+      const float inv = 1.0f / sqrtf(vv.y + eps), xh = (xv.y - m.y) * inv;
+      o.y = inv * (gy.y * g.y - s1.y * inv_count - xh * s2.y * inv_count);
+    }
+    {
+      const float inv = 1.0f / sqrtf(vv.z + eps), xh = (xv.z - m.z) * inv;
+      o.z = inv * (gy.z * g.z - s1.z * inv_count - xh * s2.z * inv_count);
+    }
+    {
+      const float inv = 1.0f / sqrtf(vv.w + eps), xh = (xv.w - m.w) * inv;
+      o.w = inv * (gy.w * g.w - s1.w * inv_count - xh * s2.w * inv_count);
+    }
+    if (rnd) { o.x = rna_tf32n(o.x); o.y = rna_tf32n(o.y); o.z = rna_tf32n(o.z); o.w = rna_tf32n(o.w); }
+    dx[i] = o;
   }
 }
 
@@ -265,6 +335,10 @@ __global__ void sn_bwd_kernel(float* __restrict__ dw, const float* __restrict__ 
   }
 }
 
+inline bool v4_ok(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f)) & 15) == 0;
+}
 inline int ew_grid(cgan_ctx* ctx, long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)ctx->num_sms * 16;
@@ -312,9 +386,16 @@ int cgan_bn_apply(cgan_ctx* ctx, float* y, const float* x, int64_t rows, int c, 
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, y && x && mean_var2c && rows > 0 && c > 0, "bad argument");
   CGAN_REQUIRE(ctx, !cond || (rows_per_sample > 0 && rows % rows_per_sample == 0), "rows_per_sample must divide rows");
+  CGAN_REQUIRE(ctx, (act & ~(1 | CGAN_ACT_ROUND_TF32)) == 0, "act must be 0 / 1 (ReLU), optionally | CGAN_ACT_ROUND_TF32");
   long long total = (long long)rows * c;
-  bn_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(y, x, total, c, rows_per_sample > 0 ? rows_per_sample : 1,
-                                                                mean_var2c, eps, gamma, beta, cond, act);
+  const long long rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (c % 4 == 0 && total / 4 < (1ll << 31) && rps < (1ll << 31) && v4_ok(y, x, mean_var2c, gamma, beta, nullptr)) {
+    bn_apply_v4_kernel<<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), (unsigned)(total / 4), (unsigned)(c / 4), (unsigned)rps,
+        mean_var2c, eps, gamma, beta, cond, act);
+  } else {
+    bn_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(y, x, total, c, rps, mean_var2c, eps, gamma, beta, cond, act);
+  }
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }
@@ -348,12 +429,19 @@ int cgan_bn_bwd_reduce(cgan_ctx* ctx, float* sums2c, float* dgamma, float* dbeta
 
 int cgan_bn_bwd_apply(cgan_ctx* ctx, float* dx, const float* dy, const float* x, int64_t rows, int c,
                       int64_t rows_per_sample, const float* mean_var2c, float eps, const float* gamma, int cond,
-                      const float* sums2c, float inv_count) {
+                      const float* sums2c, float inv_count, int round_tf32) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, dx && dy && x && mean_var2c && sums2c && rows > 0 && c > 0, "bad argument");
   long long total = (long long)rows * c;
-  bn_bwd_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(
-      dx, dy, x, total, c, rows_per_sample > 0 ? rows_per_sample : 1, mean_var2c, eps, gamma, cond, sums2c, inv_count);
+  const long long rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  if (c % 4 == 0 && total / 4 < (1ll << 31) && rps < (1ll << 31) && v4_ok(dx, dy, x, mean_var2c, gamma, sums2c)) {
+    bn_bwd_apply_v4_kernel<<<ew_grid(ctx, total / 4), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
+        (unsigned)(total / 4), (unsigned)(c / 4), (unsigned)rps, mean_var2c, eps, gamma, cond, sums2c, inv_count, round_tf32 ? 1 : 0);
+  } else {
+    bn_bwd_apply_kernel<<<ew_grid(ctx, total), 256, 0, ctx->stream>>>(dx, dy, x, total, c, rps, mean_var2c, eps, gamma, cond,
+                                                                      sums2c, inv_count, round_tf32 ? 1 : 0);
+  }
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }

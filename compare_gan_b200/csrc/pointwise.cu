@@ -57,6 +57,29 @@ int cgan_ctx_set_math_mode(cgan_ctx* ctx, int mode) {
   return CGAN_OK;
 }
 
+int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value) {
+  if (!ctx) return CGAN_ERR_ARG;
+  switch (key) {
+    case CGAN_OPT_TC_MT:
+      CGAN_REQUIRE(ctx, value == 1 || value == 2, "CGAN_OPT_TC_MT must be 1 or 2");
+      ctx->tc_mt_max = (int)value;
+      return CGAN_OK;
+    default:
+      return cgan_fail(ctx, CGAN_ERR_ARG, "%s: unknown or read-only option%s", "cgan_ctx_set_option");
+  }
+}
+
+int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, host_value, "null pointer");
+  switch (key) {
+    case CGAN_OPT_TC_MT: *host_value = ctx->tc_mt_max; return CGAN_OK;
+    case CGAN_OPT_LAST_PATH: *host_value = ctx->last_path; return CGAN_OK;
+    default:
+      return cgan_fail(ctx, CGAN_ERR_ARG, "%s: unknown option%s", "cgan_ctx_get_option");
+  }
+}
+
 const char* cgan_last_error(cgan_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 int64_t cgan_launch_count(cgan_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
@@ -137,31 +160,91 @@ __global__ void bias_add_kernel(float* __restrict__ y, const float* __restrict__
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void act_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int kind, float leak, long long n) {
-  EW_LOOP(i, n) {
-    float v = x[i];
-    if (kind == CGAN_ACT_RELU) v = fmaxf(v, 0.f);
-    else if (kind == CGAN_ACT_LRELU) v = fmaxf(v, leak * v);
-    else if (kind == CGAN_ACT_SIGMOID) v = sigmoidf_(v);
-    else v = (tanhf(v) + 1.0f) * 0.5f;
-    y[i] = v;
+__device__ __forceinline__ float rna_tf32_(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float act_fwd_1(float v, int kind, float leak) {
+  if (kind == CGAN_ACT_RELU) return fmaxf(v, 0.f);
+  if (kind == CGAN_ACT_LRELU) return fmaxf(v, leak * v);
+  if (kind == CGAN_ACT_SIGMOID) return sigmoidf_(v);
+  return (tanhf(v) + 1.0f) * 0.5f;
+}
+__device__ __forceinline__ float act_bwd_1(float g, float r, int kind, float leak) {
+  if (kind == CGAN_ACT_RELU) return r > 0.f ? g : 0.f;
+  if (kind == CGAN_ACT_LRELU) return (r > leak * r) ? g : ((r < leak * r) ? leak * g : 0.5f * (1.0f + leak) * g);
+  if (kind == CGAN_ACT_SIGMOID) return g * r * (1.0f - r);
+  float t = 2.0f * r - 1.0f;       // y=(tanh+1)/2 -> tanh = 2y-1
+  return g * 0.5f * (1.0f - t * t);
+}
+// float4 bodies (n4 = n / 4 vectors) plus a scalar tail for the last n % 4 elements; `rnd`: store TF32-rounded values
+__global__ void act_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int kind, float leak, long long n, int rnd) {
+  const long long n4 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) ? 0 : n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  EW_LOOP(i, n4) {
+    float4 v = x4[i];
+    v.x = act_fwd_1(v.x, kind, leak); v.y = act_fwd_1(v.y, kind, leak); v.z = act_fwd_1(v.z, kind, leak); v.w = act_fwd_1(v.w, kind, leak);
+    if (rnd) { v.x = rna_tf32_(v.x); v.y = rna_tf32_(v.y); v.z = rna_tf32_(v.z); v.w = rna_tf32_(v.w); }
+    y4[i] = v;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = act_fwd_1(x[i], kind, leak);
+    y[i] = rnd ? rna_tf32_(v) : v;
   }
 }
 __global__ void act_bwd_kernel(float* __restrict__ dx, const float* __restrict__ dy, const float* __restrict__ ref,
-                               int kind, float leak, long long n) {
-  EW_LOOP(i, n) {
-    float g = dy[i], r = ref[i];
-    if (kind == CGAN_ACT_RELU) g = r > 0.f ? g : 0.f;
-    else if (kind == CGAN_ACT_LRELU) g = (r > leak * r) ? g : ((r < leak * r) ? leak * g : 0.5f * (1.0f + leak) * g);
-    else if (kind == CGAN_ACT_SIGMOID) g = g * r * (1.0f - r);
-    else { float t = 2.0f * r - 1.0f; g = g * 0.5f * (1.0f - t * t); }   // y=(tanh+1)/2 -> tanh = 2y-1
-    dx[i] = g;
+                               int kind, float leak, long long n, int rnd) {
+  const long long n4 =
+      ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(ref)) & 15) ? 0 : n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(dy);
+  const float4* r4 = reinterpret_cast<const float4*>(ref);
+  float4* o4 = reinterpret_cast<float4*>(dx);
+  EW_LOOP(i, n4) {
+    float4 g = g4[i], r = r4[i];
+    g.x = act_bwd_1(g.x, r.x, kind, leak); g.y = act_bwd_1(g.y, r.y, kind, leak);
+    g.z = act_bwd_1(g.z, r.z, kind, leak); g.w = act_bwd_1(g.w, r.w, kind, leak);
+    if (rnd) { g.x = rna_tf32_(g.x); g.y = rna_tf32_(g.y); g.z = rna_tf32_(g.z); g.w = rna_tf32_(g.w); }
+    o4[i] = g;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = act_bwd_1(dy[i], ref[i], kind, leak);
+    dx[i] = rnd ? rna_tf32_(g) : g;
   }
 }
-__global__ void add_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, long long n) {
-  EW_LOOP(i, n) y[i] = a[i] + b[i];
+// generic tail of the fused convolution entry points on the exact-fp32 paths: y = round(mask(relu(y + residual)))
+__global__ void conv_post_kernel(float* __restrict__ y, long long rows, int c, int ld, const float* __restrict__ residual,
+                                 const float* __restrict__ mask, float leak, int relu, int round_out) {
+  long long n = rows * c;
+  EW_LOOP(i, n) {
+    long long r = i / c;
+    long long o = r * ld + (i - r * c);
+    float v = y[o];
+    if (residual) v += residual[o];
+    if (relu) v = fmaxf(v, 0.f);
+    if (mask) v = mask[o] > 0.f ? v : leak * v;
+    if (round_out) v = rna_tf32_(v);
+    y[o] = v;
+  }
 }
-
+__global__ void add_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, long long n, int rnd) {
+  const long long n4 =
+      ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) ? 0 : n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  EW_LOOP(i, n4) {
+    float4 u = a4[i], v = b4[i];
+    u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
+    if (rnd) { u.x = rna_tf32_(u.x); u.y = rna_tf32_(u.y); u.z = rna_tf32_(u.z); u.w = rna_tf32_(u.w); }
+    y4[i] = u;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a[i] + b[i];
+    y[i] = rnd ? rna_tf32_(v) : v;
+  }
+}
 __global__ void avgpool2_fwd_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int h, int w, int c) {
   int oh = h / 2, ow = w / 2;
   long long tot = (long long)n * oh * ow * c;
@@ -587,21 +670,36 @@ int cgan_bias_add(cgan_ctx* ctx, float* y, const float* x, const float* bias, in
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_act_fwd(cgan_ctx* ctx, float* y, const float* x, int kind, float leak, int64_t n) {
-  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
+  NONNULL(ctx);
+  const int rnd = (kind & CGAN_ACT_ROUND_TF32) ? 1 : 0;
+  kind &= ~CGAN_ACT_ROUND_TF32;
+  CGAN_REQUIRE(ctx, y && x && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
   if (n == 0) return CGAN_OK;
-  act_fwd_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, x, kind, leak, n);
+  act_fwd_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(y, x, kind, leak, n, rnd);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_act_bwd(cgan_ctx* ctx, float* dx, const float* dy, const float* ref, int kind, float leak, int64_t n) {
-  NONNULL(ctx); CGAN_REQUIRE(ctx, dx && dy && ref && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
+  NONNULL(ctx);
+  const int rnd = (kind & CGAN_ACT_ROUND_TF32) ? 1 : 0;
+  kind &= ~CGAN_ACT_ROUND_TF32;
+  CGAN_REQUIRE(ctx, dx && dy && ref && n >= 0 && kind >= 1 && kind <= 4, "bad argument");
   if (n == 0) return CGAN_OK;
-  act_bwd_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(dx, dy, ref, kind, leak, n);
+  act_bwd_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(dx, dy, ref, kind, leak, n, rnd);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
-int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n) {
+int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld, const float* residual, const float* mask,
+                            float mask_leak, int relu, int round_out) {
+  if (rows * c == 0) return CGAN_OK;
+  conv_post_kernel<<<ew_grid(ctx, rows * c), 256, 0, ctx->stream>>>(y, rows, c, ld, residual, mask, mask_leak, relu, round_out);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n) { return cgan_add_tf32(ctx, y, a, b, n, 0); }
+int cgan_add_tf32(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n, int round_tf32) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, y && a && b && n >= 0, "bad argument");
   if (n == 0) return CGAN_OK;
-  add_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(y, a, b, n);
+  add_kernel<<<ew_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(y, a, b, n, round_tf32 ? 1 : 0);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 #define POOL_ARGS_OK(ctx) CGAN_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "need even h,w")

@@ -176,6 +176,143 @@ __global__ void fwd_thin_cin_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// ---- 3x3 kernels over <= 4 input channels, fast staging ------------------------------------------------------------
+// The two kernels above spend most of their time computing addresses in the staging loop (a pixel decode with two
+// divisions per ELEMENT).  Here a CTA walks chunks of up to THIN_PB consecutive output pixels of ONE output row, so the
+// chunk origin (image, row, first column) is decoded once per chunk and every per-element quantity (tap, channel, kh, kw)
+// comes from compile-time divisors; all index arithmetic is 32-bit.
+template <int CIN>
+struct Thin3 {
+  static constexpr int M = 9 * CIN;
+  static constexpr int M4 = (M + 3) / 4 * 4;
+};
+
+struct Thin3Params {
+  int n, h, w, cout, stride, upsample, oh, ow, pad_t, pad_l;
+  int vh, vw;                 // virtual (zero-inserted) input extent
+  int chunks_per_row;         // ceil(ow / THIN_PB)
+  int nchunks;                // n * oh * chunks_per_row
+  int chunks_per_block;
+  int ld;                     // pixel stride of the output (fwd) in floats
+};
+
+// stage the receptive fields of `nb` pixels (row `oh` of image `img`, columns ow0..) as [pixel][M4] records
+template <int CIN>
+__device__ __forceinline__ void thin3_stage(float (*xs)[Thin3<CIN>::M4], const float* __restrict__ x, const Thin3Params& p,
+                                            int img, int oh, int ow0, int nb) {
+  constexpr int M = Thin3<CIN>::M, M4 = Thin3<CIN>::M4;
+  const int row_base = img * p.h;
+  for (int e = threadIdx.x; e < nb * M4; e += blockDim.x) {
+    const int pi = e / M4, m = e - pi * M4;
+    float v = 0.f;
+    if (m < M) {
+      const int tap = m / CIN, ci = m - tap * CIN;
+      const int kh = tap / 3, kw = tap - kh * 3;
+      int vh = oh * p.stride + kh - p.pad_t, vw = (ow0 + pi) * p.stride + kw - p.pad_l;
+      bool ok = vh >= 0 && vw >= 0 && vh < p.vh && vw < p.vw;
+      if (p.upsample) {
+        ok = ok && !((vh | vw) & 1);
+        vh >>= 1; vw >>= 1;
+      }
+      if (ok) v = __ldg(x + ((size_t)(row_base + vh) * p.w + vw) * CIN + ci);
+    }
+    xs[pi][m] = v;
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(128, 8)
+fwd_thin3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                 const Thin3Params p, int relu) {
+  constexpr int M = Thin3<CIN>::M, M4 = Thin3<CIN>::M4;
+  __shared__ __align__(16) float xs[THIN_PB][M4];
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < p.cout;
+  float wr[M4];
+#pragma unroll
+  for (int m = 0; m < M4; ++m) wr[m] = (co_ok && m < M) ? w[(size_t)m * p.cout + co] : 0.f;
+  const float b = (co_ok && bias) ? bias[co] : 0.f;
+  const int c0 = blockIdx.x * p.chunks_per_block, c1 = min(p.nchunks, c0 + p.chunks_per_block);
+  for (int c = c0; c < c1; ++c) {
+    const int rowid = c / p.chunks_per_row, ow0 = (c - rowid * p.chunks_per_row) * THIN_PB;
+    const int img = rowid / p.oh, oh = rowid - img * p.oh;
+    const int nb = min(THIN_PB, p.ow - ow0);
+    __syncthreads();
+    thin3_stage<CIN>(xs, x, p, img, oh, ow0, nb);
+    __syncthreads();
+    if (co_ok) {
+      float* yrow = y + ((size_t)rowid * p.ow + ow0) * p.ld + co;
+#pragma unroll 2
+      for (int pi = 0; pi < nb; ++pi) {
+        float xv[M4];
+#pragma unroll
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
+        float acc = b;
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc = fmaf(xv[m], wr[m], acc);
+        if (relu) acc = fmaxf(acc, 0.f);
+        yrow[(size_t)pi * p.ld] = acc;
+      }
+    }
+  }
+}
+
+// dW partial per CTA: thread = output channel, acc[m] over m = (tap, ci); dY is read exactly once, in 128-byte rows
+template <int CIN>
+__global__ void __launch_bounds__(128, 6)
+wgrad_thin3_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, const Thin3Params p) {
+  constexpr int M = Thin3<CIN>::M, M4 = Thin3<CIN>::M4;
+  __shared__ __align__(16) float xs[THIN_PB][M4];
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < p.cout;
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+  const int c0 = blockIdx.x * p.chunks_per_block, c1 = min(p.nchunks, c0 + p.chunks_per_block);
+  for (int c = c0; c < c1; ++c) {
+    const int rowid = c / p.chunks_per_row, ow0 = (c - rowid * p.chunks_per_row) * THIN_PB;
+    const int img = rowid / p.oh, oh = rowid - img * p.oh;
+    const int nb = min(THIN_PB, p.ow - ow0);
+    __syncthreads();
+    thin3_stage<CIN>(xs, x, p, img, oh, ow0, nb);
+    __syncthreads();
+    if (co_ok) {
+      const float* grow = dy + ((size_t)rowid * p.ow + ow0) * p.cout + co;
+#pragma unroll 2
+      for (int pi = 0; pi < nb; ++pi) {
+        const float g = __ldg(grow + (size_t)pi * p.cout);
+        float xv[M4];
+#pragma unroll
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[m] = fmaf(xv[m], g, acc[m]);
+      }
+    }
+  }
+  if (co_ok) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) partial[((size_t)blockIdx.x * M + m) * p.cout + co] = acc[m];
+  }
+}
+
+inline bool thin3_params(const cgan_conv_desc* d, int num_sms, int ctas_per_sm, int co_blocks, Thin3Params* p) {
+  if (d->kh != 3 || d->kw != 3 || d->cin < 1 || d->cin > 4) return false;
+  p->n = d->n; p->h = d->h; p->w = d->w; p->cout = d->cout; p->stride = d->stride; p->upsample = d->upsample;
+  p->oh = d->oh; p->ow = d->ow; p->pad_t = d->pad_t; p->pad_l = d->pad_l;
+  p->vh = d->upsample ? 2 * d->h : d->h;
+  p->vw = d->upsample ? 2 * d->w : d->w;
+  p->chunks_per_row = (d->ow + THIN_PB - 1) / THIN_PB;
+  long long nchunks = (long long)d->n * d->oh * p->chunks_per_row;
+  if (nchunks >= (1ll << 30) || (long long)d->n * d->h * d->w * d->cin >= (1ll << 31)) return false;
+  p->nchunks = (int)nchunks;
+  long long want = (long long)num_sms * ctas_per_sm / (co_blocks > 0 ? co_blocks : 1);
+  if (want < 1) want = 1;
+  p->chunks_per_block = (int)((nchunks + want - 1) / want);
+  if (p->chunks_per_block < 1) p->chunks_per_block = 1;
+  p->ld = d->cout;
+  return true;
+}
+
 __global__ void thin_reduce_kernel(float* __restrict__ out, const float* __restrict__ part, long long n, int blocks) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -201,6 +338,29 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
   p.vw = d->upsample ? 2 * d->w : d->w;
   p.npix = (long long)d->n * d->oh * d->ow;
   if (p.npix >= (1ll << 31)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: more than 2^31 output pixels%s", "cgan_wgrad_thin");
+  if (d->cin <= 4 && d->kh == 3 && d->kw == 3) {
+    Thin3Params q;
+    const int co_blocks = (d->cout + 127) / 128;
+    if (thin3_params(d, ctx->num_sms, 6, co_blocks, &q)) {
+      const int blocks = (q.nchunks + q.chunks_per_block - 1) / q.chunks_per_block;
+      const long long wn = 9ll * d->cin * d->cout;
+      void* ws = nullptr;
+      int rc = cgan_ws(ctx, (size_t)blocks * wn * sizeof(float), &ws);
+      if (rc) return rc;
+      float* partial = reinterpret_cast<float*>(ws);
+      dim3 grid(blocks, co_blocks);
+      switch (d->cin) {
+        case 1: wgrad_thin3_kernel<1><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        case 2: wgrad_thin3_kernel<2><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        case 3: wgrad_thin3_kernel<3><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        default: wgrad_thin3_kernel<4><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+      }
+      CGAN_LAUNCHED(ctx);
+      thin_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, blocks);
+      CGAN_LAUNCHED(ctx);
+      return CGAN_OK;
+    }
+  }
   long long want_blocks = 4ll * ctx->num_sms;
   long long ppb = (p.npix + want_blocks - 1) / want_blocks;
   ppb = (ppb + THIN_PB - 1) / THIN_PB * THIN_PB;
@@ -243,6 +403,23 @@ int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
   p.vh = d->upsample ? 2 * d->h : d->h;
   p.vw = d->upsample ? 2 * d->w : d->w;
   p.npix = (long long)d->n * d->oh * d->ow;
+  if (d->kh == 3 && d->kw == 3) {
+    Thin3Params q;
+    const int threads3 = d->cout >= 128 ? 128 : ((d->cout + 31) / 32 * 32);
+    const int co_blocks3 = (d->cout + threads3 - 1) / threads3;
+    if (thin3_params(d, ctx->num_sms, 8 * 128 / threads3, co_blocks3, &q)) {
+      q.ld = ldy;
+      dim3 grid((q.nchunks + q.chunks_per_block - 1) / q.chunks_per_block, co_blocks3);
+      switch (d->cin) {
+        case 1: fwd_thin3_kernel<1><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu); break;
+        case 2: fwd_thin3_kernel<2><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu); break;
+        case 3: fwd_thin3_kernel<3><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu); break;
+        default: fwd_thin3_kernel<4><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu); break;
+      }
+      CGAN_LAUNCHED(ctx);
+      return CGAN_OK;
+    }
+  }
   const int threads = d->cout >= 128 ? 128 : ((d->cout + 31) / 32 * 32);
   const int co_blocks = (d->cout + threads - 1) / threads;
   long long want_blocks = 16ll * ctx->num_sms * 128 / threads / co_blocks;     // ~16 resident warps' worth of CTAs per SM, x2 waves

@@ -38,6 +38,7 @@ struct WgParams {
   int cin, cout, taps_total;
   int stages, tmem_cols;                 // pipeline depth chosen so that two CTAs share an SM; TMEM columns = pow2 >= mt*bn
   int mt;                                // (tap, ci-tile) units per CTA that share one dY tile (mt accumulators in TMEM)
+  int round_a, round_b;                  // round the X / dY tiles to nearest TF32 in shared memory (operand not pre-rounded)
   float* partial;                        // [split][taps_total][cin][cout]
 };
 
@@ -139,7 +140,7 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&ready_bar[stage], phase);
+      mbar_wait((p.round_a | p.round_b) ? &ready_bar[stage] : &full_bar[stage], phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -158,16 +159,18 @@ wgrad_tc_kernel(const __grid_constant__ BMaps tm_x, const __grid_constant__ BMap
     }
   } else {
     const int q = threadIdx.x - 64;
-    {
+    if (p.round_a | p.round_b) {
       int stage = 0;
       uint32_t phase = 0;
-      const int n4 = stage_bytes / 16;
+      // only the operand(s) that are not pre-rounded are swept: [0, a_bytes) is X, [a_bytes, stage_bytes) is dY
+      const int i0 = p.round_a ? 0 : a_bytes / 16;
+      const int n4 = (p.round_b ? stage_bytes : a_bytes) / 16;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         const uint32_t s4 = smem_u32(smem + stage * stage_bytes);
-        // stage_bytes is a multiple of 4 KB (32-pixel boxes of 128 B rows): 256 threads x 16 B per sweep
+        // the ranges are multiples of 4 KB (32-pixel boxes of 128 B rows): 256 threads x 16 B per sweep
 #pragma unroll 4
-        for (int i = q; i < n4; i += 32 * WG_RWARPS) {
+        for (int i = i0 + q; i < n4; i += 32 * WG_RWARPS) {
           float4 v = lds128(s4 + i * 16);
           v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
           sts128(s4 + i * 16, v);
@@ -261,9 +264,11 @@ bool cgan_wgrad_tc_ok(const cgan_conv_desc* d) {
   return box32(d->n, d->h, d->w, &bw, &bh, &bni);
 }
 
-int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw) {
+int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw, int x_tf32, int dy_tf32) {
   WgParams p;
   memset(&p, 0, sizeof(p));
+  p.round_a = x_tf32 ? 0 : 1;
+  p.round_b = dy_tf32 ? 0 : 1;
   const int gh = d->stride == 2 ? d->oh : d->h, gw = d->stride == 2 ? d->ow : d->w;     // pixel-loop grid
   if (!box32(d->n, gh, gw, &p.bw, &p.bh, &p.bni)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: geometry%s", "cgan_wgrad_tc");
   p.tiles_w = gw / p.bw;
@@ -389,6 +394,7 @@ int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* 
   p.cin = k1; p.cout = k2; p.taps_total = 1;
   p.ntaps = 1;
   p.mt = 1;
+  p.round_a = p.round_b = 1;
   p.partial = c;
   BMaps tm_x, tm_dy;
   memset(&tm_x, 0, sizeof(tm_x));

@@ -17,14 +17,22 @@ NAN_DETECTED = eval_utils.NAN_DETECTED
 
 
 def _update_bn_accumulators(gan, batch_size, num_accu_examples=204800, rng=None):
-  """reference eval_gan_lib.py:65-92: fill accu_mean/accu_variance by running G with update_accus=1."""
+  """reference eval_gan_lib.py:65-92: fill accu_mean/accu_variance by running G with update_accus=1 for
+  num_accu_examples // batch_size batches.  The reference loads a fresh module per evaluation, i.e. its accumulators
+  start at (0, 0, 1e-12): they are reset here so that repeated evaluations of one object do not average in the
+  statistics of older weights."""
   accus = [v for k, v in gan.store.vars.items() if k.endswith("accu/update_accus")]
   if not accus:
     return False
   rng = rng or np.random
+  for k, v in gan.store.vars.items():
+    if k.endswith("accu/accu_mean") or k.endswith("accu/accu_variance"):
+      K.fill_(v, 0.0)
+    elif k.endswith("accu/accu_counter"):
+      K.fill_(v, 1e-12)
   for v in accus:
     K.fill_(v, 1.0)
-  for _ in range(int(np.ceil(num_accu_examples / batch_size))):
+  for _ in range(num_accu_examples // batch_size):
     generate_batch(gan, batch_size, rng)
   for v in accus:
     K.fill_(v, 0.0)

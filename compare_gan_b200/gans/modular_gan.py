@@ -216,7 +216,7 @@ class ModularGAN(AbstractGAN):
         f = dict(self.inputs[i])
         f["generated"] = tape.DT(gen(i, False).t)       # tf.stop_gradient
         self.create_loss(f, f.get("labels"), for_discriminator=True)
-        grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add)
+        grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add_grad)
         scale = self._apply_grads("discriminator", self.flat_d, grads, list(d_params.keys()))
         self.d_opt.apply(scale)
         K._call("copy", self.losses.ptr + 4 * i, self.d_loss.ptr, 1)
@@ -224,7 +224,7 @@ class ModularGAN(AbstractGAN):
       f = dict(self.inputs[k])                          # _train_generator (:487-510)
       f["generated"] = gen(k, True)
       self.create_loss(f, f.get("labels"), for_discriminator=False)
-      grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add)
+      grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add_grad)
       scale = self._apply_grads("generator", self.flat_g, grads, list(g_params.keys()))
       self.g_opt.apply(scale, self.ema, self._ema_decay, self._ema_start_step)
       K._call("copy", self.losses.ptr + 4 * k, self.g_loss.ptr, 1)

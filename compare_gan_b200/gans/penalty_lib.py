@@ -24,7 +24,7 @@ def wgangp_penalty(discriminator, x, x_fake, y, is_training, alpha=None):
   with tape.record(True):
     logits = discriminator(interpolates, y=y, is_training=is_training, reuse=True)[1]
     ones = K.fill_(K.empty(*logits.shape), 1.0)
-    (gradients,) = tape.backward([(logits, ones)], [interpolates], K.add, create_graph=True)
+    (gradients,) = tape.backward([(logits, ones)], [interpolates], K.add_grad, create_graph=True)
     return K.gp_penalty(gradients)
 
 

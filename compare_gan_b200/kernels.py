@@ -1,6 +1,10 @@
 """Taped device ops: each function launches sm_100a kernels through the C-ABI (include/cgan_b200.h)
-and records its vector-Jacobian product on the tape (tape.py).  The vjps are written with the same
-ops, so second-order differentiation (WGAN-GP, gans/penalty_lib.py:59-82) works by construction.
+and records its vector-Jacobian product on the tape (tape.py).  The vjps of the ops a discriminator
+without normalisation is made of (convolutions, matmul, bias, (leaky) ReLU, pools, reshapes, adds) are
+written with the same taped ops, so second-order differentiation (WGAN-GP, gans/penalty_lib.py:59-82)
+works by construction for them.  The vjps of batch norm, softmax and spectral normalisation w.r.t. its
+weight launch raw kernels: differentiating THROUGH them (a gradient penalty on a discriminator with
+BN / attention) raises NotImplementedError instead of silently dropping the second-order terms.
 
 These are the B200 stand-ins for the TF library calls the reference's ops library makes
 (arch_ops.py / resnet_ops.py / loss_lib.py / penalty_lib.py); file:line citations sit on each op.
@@ -10,9 +14,69 @@ import ctypes
 import torch
 
 from . import _lib
-from .tape import DT, attach, no_record
+from .tape import DT, attach, no_record, recording
+from .tape import grad_accumulator as _grad_accumulator
 
-_RT = {"lib": None, "device": None}
+_RT = {"lib": None, "device": None, "math_mode": 0}
+
+# test hook: when set to a dict, every contraction records what arithmetic it performed —
+# {(kind, n, h, w, cin, cout, kh, kw, stride): (path, a_tf32, b_tf32)} with path "tcgen05_tf32" | "simt_fp32" |
+# "thin_fp32", h/w the (virtual, i.e. zero-inserted) input extent, and a_tf32 / b_tf32 whether the first / second operand
+# entered the products rounded to TF32 (rounded by the tensor-core kernel, or already stored rounded by its producer);
+# tests feed this to the oracle's TF32-operand emulation (oracle/tf_ops.py)
+CONV_TRACE = None
+# test hook: callable(kind, **operands) invoked after every contraction with its operand and result tensors (tests
+# recompute each one on the CPU, in situ, with the arithmetic CONV_TRACE reports)
+CONV_CHECK = None
+
+
+def tf32_on():
+  """True in math_mode 1: tensor-core contractions round their operands to TF32, so producers may pre-round."""
+  return _RT["math_mode"] == 1
+
+
+def _no_second_order(name):
+  """Called by the vjps that launch raw (untaped) kernels: under tape.backward(create_graph=True) their output would
+  silently lack its dependence on the incoming gradient and the stashed tensors."""
+  if recording():
+    raise NotImplementedError("second-order differentiation through %s is not implemented (its backward is not a taped op); "
+                              "WGAN-GP style penalties need a discriminator without batch norm / attention / spectral norm "
+                              "gradients in the differentiated path" % name)
+
+
+def _trace(kind, key, a_pre=False, b_pre=False, b_is_weight=True):
+  if CONV_TRACE is not None:
+    path = _lib.PATH_NAMES[_RT["lib"].get_option(_lib.OPT_LAST_PATH)]
+    tc = path == "tcgen05_tf32"
+    rec = (path, bool(tc or (a_pre and tf32_on())), bool(tc or (b_pre and tf32_on() and not b_is_weight)))
+    prev = CONV_TRACE.setdefault((kind,) + tuple(key), rec)
+    if prev != rec:
+      raise AssertionError("contraction %s %s ran as %s and as %s" % (kind, key, prev, rec))
+
+
+def _desc_key(d):
+  up = 2 if d.upsample else 1
+  return (d.n, d.h * up, d.w * up, d.cin, d.cout, d.kh, d.kw, d.stride)
+
+
+_TC_NODES = ("conv2d", "conv2d_dgrad")
+_PASS_NODES = ("avgpool2", "reshape")
+
+
+def _grad_feeds_tc(t):
+  """Will the gradient w.r.t. `t` be the dy operand of a tensor-core contraction?  (Then its producer stores it
+  TF32-rounded and the contraction skips its rounding pass; a wrong guess only costs that pass.)"""
+  if not tf32_on() or (t is not None and len(t.shape) == 4 and t.shape[-1] <= 4):
+    return False          # (3-channel image-side contractions run in the exact-fp32 streaming kernels)
+  for _ in range(4):
+    if t is None or t.node is None:
+      return False
+    if t.node.name in _TC_NODES:
+      return True
+    if t.node.name not in _PASS_NODES:
+      return False
+    t = t.node.inputs[0]
+  return False
 
 ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH01 = 1, 2, 3, 4
 LOSSES = {"non_saturating": 0, "hinge": 1, "wasserstein": 2, "least_squares": 3}
@@ -75,15 +139,25 @@ def copy_(dst, src):
 def reshape(x, *shape):
   """tf.reshape: zero-copy view, taped."""
   y = DT(x.t.view(*shape))
+  y.tf32 = x.tf32
   xs = x.shape
   return attach("reshape", y, [x], lambda g, needs: [reshape(g, *xs)])
 
 
-def add(a, b):
+def add(a, b, round_tf32=False):
   assert a.shape == b.shape, (a.shape, b.shape)
   y = empty(*a.shape)
-  _call("add", y.ptr, a.ptr, b.ptr, y.numel)
+  rnd = bool(round_tf32) and tf32_on()
+  _call("add_tf32", y.ptr, a.ptr, b.ptr, y.numel, int(rnd))
+  y.tf32 = rnd
   return attach("add", y, [a, b], lambda g, needs: [g if needs[0] else None, g if needs[1] else None])
+
+
+@_grad_accumulator
+def add_grad(prev, g, tensor):
+  """Gradient accumulation for tape.backward: the sum is stored TF32-rounded when it is about to feed tensor-core
+  gradient contractions (the tensor it belongs to was produced by a convolution)."""
+  return add(prev, g, round_tf32=_grad_feeds_tc(tensor))
 
 
 def affine(x, a, c=0.0):
@@ -116,6 +190,7 @@ def concat_rows(a, b):
 def slice_rows(x, lo, hi):
   """x[lo:hi] as a zero-copy view (tf.split on axis 0, modular_gan.py:660-661)."""
   y = DT(x.t[lo:hi])
+  y.tf32 = x.tf32
   n0 = x.shape[0]
 
   def vjp(g, needs):
@@ -173,9 +248,21 @@ def conv_desc(n, h, w, cin, cout, kh, kw, stride, upsample, padding="SAME"):
   return _lib.ConvDesc(n, h, w, cin, cout, kh, kw, stride, 1 if upsample else 0, oh, ow, pt, pl)
 
 
-def _conv_fwd_raw(d, x, w, bias):
+def _epilogue(bias=None, residual=None, mask=None, mask_leak=0.0, relu=False, round_out=False, in_tf32=False, ldy=0):
+  flags = (_lib.CONV_RELU if relu else 0) | (_lib.CONV_ROUND_OUT if round_out else 0) | (_lib.CONV_IN_TF32 if in_tf32 else 0)
+  return _lib.ConvEpilogue(None if bias is None else bias.ptr, None if residual is None else residual.ptr,
+                           None if mask is None else mask.ptr, float(mask_leak), flags, int(ldy))
+
+
+def _conv_fwd_raw(d, x, w, bias, relu=False, residual=None, round_out=False):
   y = empty(d.n, d.oh, d.ow, d.cout)
-  _call("conv2d_fwd", ctypes.byref(d), x.ptr, w.ptr, None if bias is None else bias.ptr, y.ptr)
+  rnd = bool(round_out) and tf32_on()
+  ep = _epilogue(bias, residual, relu=relu, round_out=rnd, in_tf32=x.tf32 and tf32_on())
+  _call("conv2d_fwd_ex", ctypes.byref(d), x.ptr, w.ptr, ctypes.byref(ep), y.ptr)
+  _trace("fwd", _desc_key(d), x.tf32)
+  y.tf32 = rnd
+  if CONV_CHECK is not None:
+    CONV_CHECK("fwd", d=d, x=x, w=w, bias=bias, residual=residual, relu=relu, round_out=rnd, out=y)
   return y
 
 
@@ -216,46 +303,75 @@ class ChannelSink(object):
     _call("copy2d", buf.ptr, self.channels, off, t.ptr, c, 0, n * h * w, c)
 
 
-def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME"):
+def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME", relu=False, residual=None, round_out=False):
   """tf.nn.conv2d(..., "SAME") + bias (arch_ops.py:568-572); `upsample` fuses resnet_ops.unpool
-  (resnet_ops.py:35-56, 122-123) without materialising the zeros.  w is HWIO."""
+  (resnet_ops.py:35-56, 122-123) without materialising the zeros.  w is HWIO.
+
+  Epilogue fusions (include/cgan_b200.h, cgan_conv2d_fwd_ex): `residual` (same shape as the output) is added before the
+  activation (the `h + shortcut` of resnet_ops.py:181), `relu` applies tf.nn.relu to the result (the pre-activation of
+  the NEXT convolution, resnet_ops.py:174), `round_out` stores TF32-rounded values in math_mode 1 (the output only feeds
+  tensor-core contractions)."""
   n, h, ww, cin = x.shape
   kh, kw, wcin, cout = w.shape
   if wcin != cin:
     raise ValueError("conv2d: kernel expects %d input channels, got %d" % (wcin, cin))
   d = conv_desc(n, h, ww, cin, cout, kh, kw, stride, upsample, padding)
-  y = _conv_fwd_raw(d, x, w, bias)
+  if residual is not None and residual.shape != (d.n, d.oh, d.ow, d.cout):
+    raise ValueError("conv2d: residual shape %s does not match the output %s" % (residual.shape, (d.n, d.oh, d.ow, d.cout)))
+  y = _conv_fwd_raw(d, x, w, bias, relu, residual, round_out)
+  if relu and RELU_OBSERVERS:
+    for fn in RELU_OBSERVERS:
+      fn(y.t > 0)
+  yv = DT(y.t) if relu else None        # y > 0  <=>  pre-activation > 0
 
   def vjp(g, needs):
-    return [conv2d_dgrad(d, g, w) if needs[0] else None,
+    if relu:
+      g = act_bwd(g, yv, ACT_RELU, round_tf32=True)
+    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
             conv2d_wgrad(d, x, g) if needs[1] else None,
-            colsum(reshape(g, -1, cout)) if (bias is not None and needs[2]) else None]
-  return attach("conv2d", y, [x, w, bias], vjp)
+            colsum(reshape(g, -1, cout)) if (bias is not None and needs[2]) else None,
+            g if (residual is not None and needs[3]) else None]
+  return attach("conv2d", y, [x, w, bias, residual], vjp)
 
 
-def conv2d_dgrad(d, dy, w):
-  """Input gradient of conv2d == tf.nn.conv2d_transpose (arch_ops.py:588-589)."""
+def conv2d_dgrad(d, dy, w, bias=None, round_out=False):
+  """Input gradient of conv2d == tf.nn.conv2d_transpose (+ bias, arch_ops.py:588-592)."""
   dx = empty(d.n, d.h, d.w, d.cin)
-  _call("conv2d_dgrad", ctypes.byref(d), dy.ptr, w.ptr, dx.ptr)
+  rnd = bool(round_out) and tf32_on()
+  ep = _epilogue(bias, round_out=rnd, in_tf32=dy.tf32 and tf32_on())
+  _call("conv2d_dgrad_ex", ctypes.byref(d), dy.ptr, w.ptr, ctypes.byref(ep), dx.ptr)
+  _trace("dgrad", _desc_key(d), dy.tf32)
+  dx.tf32 = rnd
+  if CONV_CHECK is not None:
+    CONV_CHECK("dgrad", d=d, dy=dy, w=w, bias=bias, round_out=rnd, out=dx)
+  cin = d.cin
 
   def vjp(g, needs):   # linear in dy and in w
-    return [_taped_fwd(d, g, w) if needs[0] else None,
-            conv2d_wgrad(d, g, dy) if needs[1] else None]
-  return attach("conv2d_dgrad", dx, [dy, w], vjp)
+    return [_taped_fwd(d, g, w, round_out=_grad_feeds_tc(dy)) if needs[0] else None,
+            conv2d_wgrad(d, g, dy) if needs[1] else None,
+            colsum(reshape(g, -1, cin)) if (bias is not None and needs[2]) else None]
+  return attach("conv2d_dgrad", dx, [dy, w, bias], vjp)
 
 
-def _taped_fwd(d, x, w):
-  y = _conv_fwd_raw(d, x, w, None)
+def _taped_fwd(d, x, w, round_out=False):
+  y = _conv_fwd_raw(d, x, w, None, round_out=round_out)
 
   def vjp(g, needs):
-    return [conv2d_dgrad(d, g, w) if needs[0] else None, conv2d_wgrad(d, x, g) if needs[1] else None]
+    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
+            conv2d_wgrad(d, x, g) if needs[1] else None]
   return attach("conv2d", y, [x, w], vjp)
 
 
 def conv2d_wgrad(d, x, dy):
   """Filter gradient (TF Conv2DBackpropFilter); deterministic split-K."""
   dw = empty(d.kh, d.kw, d.cin, d.cout)
-  _call("conv2d_wgrad", ctypes.byref(d), x.ptr, dy.ptr, dw.ptr)
+  flags = 0
+  if tf32_on():
+    flags = (_lib.CONV_IN_TF32 if x.tf32 else 0) | (_lib.CONV_IN2_TF32 if dy.tf32 else 0)
+  _call("conv2d_wgrad_ex", ctypes.byref(d), x.ptr, dy.ptr, flags, dw.ptr)
+  _trace("wgrad", _desc_key(d), x.tf32, dy.tf32, b_is_weight=False)
+  if CONV_CHECK is not None:
+    CONV_CHECK("wgrad", d=d, x=x, dy=dy, out=dw)
 
   def vjp(g, needs):
     raise NotImplementedError("third-order differentiation through conv2d_wgrad is not needed on this path")
@@ -264,7 +380,8 @@ def conv2d_wgrad(d, x, dy):
 
 def deconv2d(x, w, bias, out_hw, stride):
   """tf.nn.conv2d_transpose + bias (arch_ops.py:579-592).  w is [kh,kw,cout,cin(=x channels)]: as an HWIO conv
-  kernel it maps the deconv OUTPUT (cout channels) to x, so deconv(x) is that conv's input gradient."""
+  kernel it maps the deconv OUTPUT (cout channels) to x, so deconv(x) is that conv's input gradient; the bias is added
+  in the same kernel's epilogue."""
   n, h, ww, cin = x.shape
   kh, kw, cout, wcin = w.shape
   if wcin != cin:
@@ -273,8 +390,7 @@ def deconv2d(x, w, bias, out_hw, stride):
   d = conv_desc(n, oh, ow, cout, cin, kh, kw, stride, False)
   if (d.oh, d.ow) != (h, ww):
     raise ValueError("deconv2d: output shape %s incompatible with input %s" % ((oh, ow), (h, ww)))
-  y = conv2d_dgrad(d, x, w)
-  return bias_add(y, bias) if bias is not None else y
+  return conv2d_dgrad(d, x, w, bias)
 
 
 def matmul(a, b, ta=False, tb=False):
@@ -307,6 +423,9 @@ def bmm(a, b, ta=False, tb=False):
   c = empty(bsz, m, n)
   _call("gemm_batched", int(ta), int(tb), m, n, k, 1.0, a.ptr, a.shape[2], a.shape[1] * a.shape[2],
         b.ptr, b.shape[2], b.shape[1] * b.shape[2], 0.0, c.ptr, n, m * n, bsz)
+  _trace("bmm", (bsz, int(ta), int(tb), m, n, k))
+  if CONV_CHECK is not None:
+    CONV_CHECK("bmm", a=a, b=b, ta=ta, tb=tb, out=c)
 
   def vjp(g, needs):
     ga = gb = None
@@ -341,35 +460,41 @@ def bias_add(x, bias):
 RELU_OBSERVERS = []     # test hook: callables receiving the boolean "input > 0" mask of every (leaky-)ReLU evaluated
 
 
-def act(x, kind, leak=0.0):
+def act(x, kind, leak=0.0, round_tf32=False):
+  """Pointwise activation; `round_tf32` (math_mode 1): the result only feeds tensor-core contractions, store it
+  TF32-rounded so that they skip their operand-rounding pass."""
   if RELU_OBSERVERS and kind in (ACT_RELU, ACT_LRELU):
     for fn in RELU_OBSERVERS:
       fn(x.t > 0)
   y = empty(*x.shape)
-  _call("act_fwd", y.ptr, x.ptr, kind, float(leak), y.numel)
+  rnd = bool(round_tf32) and tf32_on()
+  _call("act_fwd", y.ptr, x.ptr, kind | (_lib.ACT_ROUND_TF32 if rnd else 0), float(leak), y.numel)
+  y.tf32 = rnd or (kind == ACT_RELU and x.tf32)
   # a closure must never hold its own output DT (that would be a DT -> node -> closure -> DT reference cycle and delay
   # freeing the stash until a cyclic GC pass): wrap the storage in a fresh, tape-less DT instead
   ref = x if kind in (ACT_RELU, ACT_LRELU) else DT(y.t)
-  return attach("act%d" % kind, y, [x], lambda g, needs: [act_bwd(g, ref, kind, leak)])
+  return attach("act%d" % kind, y, [x], lambda g, needs: [act_bwd(g, ref, kind, leak, round_tf32=_grad_feeds_tc(x))])
 
 
-def act_bwd(g, ref, kind, leak=0.0):
+def act_bwd(g, ref, kind, leak=0.0, round_tf32=False):
   dx = empty(*g.shape)
-  _call("act_bwd", dx.ptr, g.ptr, ref.ptr, kind, float(leak), dx.numel)
+  rnd = bool(round_tf32) and tf32_on()
+  _call("act_bwd", dx.ptr, g.ptr, ref.ptr, kind | (_lib.ACT_ROUND_TF32 if rnd else 0), float(leak), dx.numel)
+  dx.tf32 = rnd or (kind == ACT_RELU and g.tf32)        # a 0/1 mask keeps TF32 values TF32
 
   def vjp(gg, needs):
     if kind not in (ACT_RELU, ACT_LRELU):
       raise NotImplementedError("second derivative only needed for piecewise-linear activations")
-    return [act_bwd(gg, ref, kind, leak)]   # the mask is constant almost everywhere: no gradient to `ref`
+    return [act_bwd(gg, ref, kind, leak, round_tf32=_grad_feeds_tc(g))]   # the mask is constant almost everywhere
   return attach("act_bwd%d" % kind, dx, [g], vjp)
 
 
-def relu(x):
-  return act(x, ACT_RELU)
+def relu(x, round_tf32=False):
+  return act(x, ACT_RELU, round_tf32=round_tf32)
 
 
-def lrelu(x, leak=0.2):
-  return act(x, ACT_LRELU, leak)
+def lrelu(x, leak=0.2, round_tf32=False):
+  return act(x, ACT_LRELU, leak, round_tf32=round_tf32)
 
 
 def sigmoid(x):
@@ -393,6 +518,7 @@ def avgpool2_bwd(g, h, w):
   n, _, _, c = g.shape
   dx = empty(n, h, w, c)
   _call("avgpool2_bwd", dx.ptr, g.ptr, n, h, w, c)
+  dx.tf32 = g.tf32          # g / 4 is exact
   return attach("avgpool2_bwd", dx, [g], lambda gg, needs: [avgpool2(gg)])
 
 
@@ -423,6 +549,7 @@ def maxpool2(x):
   _call("maxpool2_fwd", y.ptr, x.ptr, n, h, w, c)
 
   def vjp(g, needs):
+    _no_second_order("maxpool2")
     dx = empty(n, h, w, c)
     _call("maxpool2_bwd", dx.ptr, g.ptr, x.ptr, n, h, w, c)
     return [dx]
@@ -494,6 +621,7 @@ def softmax(x):
   yv = DT(y.t)
 
   def vjp(g, needs):
+    _no_second_order("softmax")
     dx = empty(*shape)
     _call("softmax_bwd", dx.ptr, g.ptr, yv.ptr, rows, cols)
     return [dx]
@@ -523,6 +651,7 @@ def scale_by_param(x, s):
   _call("scale_by_dev", y.ptr, x.ptr, s.ptr, 1.0, 0, y.numel)
 
   def vjp(g, needs):
+    _no_second_order("scale_by_param")
     gx = gs = None
     if needs[0]:
       gx = empty(*x.shape)
@@ -560,7 +689,8 @@ class BNState(object):
     self.accu_mean = self.accu_var = self.accu_counter = self.update_accus = None
 
 
-def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_after=False, allreduce=None, world=1):
+def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_after=False, allreduce=None, world=1,
+             round_out=False):
   """Training-mode standardize_batch (+ gamma/beta) (arch_ops.py:194-319, 353-366, 435-444).
 
   gamma/beta: [C] DTs, or [N,C] when cond (conditional BN); either may be None.
@@ -580,8 +710,10 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
   _call("bn_finalize", mv.ptr, stats.ptr, c, None if mm is None else mm.ptr, None if mvv is None else mvv.ptr,
         float(decay))
   y = empty(*x.shape)
+  rnd = bool(round_out) and tf32_on()
   _call("bn_apply", y.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr,
-        None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
+        None if beta is None else beta.ptr, int(cond), (1 if relu_after else 0) | (_lib.ACT_ROUND_TF32 if rnd else 0))
+  y.tf32 = rnd
 
   yv = DT(y.t) if relu_after else None
   if relu_after and RELU_OBSERVERS:
@@ -589,6 +721,7 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
       fn(y.t > 0)
 
   def vjp(g, needs):
+    _no_second_order("bn_train")
     if relu_after:
       g = act_bwd(g, yv, ACT_RELU)    # y>0 <=> pre-activation>0
     sums = empty(2 * c)
@@ -607,13 +740,15 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
       dx = None
       if needs[0]:
         dx = empty(*x.shape)
+        rnd_dx = _grad_feeds_tc(x)
         _call("bn_bwd_apply", dx.ptr, g.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps),
-              None if gamma is None else gamma.ptr, int(cond), sums.ptr, 1.0 / count)
+              None if gamma is None else gamma.ptr, int(cond), sums.ptr, 1.0 / count, int(rnd_dx))
+        dx.tf32 = rnd_dx
     return [dx, dgamma, dbeta]
   return attach("bn_train", y, [x, gamma, beta], vjp)
 
 
-def bn_infer(x, gamma, beta, eps, state, use_moving_averages, cond=False, relu_after=False):
+def bn_infer(x, gamma, beta, eps, state, use_moving_averages, cond=False, relu_after=False, round_out=False):
   """Inference-mode standardize_batch: moving averages (arch_ops.py:66-119) or accumulators (:122-191)."""
   c = x.shape[-1]
   rows = x.numel // c
@@ -631,8 +766,10 @@ def bn_infer(x, gamma, beta, eps, state, use_moving_averages, cond=False, relu_a
     _call("bn_accumulate", mv.ptr, batch.ptr, c, state.accu_mean.ptr, state.accu_var.ptr, state.accu_counter.ptr,
           state.update_accus.ptr)
   y = empty(*x.shape)
+  rnd = bool(round_out) and tf32_on()
   _call("bn_apply", y.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr,
-        None if beta is None else beta.ptr, int(cond), 1 if relu_after else 0)
+        None if beta is None else beta.ptr, int(cond), (1 if relu_after else 0) | (_lib.ACT_ROUND_TF32 if rnd else 0))
+  y.tf32 = rnd
   return y
 
 
@@ -653,6 +790,7 @@ def spectral_normalize(w, u, left, eps=1e-12):
   wbar_v = DT(wbar.t)
 
   def vjp(g, needs):
+    _no_second_order("spectral_normalize")
     dw = empty(*w.shape)
     _call("spectral_norm_bwd", dw.ptr, g.ptr, wbar_v.ptr, rows, cols, int(left), u_used.ptr, v.ptr, sigma.ptr)
     return [dw]
@@ -701,3 +839,4 @@ def set_math_mode(mode):
   """0: exact fp32 SIMT contractions; 1: tcgen05 kind::tf32 tensor-core convolutions where the shape allows
   (operands rounded to nearest TF32, fp32 accumulation in TMEM)."""
   _call("ctx_set_math_mode", int(mode))
+  _RT["math_mode"] = int(mode)

@@ -187,7 +187,7 @@ class TaskManagerWithCsvResults(TaskManager):
 
 
 def _run_eval(gan, task_manager, eval_tasks=None, num_averaging_runs=1, num_samples=None, eval_every_steps=None,
-              timeout=0):
+              timeout=0, write=True):
   """Evaluates all unevaluated checkpoints (reference runner_lib.py:235-277); NaN samples score NAN_DETECTED."""
   from . import eval_gan_lib
   from .metrics import fid_score, inception_score
@@ -205,7 +205,8 @@ def _run_eval(gan, task_manager, eval_tasks=None, num_averaging_runs=1, num_samp
         raise
       result_dict = {}
       default_value = eval_gan_lib.NAN_DETECTED
-    task_manager.add_eval_result(ckpt, result_dict, default_value)
+    if write:          # (sharded evaluation: every rank takes part, rank 0 records the scores)
+      task_manager.add_eval_result(ckpt, result_dict, default_value)
     results[ckpt] = result_dict
   return results
 
@@ -228,36 +229,48 @@ def run_with_schedule(schedule, options=None, model_dir="/tmp/compare_gan_b200",
   dataset = datasets.get_dataset()
   gan = options["gan_class"](dataset=dataset, parameters=options, model_dir=model_dir)
   from .tpu import tpu_ops
-  per_replica = options["batch_size"] // tpu_ops.num_replicas()
+  world = tpu_ops.num_replicas()
+  rank = 0
+  if world > 1:
+    import torch.distributed as dist
+    rank = dist.get_rank()
+  per_replica = options["batch_size"] // world
   gan.build(per_replica)
   if use_graph:
     gan.capture()
-  rng = np.random.RandomState(seed)
+  # every replica draws its OWN shard of the global batch (z, sampled labels, alphas, synthetic images): identical streams
+  # would make the all-reduced gradient equal one replica's, i.e. an effective batch of per_replica
+  rng = np.random.RandomState(seed + rank)
+  if rank and hasattr(dataset, "_rng"):
+    dataset._rng = np.random.RandomState(getattr(dataset, "_seed", 547) + rank)
   cycles = num_cycles if num_cycles is not None else options["training_steps"] // max(1, options["disc_iters"])
   t0 = time.time()
   feeder = None
   if input_pipeline:
-    import torch.distributed as dist
-    feeder = PipelineFeeder(gan, dataset, per_replica, rank=dist.get_rank() if tpu_ops.num_replicas() > 1 else 0)
+    feeder = PipelineFeeder(gan, dataset, per_replica, rank=rank)
   for _ in range(cycles):
     if feeder is not None:
       feeder.feed(gan, dataset, per_replica, rng)
     else:
       gan.set_inputs(*sample_cycle_inputs(gan, dataset, per_replica, rng))
     gan.run_cycle()
-    if save_every_cycles and (_ + 1) % save_every_cycles == 0:
+    if rank == 0 and save_every_cycles and (_ + 1) % save_every_cycles == 0:
       gan.save_checkpoint(model_dir)
   d_losses, g_loss = gan.read_losses()
   if feeder is not None:
     feeder.close()
-  os.makedirs(model_dir, exist_ok=True)
-  with open(os.path.join(model_dir, "operative_config-0.gin"), "w") as f:     # GinConfigSaverHook, runner_lib.py:319
-    f.write(gin.operative_config_str())
-  gan.save_checkpoint(model_dir)
-  task_manager.mark_training_done()
+  if rank == 0:      # replicas hold identical weights: one writer for checkpoints, the operative config and the markers
+    os.makedirs(model_dir, exist_ok=True)
+    with open(os.path.join(model_dir, "operative_config-0.gin"), "w") as f:     # GinConfigSaverHook, runner_lib.py:319
+      f.write(gin.operative_config_str())
+    gan.save_checkpoint(model_dir)
+    task_manager.mark_training_done()
+  if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
   out = {"d_loss": d_losses, "g_loss": g_loss, "cycles": cycles, "seconds": time.time() - t0, "gan": gan}
   if schedule == "eval_after_train":
-    out["eval"] = _run_eval(gan, task_manager, **(eval_kwargs or {}))
+    out["eval"] = _run_eval(gan, task_manager, write=rank == 0, **(eval_kwargs or {}))
   return out
 
 

@@ -16,13 +16,16 @@ import torch
 
 class DT(object):
   """Device tensor: float32 (or int32 labels), C-contiguous; 4-D tensors are NHWC."""
-  __slots__ = ("t", "node", "req", "__weakref__")
+  __slots__ = ("t", "node", "req", "tf32", "__weakref__")
 
   def __init__(self, t, req=False):
     assert t.is_contiguous()
     self.t = t
     self.node = None
     self.req = req
+    # True when a kernel stored this tensor rounded to the nearest TF32 value (math_mode 1): tensor-core contractions
+    # that read it skip their operand-rounding pass (include/cgan_b200.h, CGAN_CONV_IN_TF32)
+    self.tf32 = False
 
   @property
   def shape(self):
@@ -38,7 +41,9 @@ class DT(object):
 
   def view(self, *shape):
     """Zero-copy reshape WITHOUT a tape link (use kernels.reshape inside differentiated code)."""
-    return DT(self.t.view(*shape))
+    v = DT(self.t.view(*shape))
+    v.tf32 = self.tf32
+    return v
 
   def cpu(self):
     return self.t.detach().cpu().numpy()
@@ -108,6 +113,15 @@ def _topo(roots):
   return order   # inputs before consumers
 
 
+_ADD_TAKES_TENSOR = {}
+
+
+def grad_accumulator(fn):
+  """Marks `fn(prev, g, tensor)` as an accumulation function that wants to know which tensor the gradient is for."""
+  _ADD_TAKES_TENSOR[fn] = True
+  return fn
+
+
 def backward(roots, wrt, add_fn, create_graph=False):
   """roots: list of (DT, seed) with seed a DT or None (meaning d(root)/d(root)=1 for scalar-loss ops).
   Returns the list of gradients for `wrt` (None where unreachable)."""
@@ -145,7 +159,7 @@ def backward(roots, wrt, add_fn, create_graph=False):
           continue
         if id(i) in grads:
           prev = grads[id(i)]
-          grads[id(i)] = add_fn(prev, gi)
+          grads[id(i)] = add_fn(prev, gi, i) if _ADD_TAKES_TENSOR.get(add_fn) else add_fn(prev, gi)
         else:
           grads[id(i)] = gi
       if oid not in keep:

@@ -40,6 +40,13 @@ int cgan_ctx_set_math_mode(cgan_ctx* ctx, int mode);
 const char* cgan_last_error(cgan_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t cgan_launch_count(cgan_ctx* ctx);
+/* Tuning knobs and introspection (tests compare kernel variants bit for bit and ask which path a contraction took).
+ *   CGAN_OPT_TC_MT      (set/get) max pixel tiles (conv) / work units (filter gradient) per tcgen05 CTA: 1 or 2.
+ *   CGAN_OPT_LAST_PATH  (get) CGAN_PATH_* taken by the most recent conv2d_fwd / dgrad / wgrad / gemm_batched call. */
+enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2 };
+enum { CGAN_PATH_SIMT_FP32 = 0, CGAN_PATH_TCGEN05_TF32 = 1, CGAN_PATH_THIN_FP32 = 2 };
+int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value);
+int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value);
 
 /* ---- utilities ------------------------------------------------------------------------ */
 int cgan_fill(cgan_ctx*, float* dst, float value, int64_t n);
@@ -83,6 +90,30 @@ int cgan_conv2d_fwd_act_ld(cgan_ctx*, const cgan_conv_desc*, const float* x, con
 int cgan_conv2d_dgrad(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w_hwio, float* dx);
 /* dw = d/dw (TF Conv2DBackpropFilter); deterministic split-K. */
 int cgan_conv2d_wgrad(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* dy, float* dw);
+/* Fused forms of the three convolution entry points: what the reference writes as separate TF ops around a convolution
+ * inside its residual blocks is done in the convolution's epilogue, so each activation tensor crosses HBM once:
+ *   y = act(conv(x, w) + bias + residual)                 residual add of resnet_ops.py:181 / resnet_biggan.py:150
+ *   act = ReLU when flags & CGAN_CONV_RELU                 tf.nn.relu of resnet_ops.py:161,174 (the consumer's pre-activation)
+ *   y = mask > 0 ? y : mask_leak * y                       the (leaky-)ReLU gradient (arch_ops.py:595-597) applied to an input
+ *                                                          gradient: mask is the activation's input (or output), same shape as y
+ *   CGAN_CONV_ROUND_OUT: y is stored rounded to the nearest TF32 value (its only consumers are tensor-core contractions,
+ *   which would round it anyway); CGAN_CONV_IN_TF32 / CGAN_CONV_IN2_TF32 assert that the first / second activation operand
+ *   (x or dy; for wgrad x and dy) already holds TF32-representable values, so the kernel skips its operand-rounding pass.
+ * In math_mode 0 (exact fp32) the rounding flags must not be set by the caller.  ldy: output pixel stride (0 = cout). */
+enum { CGAN_CONV_RELU = 1, CGAN_CONV_ROUND_OUT = 2, CGAN_CONV_IN_TF32 = 4, CGAN_CONV_IN2_TF32 = 8 };
+typedef struct {
+  const float* bias;        /* [cout] (fwd) / [cin] (dgrad), nullable */
+  const float* residual;    /* same shape as the output, nullable */
+  const float* mask;        /* same shape as the output, nullable */
+  float mask_leak;          /* 0 for ReLU, the leak for leaky ReLU */
+  int32_t flags;
+  int32_t ldy;
+} cgan_conv_epilogue;
+int cgan_conv2d_fwd_ex(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w_hwio, const cgan_conv_epilogue* ep,
+                       float* y);
+int cgan_conv2d_dgrad_ex(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w_hwio, const cgan_conv_epilogue* ep,
+                         float* dx);
+int cgan_conv2d_wgrad_ex(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* dy, int flags, float* dw);
 /* C = alpha*op(A)*op(B) + beta*C, row-major, op = transpose when flag set — tf.matmul in
  * linear (arch_ops.py:548), projection head (resnet_biggan.py:419-423), attention (arch_ops.py:744,753). */
 int cgan_gemm(cgan_ctx*, int trans_a, int trans_b, int m, int n, int k, float alpha, const float* a, int lda,
@@ -117,10 +148,11 @@ int cgan_bn_apply(cgan_ctx*, float* y, const float* x, int64_t rows, int c, int6
 int cgan_bn_bwd_reduce(cgan_ctx*, float* sums2c, float* dgamma, float* dbeta, const float* dy, const float* x,
                        int64_t rows, int c, int64_t rows_per_sample, const float* mean_var2c, float eps,
                        const float* gamma, int cond);
-/* Step 2: dx = inv*(dxhat - sums[0]/count - xhat*sums[1]/count), count = GLOBAL rows. */
+/* Step 2: dx = inv*(dxhat - sums[0]/count - xhat*sums[1]/count), count = GLOBAL rows; round_tf32: store dx rounded to the
+ * nearest TF32 value (it is the dy operand of the producing convolution's tensor-core gradients). */
 int cgan_bn_bwd_apply(cgan_ctx*, float* dx, const float* dy, const float* x, int64_t rows, int c, int64_t rows_per_sample,
                       const float* mean_var2c, float eps, const float* gamma, int cond, const float* sums2c,
-                      float inv_count);
+                      float inv_count, int round_tf32);
 
 /* ---- spectral norm (arch_ops.py:453-535) -------------------------------------------------- */
 /* One power iteration on w[rows,cols]; left=1: u[rows], v[cols] (arch_ops.py:505-509,525); left=0: u[cols], v[rows]
@@ -133,10 +165,15 @@ int cgan_spectral_norm_bwd(cgan_ctx*, float* dw, const float* dwbar, const float
 
 /* ---- pointwise / pooling ------------------------------------------------------------------- */
 enum { CGAN_ACT_RELU = 1, CGAN_ACT_LRELU = 2, CGAN_ACT_SIGMOID = 3, CGAN_ACT_TANH01 = 4 /* (tanh(x)+1)/2 */ };
+/* OR-ed into `kind` (act_fwd / act_bwd) or `act` (bn_apply): store the result rounded to the nearest TF32 value — the
+ * tensor only feeds tensor-core contractions, which then skip their own operand-rounding pass (math_mode 1 only). */
+enum { CGAN_ACT_ROUND_TF32 = 0x100 };
 int cgan_act_fwd(cgan_ctx*, float* y, const float* x, int kind, float leak, int64_t n);
 /* dx = dy * act'(.) ; `ref` is x for relu/lrelu and y for sigmoid/tanh01 */
 int cgan_act_bwd(cgan_ctx*, float* dx, const float* dy, const float* ref, int kind, float leak, int64_t n);
 int cgan_add(cgan_ctx*, float* y, const float* a, const float* b, int64_t n);
+/* same, optionally storing TF32-rounded sums (gradient accumulation in front of a tensor-core contraction) */
+int cgan_add_tf32(cgan_ctx*, float* y, const float* a, const float* b, int64_t n, int round_tf32);
 /* 2x2 stride-2 average pool (resnet_ops.py:131-133) and its adjoint */
 int cgan_avgpool2_fwd(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c);
 int cgan_avgpool2_bwd(cgan_ctx*, float* dx, const float* dy, int n, int h, int w, int c);

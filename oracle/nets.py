@@ -12,6 +12,18 @@ import torch
 from . import tf_ops as T
 
 
+# test hook: callables fn(scope_name, tensor) receiving the output of every linear / conv2d / deconv2d / non_local_block
+ACT_OBSERVERS = []
+
+
+def _observe(store, y):
+  if ACT_OBSERVERS:
+    name = "/".join(store._scope)
+    for fn in ACT_OBSERVERS:
+      fn(name, y)
+  return y
+
+
 class Cfg(object):
   """The gin bindings that matter on the hot path."""
 
@@ -147,7 +159,7 @@ def linear(store, cfg, x, out, scope, use_sn=False, use_bias=True, bias_start=0.
     y = x @ k
     if use_bias:
       y = y + store.get("bias", (out,), ("const", bias_start))
-    return y
+    return _observe(store, y)
 
 
 def conv2d(store, cfg, x, out, kh, kw, stride, name, use_sn=False, use_bias=True):
@@ -159,7 +171,7 @@ def conv2d(store, cfg, x, out, kh, kw, stride, name, use_sn=False, use_bias=True
     y = T.conv2d_same(x, w, stride)
     if use_bias:
       y = y + store.get("bias", (out,), ("zeros",))
-    return y
+    return _observe(store, y)
 
 
 def deconv2d(store, cfg, x, out_shape, kh, kw, stride, name, use_sn=False):
@@ -169,7 +181,7 @@ def deconv2d(store, cfg, x, out_shape, kh, kw, stride, name, use_sn=False):
     if use_sn:
       w = spectral_norm(store, cfg, w)
     y = T.conv2d_transpose_same(x, w, (out_shape[1], out_shape[2]), stride)
-    return y + store.get("bias", (out_shape[-1],), ("zeros",))
+    return _observe(store, y + store.get("bias", (out_shape[-1],), ("zeros",)))
 
 
 def standardize_batch(store, cfg, x, is_training):
@@ -258,13 +270,13 @@ def non_local_block(store, cfg, x, name, use_sn):
     theta = theta.reshape(n, h * w, ca)
     phi = conv2d(store, cfg, x, ca, 1, 1, 1, "conv2d_phi", use_sn, use_bias=False)
     phi = T.max_pool2(phi).reshape(n, h * w // 4, ca)
-    attn = torch.softmax(theta @ phi.transpose(1, 2), dim=-1)
+    attn = torch.softmax(T.bmm(theta, phi, False, True), dim=-1)
     g = conv2d(store, cfg, x, cg, 1, 1, 1, "conv2d_g", use_sn, use_bias=False)
     g = T.max_pool2(g).reshape(n, h * w // 4, cg)
-    attn_g = (attn @ g).reshape(n, h, w, cg)
+    attn_g = T.bmm(attn, g).reshape(n, h, w, cg)
     sigma = store.get("sigma", (), ("zeros",))
     attn_g = conv2d(store, cfg, attn_g, c, 1, 1, 1, "conv2d_attn_g", use_sn, use_bias=False)
-    return x + sigma * attn_g
+    return _observe(store, x + sigma * attn_g)
 
 
 # --------------------------------------------------------------------------- resnet_ops
@@ -295,7 +307,7 @@ def resnet_block(store, cfg, x, name, cin, cout, scale, is_gen, y, is_training, 
     h = apply_bn(store, cfg, bn, h, y, is_training, "bn2", use_sn)
     h = torch.relu(h)
     h = _get_conv(store, cfg, h, cout, cout, scale2, "conv2", use_sn)
-    return h + shortcut
+    return _observe(store, h + shortcut)
 
 
 def biggan_block(store, cfg, x, name, cin, cout, scale, is_gen, y, is_training, bn, use_sn,
@@ -312,7 +324,7 @@ def biggan_block(store, cfg, x, name, cin, cout, scale, is_gen, y, is_training, 
     h = _get_conv(store, cfg, h, cout, cout, scale2, "conv2", use_sn)
     if add_shortcut:
       h = h + _get_conv(store, cfg, x, cin, cout, scale, "conv_shortcut", use_sn, ksize=1)
-    return h
+    return _observe(store, h)
 
 
 # --------------------------------------------------------------------------- architectures

@@ -20,8 +20,163 @@ def _same_pads(n, k, s):
   return out, total // 2, total - total // 2
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# TF32-operand emulation (test infrastructure).  The engine's math_mode 1 evaluates every convolution-like contraction
+# that the library routes to the tensor cores as: round both operands to the nearest TF32 value (cvt.rna: 10 mantissa
+# bits, ties away from zero), multiply exactly, accumulate in fp32.  Its backward applies the same rule to each gradient
+# contraction separately (dx = dgrad(rna(dy), rna(w)), dw = wgrad(rna(x), rna(dy))).  With TF32_PLAN set to the
+# {(kind, n, h, w, cin, cout, kh, kw, stride): path} dictionary recorded by the engine (kernels.CONV_TRACE), the
+# convolutions below reproduce exactly that arithmetic, so an engine run in math_mode 1 can be compared with this oracle
+# at fp32-accumulation-order tolerance (~1e-5) instead of the ~1e-3 that separates TF32 from fp32 — and the difference
+# between this oracle with and without the plan is what the precision mode itself costs, independent of our kernels.
+TF32_PLAN = None
+
+
+def rna_tf32(t):
+  """Round to the nearest TF32-representable value, ties away from zero (PTX cvt.rna.tf32.f32)."""
+  a = t.detach().to(torch.float32).contiguous()
+  bits = a.view(torch.int32)
+  out = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+  return out.to(t.dtype)
+
+
+def _tf32_used(kind, key):
+  """(first operand rounded, second operand rounded) for this contraction, from the engine's record."""
+  if TF32_PLAN is None:
+    return False, False
+  rec = TF32_PLAN.get((kind,) + tuple(int(v) for v in key))
+  if rec is None:
+    raise KeyError("TF32 plan has no entry for %s %s (the engine never ran this contraction)" % (kind, key))
+  return bool(rec[1]), bool(rec[2])
+
+
+def _r(t, on):
+  return rna_tf32(t) if on else t
+
+
+def _conv_key(x_shape, w_shape, stride):
+  n, h, w, cin = x_shape
+  kh, kw, _, cout = w_shape
+  return (n, h, w, cin, cout, kh, kw, stride)
+
+
+def _conv_raw(x, w_hwio, stride):
+  kh, kw = w_hwio.shape[0], w_hwio.shape[1]
+  _, pt, pb = _same_pads(x.shape[1], kh, stride)
+  _, pl, pr = _same_pads(x.shape[2], kw, stride)
+  xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+  return F.conv2d(xn, w_hwio.permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+
+
+def _dgrad_raw(gy, w_hwio, x_shape, stride):
+  kh, kw = w_hwio.shape[0], w_hwio.shape[1]
+  n, h, w, cin = x_shape
+  _, pt, pb = _same_pads(h, kh, stride)
+  _, pl, pr = _same_pads(w, kw, stride)
+  gxp = torch.nn.grad.conv2d_input((n, cin, h + pt + pb, w + pl + pr), w_hwio.permute(3, 2, 0, 1),
+                                   gy.permute(0, 3, 1, 2), stride=stride)
+  return gxp[:, :, pt:pt + h, pl:pl + w].permute(0, 2, 3, 1)
+
+
+def _wgrad_raw(x, gy, w_shape, stride):
+  kh, kw, cin, cout = w_shape
+  _, pt, pb = _same_pads(x.shape[1], kh, stride)
+  _, pl, pr = _same_pads(x.shape[2], kw, stride)
+  xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+  gw = torch.nn.grad.conv2d_weight(xn, (cout, cin, kh, kw), gy.permute(0, 3, 1, 2), stride=stride)
+  return gw.permute(2, 3, 1, 0)
+
+
+class _Tf32Conv(torch.autograd.Function):
+  """y = conv(x, w) with the engine's per-contraction operand rounding; mirrors kernels.conv2d / _taped_fwd."""
+
+  @staticmethod
+  def forward(ctx, x, w, stride):
+    ctx.save_for_backward(x, w)
+    ctx.stride = stride
+    ra, rb = _tf32_used("fwd", _conv_key(x.shape, w.shape, stride))
+    return _conv_raw(_r(x, ra), _r(w, rb), stride)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, w = ctx.saved_tensors
+    gx = _Tf32Dgrad.apply(gy, w, tuple(x.shape), ctx.stride) if ctx.needs_input_grad[0] else None
+    gw = _Tf32Wgrad.apply(x, gy, tuple(w.shape), ctx.stride) if ctx.needs_input_grad[1] else None
+    return gx, gw, None
+
+
+class _Tf32Dgrad(torch.autograd.Function):
+  """dx = conv_transpose(dy, w); mirrors kernels.conv2d_dgrad (linear in dy and in w)."""
+
+  @staticmethod
+  def forward(ctx, gy, w, x_shape, stride):
+    ctx.save_for_backward(gy, w)
+    ctx.x_shape, ctx.stride = x_shape, stride
+    ra, rb = _tf32_used("dgrad", _conv_key(x_shape, w.shape, stride))
+    return _dgrad_raw(_r(gy, ra), _r(w, rb), x_shape, stride)
+
+  @staticmethod
+  def backward(ctx, ggx):
+    gy, w = ctx.saved_tensors
+    ggy = _Tf32Conv.apply(ggx, w, ctx.stride) if ctx.needs_input_grad[0] else None
+    gw = _Tf32Wgrad.apply(ggx, gy, tuple(w.shape), ctx.stride) if ctx.needs_input_grad[1] else None
+    return ggy, gw, None, None
+
+
+class _Tf32Wgrad(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, gy, w_shape, stride):
+    ra, rb = _tf32_used("wgrad", _conv_key(x.shape, w_shape, stride))
+    return _wgrad_raw(_r(x, ra), _r(gy, rb), w_shape, stride)
+
+  @staticmethod
+  def backward(ctx, g):
+    raise NotImplementedError("third-order differentiation through the filter gradient is not needed on this path")
+
+
+class _Tf32Bmm(torch.autograd.Function):
+  """op(a) @ op(b) per image with the engine's operand rounding (kernels.bmm: attention products, arch_ops.py:744,753)."""
+
+  @staticmethod
+  def forward(ctx, a, b, ta, tb):
+    ctx.save_for_backward(a, b)
+    ctx.ta, ctx.tb = ta, tb
+    return _bmm_raw(a, b, ta, tb)
+
+  @staticmethod
+  def backward(ctx, g):
+    a, b = ctx.saved_tensors
+    ta, tb = ctx.ta, ctx.tb
+    ga = gb = None
+    if ctx.needs_input_grad[0]:
+      ga = _bmm_raw(b, g, tb, True) if ta else _bmm_raw(g, b, False, not tb)
+    if ctx.needs_input_grad[1]:
+      gb = _bmm_raw(g, a, True, ta) if tb else _bmm_raw(a, g, not ta, False)
+    return ga, gb, None, None
+
+
+def _bmm_raw(a, b, ta, tb):
+  bsz = a.shape[0]
+  m = a.shape[2] if ta else a.shape[1]
+  k = a.shape[1] if ta else a.shape[2]
+  n = b.shape[1] if tb else b.shape[2]
+  ra, rb = _tf32_used("bmm", (bsz, int(ta), int(tb), m, n, k))
+  a, b = _r(a, ra), _r(b, rb)
+  return torch.bmm(a.transpose(1, 2) if ta else a, b.transpose(1, 2) if tb else b)
+
+
+def bmm(a, b, ta=False, tb=False):
+  """Batched tf.matmul (arch_ops.py:744, 753); follows the TF32 plan when one is set."""
+  if TF32_PLAN is None:
+    return torch.bmm(a.transpose(1, 2) if ta else a, b.transpose(1, 2) if tb else b)
+  return _Tf32Bmm.apply(a, b, ta, tb)
+
+
 def conv2d_same(x, w_hwio, stride=1):
   """tf.nn.conv2d(x, w, strides=[1,s,s,1], padding="SAME") — arch_ops.py:568."""
+  if TF32_PLAN is not None:
+    return _Tf32Conv.apply(x, w_hwio, stride)
   kh, kw = w_hwio.shape[0], w_hwio.shape[1]
   _, pt, pb = _same_pads(x.shape[1], kh, stride)
   _, pl, pr = _same_pads(x.shape[2], kw, stride)
@@ -36,6 +191,10 @@ def conv2d_transpose_same(x, w_hwoi, out_hw, stride):
   Adjoint of "SAME-pad then VALID conv": full transposed conv, then crop the
   SAME padding.  ``w_hwoi`` is ``[kh,kw,cout,cin]`` (cin = x channels).
   """
+  if TF32_PLAN is not None:
+    # w is the HWIO kernel of the conv that maps the OUTPUT (cout channels) back to x: deconv(x) is its input gradient
+    n = x.shape[0]
+    return _Tf32Dgrad.apply(x, w_hwoi, (n, out_hw[0], out_hw[1], w_hwoi.shape[2]), stride)
   kh, kw = w_hwoi.shape[0], w_hwoi.shape[1]
   oh, ow = out_hw
   _, pt, _ = _same_pads(oh, kh, stride)

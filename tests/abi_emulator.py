@@ -28,6 +28,12 @@ def f64(ptr, n):
   return np.ctypeslib.as_array((ctypes.c_double * int(n)).from_address(int(ptr)))
 
 
+def rna_tf32(a):
+  """cvt.rna.tf32.f32 on a float32 array: round the 13 low mantissa bits to nearest, ties away from zero."""
+  a = np.ascontiguousarray(a, np.float32)
+  return ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def _desc(ref):
   d = ref._obj            # ctypes.byref(ConvDesc)
   return d
@@ -53,15 +59,24 @@ def _conv_forward(x, w, d):
 class EmulatedLib(object):
   """Same surface as compare_gan_b200._lib.Lib: call(name, *args), launch_count(), set_stream()."""
 
+  emulated = True
+
   def __init__(self):
     self.launches = 0
     self.math_mode = 0
+    self.last_path = 0
 
   def set_stream(self, stream):
     pass
 
   def launch_count(self):
     return self.launches
+
+  def get_option(self, key):
+    return {1: 2, 2: self.last_path}[key]
+
+  def set_option(self, key, value):
+    assert key == 1 and value in (1, 2)
 
   def call(self, name, *args):
     self.launches += 1
@@ -71,6 +86,20 @@ class EmulatedLib(object):
   def cgan_ctx_set_math_mode(self, mode):
     assert mode in (0, 1)
     self.math_mode = mode
+
+  def cgan_ctx_set_option(self, key, value):
+    assert key == 1 and value in (1, 2)
+
+  def cgan_ctx_get_option(self, key, out):
+    out._obj.value = self.get_option(key)
+
+  def _tc(self, d=None):
+    """math_mode 1 is emulated as the tensor-core ARITHMETIC (operands rounded to the nearest TF32 value, fp32
+    accumulation) for every contraction with more than 4 input channels; the image-side layers stay exact like the thin
+    kernels.  Sets the path CGAN_OPT_LAST_PATH reports."""
+    tc = self.math_mode == 1 and (d is None or (d.cin > 4 and d.cout > 4))
+    self.last_path = 1 if tc else 0
+    return tc
 
   def cgan_fill(self, dst, value, n):
     f32(dst, n)[:] = np.float32(value)
@@ -121,6 +150,8 @@ class EmulatedLib(object):
   def cgan_conv2d_fwd_act_ld(self, dref, x, w, bias, act, y, ldy):
     d = _desc(dref)
     xt, wt = self._conv_tensors(d, x, w)
+    if self._tc(d):
+      xt, wt = torch.from_numpy(rna_tf32(xt.numpy())), torch.from_numpy(rna_tf32(wt.numpy()))
     out = _conv_forward(xt, wt, d).numpy()
     if bias is not None:
       out = out + f32(bias, d.cout)
@@ -134,11 +165,48 @@ class EmulatedLib(object):
       for p in range(pixels):
         f32(y + 4 * p * ldy, d.cout)[:] = out[p]
 
+  def _post(self, out_ptr, n, ep, relu_done=False):
+    """Epilogue of the *_ex convolution entry points on a dense output of n floats."""
+    o = f32(out_ptr, n)
+    if ep.residual:
+      o += f32(ep.residual, n)
+    if (ep.flags & 1) and not relu_done:
+      np.maximum(o, 0, out=o)
+    if ep.mask:
+      m = f32(ep.mask, n)
+      o[:] = np.where(m > 0, o, np.float32(ep.mask_leak) * o)
+    if ep.flags & 2:
+      o[:] = rna_tf32(o)
+
+  def cgan_conv2d_fwd_ex(self, dref, x, w, epref, y):
+    d, ep = _desc(dref), epref._obj
+    ldy = ep.ldy or d.cout
+    assert ldy == d.cout or not (ep.residual or ep.mask or (ep.flags & 2)), "strided fused outputs are not emulated"
+    plain_relu = (ep.flags & 1) and not (ep.residual or ep.mask)
+    self.cgan_conv2d_fwd_act_ld(dref, x, w, ep.bias, 1 if plain_relu else 0, y, ldy)
+    if ldy == d.cout:
+      self._post(y, d.n * d.oh * d.ow * d.cout, ep, relu_done=plain_relu)
+
+  def cgan_conv2d_dgrad_ex(self, dref, dy, w, epref, dx):
+    d = _desc(dref)
+    self.cgan_conv2d_dgrad(dref, dy, w, dx)
+    if epref is not None:
+      ep = epref._obj
+      n = d.n * d.h * d.w * d.cin
+      if ep.bias:
+        f32(dx, n).reshape(-1, d.cin)[:] += f32(ep.bias, d.cin)
+      self._post(dx, n, ep)
+
+  def cgan_conv2d_wgrad_ex(self, dref, x, dy, flags, dw):
+    self.cgan_conv2d_wgrad(dref, x, dy, dw)
+
   def cgan_conv2d_dgrad(self, dref, dy, w, dx):
     d = _desc(dref)
     x = torch.zeros(d.n, d.h, d.w, d.cin, requires_grad=True)
     wt = torch.from_numpy(f32(w, d.kh * d.kw * d.cin * d.cout).reshape(d.kh, d.kw, d.cin, d.cout).copy())
     g = torch.from_numpy(f32(dy, d.n * d.oh * d.ow * d.cout).reshape(d.n, d.oh, d.ow, d.cout).copy())
+    if self._tc(d):
+      wt, g = torch.from_numpy(rna_tf32(wt.numpy())), torch.from_numpy(rna_tf32(g.numpy()))
     _conv_forward(x, wt, d).backward(g)
     f32(dx, x.numel())[:] = x.grad.numpy().ravel()
 
@@ -147,6 +215,8 @@ class EmulatedLib(object):
     xt = torch.from_numpy(f32(x, d.n * d.h * d.w * d.cin).reshape(d.n, d.h, d.w, d.cin).copy())
     wt = torch.zeros(d.kh, d.kw, d.cin, d.cout, requires_grad=True)
     g = torch.from_numpy(f32(dy, d.n * d.oh * d.ow * d.cout).reshape(d.n, d.oh, d.ow, d.cout).copy())
+    if self._tc(d):
+      xt, g = torch.from_numpy(rna_tf32(xt.numpy())), torch.from_numpy(rna_tf32(g.numpy()))
     _conv_forward(xt, wt, d).backward(g)
     f32(dw, wt.numel())[:] = wt.grad.numpy().ravel()
 
@@ -154,6 +224,8 @@ class EmulatedLib(object):
     self.cgan_gemm_batched(ta, tb, m, n, k, alpha, a, lda, 0, b, ldb, 0, beta, c, ldc, 0, 1)
 
   def cgan_gemm_batched(self, ta, tb, m, n, k, alpha, a, lda, sa, b, ldb, sb, beta, c, ldc, sc, batch):
+    tc = self._tc() and batch > 1
+    self.last_path = 1 if tc else 0
     for i in range(batch):
       ar, ac = (k, m) if ta else (m, k)
       br, bc = (n, k) if tb else (k, n)
@@ -163,6 +235,8 @@ class EmulatedLib(object):
       B = np.lib.stride_tricks.as_strided(bm, (br, bc), (4 * ldb, 4))
       A = A.T if ta else A
       B = B.T if tb else B
+      if tc:
+        A, B = rna_tf32(A), rna_tf32(B)
       cm = f32(c + 4 * i * sc, (m - 1) * ldc + n)
       C = np.lib.stride_tricks.as_strided(cm, (m, n), (4 * ldc, 4))
       res = np.float32(alpha) * (A.astype(np.float32) @ B.astype(np.float32))
@@ -216,6 +290,7 @@ class EmulatedLib(object):
     return np.repeat(f32(ptr, samples * c).reshape(samples, c), rows_per_sample, axis=0)
 
   def cgan_bn_apply(self, y, x, rows, c, rows_per_sample, mean_var, eps, gamma, beta, cond, act):
+    rnd, act = act & 0x100, act & 0xFF
     mv = f32(mean_var, 2 * c)
     xv = f32(x, rows * c).reshape(rows, c)
     out = (xv - mv[:c]) * (np.float32(1.0) / np.sqrt(mv[c:] + np.float32(eps)))
@@ -226,7 +301,7 @@ class EmulatedLib(object):
       out = out + b
     if act == 1:
       out = np.maximum(out, 0)
-    f32(y, rows * c).reshape(rows, c)[:] = out
+    f32(y, rows * c).reshape(rows, c)[:] = rna_tf32(out) if rnd else out
 
   def cgan_bn_bwd_reduce(self, sums, dgamma, dbeta, dy, x, rows, c, rows_per_sample, mean_var, eps, gamma, cond):
     mv = f32(mean_var, 2 * c)
@@ -244,7 +319,8 @@ class EmulatedLib(object):
     if dbeta is not None:
       f32(dbeta, groups * c).reshape(groups, c)[:] = g.reshape(groups, -1, c).sum(1)
 
-  def cgan_bn_bwd_apply(self, dx, dy, x, rows, c, rows_per_sample, mean_var, eps, gamma, cond, sums, inv_count):
+  def cgan_bn_bwd_apply(self, dx, dy, x, rows, c, rows_per_sample, mean_var, eps, gamma, cond, sums, inv_count,
+                        round_tf32=0):
     mv = f32(mean_var, 2 * c)
     inv = 1.0 / np.sqrt(mv[c:].astype(np.float64) + eps)
     xhat = (f32(x, rows * c).reshape(rows, c).astype(np.float64) - mv[:c]) * inv
@@ -252,7 +328,8 @@ class EmulatedLib(object):
     gam = self._per_row(gamma, rows, c, rows_per_sample, cond)
     dxhat = g * gam if gam is not None else g
     s = f32(sums, 2 * c).astype(np.float64)
-    f32(dx, rows * c).reshape(rows, c)[:] = inv * (dxhat - s[:c] * inv_count - xhat * s[c:] * inv_count)
+    out = (inv * (dxhat - s[:c] * inv_count - xhat * s[c:] * inv_count)).astype(np.float32)
+    f32(dx, rows * c).reshape(rows, c)[:] = rna_tf32(out) if round_tf32 else out
 
   # ---- spectral norm --------------------------------------------------------------------------
   @staticmethod
@@ -291,13 +368,15 @@ class EmulatedLib(object):
 
   # ---- pointwise / pooling --------------------------------------------------------------------
   def cgan_act_fwd(self, y, x, kind, leak, n):
+    rnd, kind = kind & 0x100, kind & 0xFF
     v = f32(x, n)
     out = {1: lambda: np.maximum(v, 0), 2: lambda: np.maximum(v, np.float32(leak) * v),
            3: lambda: (1.0 / (1.0 + np.exp(-v.astype(np.float64)))).astype(np.float32),
            4: lambda: ((np.tanh(v.astype(np.float64)) + 1.0) / 2.0).astype(np.float32)}[kind]()
-    f32(y, n)[:] = out
+    f32(y, n)[:] = rna_tf32(out) if rnd else out
 
   def cgan_act_bwd(self, dx, dy, ref, kind, leak, n):
+    rnd, kind = kind & 0x100, kind & 0xFF
     g, r = f32(dy, n), f32(ref, n)
     if kind == 1:
       out = g * (r > 0)
@@ -307,10 +386,14 @@ class EmulatedLib(object):
       out = g * r * (1 - r)
     else:                                  # y = (tanh+1)/2  =>  dy/dx = (1 - tanh^2)/2 = 2 y (1 - y)
       out = g * 2 * r * (1 - r)
-    f32(dx, n)[:] = out
+    f32(dx, n)[:] = rna_tf32(out) if rnd else out
 
   def cgan_add(self, y, a, b, n):
     f32(y, n)[:] = f32(a, n) + f32(b, n)
+
+  def cgan_add_tf32(self, y, a, b, n, round_tf32):
+    out = f32(a, n) + f32(b, n)
+    f32(y, n)[:] = rna_tf32(out) if round_tf32 else out
 
   def cgan_avgpool2_fwd(self, y, x, n, h, w, c):
     v = f32(x, n * h * w * c).reshape(n, h // 2, 2, w // 2, 2, c)

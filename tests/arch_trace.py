@@ -75,15 +75,19 @@ def _reshape(x, *shape):
   return shape
 
 
-def _conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME"):
+def _conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME", relu=False, residual=None, round_out=False):
   n, h, ww, cin = x.shape
   kh, kw, wcin, cout = w.shape
   if wcin != cin:
     raise ValueError("conv2d: kernel expects %d input channels, got %d" % (wcin, cin))
   vh, vw = (2 * h, 2 * ww) if upsample else (h, ww)
   if padding == "SAME":
-    return (n, -(-vh // stride), -(-vw // stride), cout)
-  return (n, (vh - kh) // stride + 1, (vw - kw) // stride + 1, cout)
+    out = (n, -(-vh // stride), -(-vw // stride), cout)
+  else:
+    out = (n, (vh - kh) // stride + 1, (vw - kw) // stride + 1, cout)
+  if residual is not None and tuple(residual.shape) != out:
+    raise ValueError("conv2d: residual shape %s does not match the output %s" % (residual.shape, out))
+  return out
 
 
 def _deconv2d(x, w, bias, out_hw, stride):

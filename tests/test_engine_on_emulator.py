@@ -15,6 +15,9 @@ STEP_TESTS = ["test_resnet_cifar_forward", "test_resnet_cifar_cycle_sn_bn", "tes
               "test_initialisation_rules_and_training_determinism"]
 EVAL_TESTS = ["test_resize_bilinear_matches_tf_semantics", "test_pool2d_tf_semantics", "test_inception_v3_features",
               "test_train_from_input_pipeline", "test_eval_after_train_schedule_and_checkpoint_roundtrip"]
+# math_mode 1 above the emulator (which models the tensor-core ARITHMETIC: TF32-rounded operands, fp32 accumulation):
+# the pre-rounding / fused-epilogue plumbing of kernels.py, the in-situ contraction checker and the TF32-emulating oracle
+TF32_CASES = ["resnet_cifar", "resnet5_wgangp"]
 
 
 @pytest.mark.parametrize("name", STEP_TESTS)
@@ -38,6 +41,22 @@ def test_evaluation_and_schedule_suite_on_the_emulator(name, tmp_path):
   fn = getattr(gpu_tests, name)
   with emulated_library():
     fn(K, tmp_path) if "tmp_path" in inspect.signature(fn).parameters else fn(K)
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+def test_tf32_mode_network_parity_on_the_emulator(case):
+  import tests.test_tf32_parity_gpu as gpu_tests
+  with emulated_library() as lib:
+    gpu_tests.test_tf32_network_parity(case)
+    assert lib.launches > 0
+
+
+def test_inference_mode_generator_and_eval_loop_on_the_emulator():
+  """Accumulator fill, EMA weight swap, inference-mode generator and the whole evaluation loop vs oracle/eval.py."""
+  import tests.test_eval_gpu as gpu_tests
+  from compare_gan_b200 import kernels as K
+  with emulated_library():
+    gpu_tests.test_inference_mode_generator_and_eval_loop_match_the_oracle(K, "accumulators_and_ema")
 
 
 def _kernel_test_cases():

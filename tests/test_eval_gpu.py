@@ -173,3 +173,69 @@ def test_train_from_input_pipeline(K, tmp_path):
   for i in range(k1):
     want = fake[ids[(2 * k1 + i) * 8:(2 * k1 + i + 1) * 8]]
     np.testing.assert_array_equal(gan.inputs[i]["images"].cpu(), want)
+
+
+@pytest.mark.parametrize("case", ["moving_averages", "accumulators_and_ema"])
+def test_inference_mode_generator_and_eval_loop_match_the_oracle(K, case):
+  """The evaluation hand-off of the reference (eval_gan_lib.py:65-212, modular_gan.py:266-285) against its oracle
+  restatement (oracle/eval.py), from IDENTICAL trained state: the generator in inference mode reads the BN moving
+  averages (resnet_cifar10.gin) or the accumulators filled by `_update_bn_accumulators` with the EMA shadows swapped in
+  for the weights (biggan_imagenet128.gin); then the whole loop — seed, z / label stream, batches, fake data sets,
+  Inception features, FID / IS / KID — within the +-0.5 % north_star states."""
+  from compare_gan_b200 import eval_gan_lib, eval_utils
+  from compare_gan_b200.metrics import fid_score, inception_score, kid_score
+  from oracle import eval as oeval
+  from tests.gpu_util import make_inputs
+  if case == "moving_averages":
+    eng, orc = make_pair("resnet_cifar_arch", (32, 32, 3), 8, d_sn=True, disc_iters=1)
+    nc, zd = 0, 128
+  else:
+    eb = ["resnet_biggan.Generator.blocks_with_attention = 'B2'", "resnet_biggan.Discriminator.blocks_with_attention = 'B1'"]
+    eng, orc = make_pair("resnet_biggan_arch", (32, 32, 3), 8, loss="hinge", disc_iters=1, g_bn="conditional_batch_norm",
+                         g_sn=True, d_sn=True, sn_singular="auto", conditional=True, num_classes=10, initializer="orthogonal",
+                         use_moving_averages=False, g_lr=1e-3, d_lr=5e-4, beta1=0.0, beta2=0.999, z_dim=120, g_use_ema=True,
+                         ema_start_step=0, ch=8, extra_bindings=eb, project_y=True)
+    nc, zd = 10, 120
+  rng = np.random.RandomState(2)
+  for _ in range(2):          # the state the evaluation reads must differ from its initial values
+    eng.set_inputs(*make_inputs(rng, 1, 8, (32, 32, 3), zd, nc))
+    eng.run_cycle()
+  eng.read_losses()
+  orc._ensure_opts()
+  orc.store.load_numpy(eng.state_numpy())
+  if eng.ema is not None:
+    shadow = eng.ema.cpu()
+    assert not np.array_equal(shadow, eng.flat_g["param"].cpu()), "EMA shadows should differ from the weights here"
+    for name, (off, n) in eng.flat_g["views"].items():
+      orc.ema[name] = torch.from_numpy(shadow[off:off + n].reshape(orc.ema[name].shape).copy())
+  # (a) the accumulator pass and one inference batch, same RNG stream on both sides
+  with eval_gan_lib.use_ema_weights(eng):
+    r = np.random.RandomState(42)
+    had = eval_gan_lib._update_bn_accumulators(eng, 8, 48, r)
+    imgs = eval_gan_lib.generate_batch(eng, 8, r).cpu()
+  with oeval._EmaWeights(orc):
+    r = np.random.RandomState(42)
+    ohad = oeval.update_bn_accumulators(orc, 8, 48, r)
+    oimgs = oeval.sample_batch(orc, 8, r).numpy()
+  assert had == ohad == (case != "moving_averages")
+  assert_close(imgs, oimgs, 5e-4, "inference-mode generator (%s)" % case)
+  if had:
+    es = eng.state_numpy()
+    for k, v in orc.store.vars.items():
+      if "/accu/" in k:
+        assert_close(es[k], v.numpy(), 1e-4, k)
+    assert float(es["generator/B1/bn1/accu/accu_counter"]) == pytest.approx(6.0)
+  # weights are back in place after the EMA swap
+  np.testing.assert_array_equal(eng.state_numpy()["generator/fc_noise/kernel"], orc.store.vars["generator/fc_noise/kernel"].detach().numpy())
+  # (b) the whole loop
+  n = 64
+  real = np.random.RandomState(3).rand(n, 32, 32, 3).astype(np.float32)
+  tasks = [fid_score.FIDScoreTask(), inception_score.InceptionScoreTask(), kid_score.KIDScoreTask()]
+  res = eval_gan_lib.evaluate(eng, tasks, num_averaging_runs=2, num_samples=n, batch_size=16, seed=42, real_images=real,
+                              num_accu_examples=48, use_graph=False)
+  ref, _ = oeval.evaluate(orc, eval_utils.get_inception().host_weights, real, n, batch_size=16, seed=42,
+                          num_averaging_runs=2, num_accu_examples=48)
+  for key in ("fid_score", "inception_score", "kid_score"):
+    a, b = res[key + "_mean"], ref[key + "_mean"]
+    assert abs(a - b) <= 5e-3 * abs(b) + (1e-6 if key == "kid_score" else 0), (key, a, b)
+    assert len(res[key + "_list"].split("_")) == 2
