@@ -5,6 +5,7 @@ gin files bind `G.batch_norm_fn`, `G.spectral_norm`, `D.spectral_norm`, ... (ref
 ("generator" / "discriminator" — the root of the checkpoint key space) and runs the definition.
 """
 from .. import gin_lite as gin
+from .. import kernels as K
 from .. import utils
 from .. import variables as V
 
@@ -24,7 +25,15 @@ class _Network(object):
     return list(V.current().trainable_under(self._name).values())
 
   def _run(self, **inputs):
-    with V.variable_scope(self._name):
+    # one batched spectral-norm launch per call for the network's small weights (kernels.SNBatch), keyed by the variable
+    # store in use (a network object may be run against several stores in tests)
+    states = self.__dict__.setdefault("_sn_states", {})
+    store = V.current()
+    state = states.get(id(store))
+    if state is None or state[0]() is not store:
+      import weakref
+      state = states[id(store)] = (weakref.ref(store), K.SNBatch())
+    with K.sn_batch(state[1]), V.variable_scope(self._name):
       return self.apply(**inputs)
 
   def batch_norm(self, inputs, **kwargs):

@@ -56,6 +56,14 @@ struct TcParams {
   long long s_n, s_h, s_w, base;    // output element strides / offset (floats)
   float* out;
   const float* bias;
+  // halo mode (conv_tc_halo_kernel): the taps come in `hg` groups of `hnv` vertically consecutive taps that share their
+  // horizontal offset; one TMA box of bh + hnv - 1 rows serves all taps of a group (the vertical shift is a descriptor
+  // offset of bw rows), so the activation operand crosses L2 -> smem `hg` times per channel chunk instead of hg * hnv
+  int hg, hnv;
+  int h_off_w[4], h_off_h0[4], h_wtap[4][4];
+  int a_halo_bytes;                 // smem footprint of one tile's halo box (1024-aligned)
+  int a_box_bytes;                  // bytes TMA writes per halo box
+  int sa_stages, sb_stages;
 };
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
@@ -74,6 +82,79 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // up to four views of the input tensor (the sub-pixel phases of a 2x-upsampled gradient); plain convs use view 0
 struct AMaps { CUtensorMap m[4]; };
 
+
+__device__ __forceinline__ void tc_tile_origin(const TcParams& p, int t, int& ow0, int& oh0, int& n0) {
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  ow0 = tw * p.bw; oh0 = th * p.bh; n0 = tn * p.bni;
+}
+
+// Epilogue of warps 2..9: tcgen05.ld the accumulators of this CTA's tiles, apply bias / residual / ReLU / mask / TF32
+// rounding, store.  TMEM lane quarter is fixed by (warp id % 4); row of the tile = TMEM lane.
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int tile0, int nt_here, int nb0, int warp,
+                                            int lane) {
+  const int quarter = warp & 3;
+  const int m = quarter * 32 + lane;
+  const int wi = m % p.bw;
+  const int hi = (m / p.bw) % p.bh;
+  const int ni = m / (p.bw * p.bh);
+  for (int tl = 0; tl < nt_here; ++tl) {
+    int ow0, oh0, n0;
+    tc_tile_origin(p, tile0 + tl, ow0, oh0, n0);
+    // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
+    const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
+    float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
+                  (long long)(ow0 + wi) * p.s_w + nb0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * p.bn);
+    // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
+    const int nchunks = p.bn / 32, csplit = (nchunks + 1) / 2;
+    const int cbeg = (warp - 2) < 4 ? 0 : csplit * 32, cend = (warp - 2) < 4 ? csplit * 32 : p.bn;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + (uint32_t)c0, r);
+      if (!row_ok) continue;                 // (the tcgen05.ld above is warp-collective; only the stores are predicated)
+      const long long roff = orow - p.out;   // residual / mask share the output's geometry
+      if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+          v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+          if (p.bias) {
+            const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          }
+          if (p.residual) {
+            const float4 rv = *reinterpret_cast<const float4*>(p.residual + roff + c0 + j);
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
+          if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (p.mask) {
+            const float4 mv = *reinterpret_cast<const float4*>(p.mask + roff + c0 + j);
+            v.x = mv.x > 0.f ? v.x : p.mask_leak * v.x; v.y = mv.y > 0.f ? v.y : p.mask_leak * v.y;
+            v.z = mv.z > 0.f ? v.z : p.mask_leak * v.z; v.w = mv.w > 0.f ? v.w : p.mask_leak * v.w;
+          }
+          if (p.round_out) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
+          *reinterpret_cast<float4*>(orow + c0 + j) = v;
+        }
+      } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nb0 + c0 + j < p.cout) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias) v += p.bias[nb0 + c0 + j];
+            if (p.residual) v += p.residual[roff + c0 + j];
+            if (p.relu) v = fmaxf(v, 0.f);
+            if (p.mask) v = p.mask[roff + c0 + j] > 0.f ? v : p.mask_leak * v;
+            if (p.round_out) v = rna_tf32(v);
+            orow[c0 + j] = v;
+          }
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
@@ -96,13 +177,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   // fetched from L2 once per k-block for mt*128 pixels: the kernel is bound by L2->SM bytes per MMA, not by HBM.
   const int tile0 = blockIdx.x * p.mt;
   const int nt_here = min(p.mt, p.tiles_total - tile0);
-  auto tile_origin = [&](int i, int& ow0, int& oh0, int& n0) {
-    int t = tile0 + i;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int tn = t / p.tiles_h;
-    ow0 = tw * p.bw; oh0 = th * p.bh; n0 = tn * p.bni;
-  };
+  auto tile_origin = [&](int i, int& ow0, int& oh0, int& n0) { tc_tile_origin(p, tile0 + i, ow0, oh0, n0); };
   const int nb0 = blockIdx.y * p.bn;          // first output channel of this CTA
 
   if (warp == 0 && lane == 0) {
@@ -204,76 +279,156 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // TMEM lane quarter is fixed by (warp id % 4); row of the tile = TMEM lane
-    const int quarter = warp & 3;
-    const int m = quarter * 32 + lane;
-    const int wi = m % p.bw;
-    const int hi = (m / p.bw) % p.bh;
-    const int ni = m / (p.bw * p.bh);
-    for (int tl = 0; tl < nt_here; ++tl) {
-    int ow0, oh0, n0;
-    tile_origin(tl, ow0, oh0, n0);
-    // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
-    const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
-    float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
-                  (long long)(ow0 + wi) * p.s_w + nb0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * p.bn);
-    // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
-    const int nchunks = p.bn / 32, csplit = (nchunks + 1) / 2;
-    const int cbeg = (warp - 2) < 4 ? 0 : csplit * 32, cend = (warp - 2) < 4 ? csplit * 32 : p.bn;
-    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-      uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok) continue;                 // (the tcgen05.ld above is warp-collective; only the stores are predicated)
-      const long long roff = orow - p.out;   // residual / mask share the output's geometry
-      if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v;
-          v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
-          v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-          if (p.bias) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- halo variant ------------------------------------------------------------------------------------------------
+// 3x3 stride-1 convolutions (forward and input gradient) are bound by the L2 -> shared-memory operand feed, not by the
+// tensor pipe: per 32-channel k-block a CTA pulls 16 KB of activations per pixel tile for every one
+// of the nine taps although the nine boxes overlap almost completely.  Here the three taps of one kernel COLUMN share a
+// single TMA box of bh + 2 image rows; the vertical shift of a tap is a descriptor start-address offset of bw pixel rows
+// (a multiple of 1024 B, so the 128B-swizzle phase is unchanged).  The activation operand is fetched 3 x (bh+2)/bh times
+// per chunk instead of 9 x (x1.5 instead of x9 at 4-row tiles), which also halves the in-smem rounding work of operands
+// that are not pre-rounded.  Activations and weights run in two rings of their own (a halo box lives for three k-blocks).
+// Up to four pixel tiles per CTA share each weight tile (mt x bn <= 512 TMEM columns), one CTA per SM.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.bn * TC_BK * 4;
+  const int a_stage = p.mt * p.a_halo_bytes;
+  uint8_t* smem_b = smem + p.sa_stages * a_stage;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + p.sb_stages * b_bytes);
+  uint64_t* a_ready = a_full + p.sa_stages;
+  uint64_t* a_empty = a_ready + p.sa_stages;
+  uint64_t* b_full = a_empty + p.sa_stages;
+  uint64_t* b_empty = b_full + p.sb_stages;
+  uint64_t* tmem_full_bar = b_empty + p.sb_stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile0 = blockIdx.x * p.mt;
+  const int nt_here = min(p.mt, p.tiles_total - tile0);
+  const int nb0 = blockIdx.y * p.bn;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.sa_stages; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_ready[s], TC_RWARPS);
+        mbar_init(&a_empty[s], 1);
+      }
+      for (int s = 0; s < p.sb_stages; ++s) {
+        mbar_init(&b_full[s], 1);
+        mbar_init(&b_empty[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: per (channel chunk, tap column) one halo box per tile, then the hnv weight tiles =====
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int g = 0; g < p.hg; ++g) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], (uint32_t)(nt_here * p.a_box_bytes));
+          for (int i = 0; i < nt_here; ++i) {
+            int ow0, oh0, n0;
+            tc_tile_origin(p, tile0 + i, ow0, oh0, n0);
+            tma_load_4d(smem + sa * a_stage + i * p.a_halo_bytes, &tm_a, &a_full[sa], kc * TC_BK, ow0 + p.h_off_w[g],
+                        oh0 + p.h_off_h0[g], n0);
           }
-          if (p.residual) {
-            const float4 rv = *reinterpret_cast<const float4*>(p.residual + roff + c0 + j);
-            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-          }
-          if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (p.mask) {
-            const float4 mv = *reinterpret_cast<const float4*>(p.mask + roff + c0 + j);
-            v.x = mv.x > 0.f ? v.x : p.mask_leak * v.x; v.y = mv.y > 0.f ? v.y : p.mask_leak * v.y;
-            v.z = mv.z > 0.f ? v.z : p.mask_leak * v.z; v.w = mv.w > 0.f ? v.w : p.mask_leak * v.w;
-          }
-          if (p.round_out) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
-          *reinterpret_cast<float4*>(orow + c0 + j) = v;
-        }
-      } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (nb0 + c0 + j < p.cout) {
-            float v = __uint_as_float(r[j]);
-            if (p.bias) v += p.bias[nb0 + c0 + j];
-            if (p.residual) v += p.residual[roff + c0 + j];
-            if (p.relu) v = fmaxf(v, 0.f);
-            if (p.mask) v = p.mask[roff + c0 + j] > 0.f ? v : p.mask_leak * v;
-            if (p.round_out) v = rna_tf32(v);
-            orow[c0 + j] = v;
+          if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+          for (int t = 0; t < p.hnv; ++t) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], (uint32_t)b_bytes);
+            tma_load_3d(smem_b + sb * b_bytes, &tm_b, &b_full[sb], kc * TC_BK, nb0, p.h_wtap[g][t]);
+            if (++sb == p.sb_stages) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t tap_shift = (uint32_t)(p.bw * 128);          // one image row of the box = bw pixel rows of 128 B
+    for (int kc = 0; kc < p.kchunks; ++kc) {
+      for (int g = 0; g < p.hg; ++g) {
+        mbar_wait(p.round_a ? &a_ready[sa] : &a_full[sa], pa);
+        const uint32_t a_addr = smem_u32(smem + sa * a_stage);
+        for (int t = 0; t < p.hnv; ++t) {
+          mbar_wait(&b_full[sb], pb);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t b_addr = smem_u32(smem_b + sb * b_bytes);
+            const uint32_t first = (kc | g | t) ? 1u : 0u;
+            for (int i = 0; i < nt_here; ++i) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 8; ++k)
+                umma_tf32(tmem_base + (uint32_t)(i * p.bn), make_desc(a_addr + i * p.a_halo_bytes + t * tap_shift + k * 32),
+                          make_desc(b_addr + k * 32), idesc, (first | (uint32_t)k) ? 1u : 0u);
+            }
+            umma_commit(&b_empty[sb]);
+            if (t == p.hnv - 1) umma_commit(&a_empty[sa]);
+            if (kc == p.kchunks - 1 && g == p.hg - 1 && t == p.hnv - 1) umma_commit(tmem_full_bar);
+          }
+          __syncwarp();
+          if (++sb == p.sb_stages) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+      }
     }
+  } else {
+    // ===== warps 2..9: round the halo boxes to nearest TF32 in smem (operand not pre-rounded), then the epilogue =====
+    if (p.round_a) {
+      const int q = threadIdx.x - 64;
+      const int n16 = p.a_box_bytes / 16;            // float4s per box (a multiple of 32 * TC_RWARPS, host-checked)
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int it = 0; it < p.kchunks * p.hg; ++it) {
+        mbar_wait(&a_full[sa], pa);
+        for (int tl = 0; tl < nt_here; ++tl) {
+          const uint32_t a4 = smem_u32(smem + sa * a_stage + tl * p.a_halo_bytes);
+#pragma unroll 2
+          for (int i = q; i < n16; i += 32 * TC_RWARPS) {
+            float4 v = lds128(a4 + i * 16);
+            v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w);
+            sts128(a4 + i * 16, v);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[sa]);
+        if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -416,6 +571,97 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   if (!wt) {
     int rc = cgan_tc_prep_weights(ctx, wsrc, taps_total, transpose_w, ncols, kdim, &wt);
     if (rc) return rc;
+  }
+
+  // ---- halo variant: three taps of a kernel column share one (bh+2)-row activation box --------------------------------
+  if (ctx->tc_halo && nviews == 1 && wimg_stride == 0 && ntaps == 9 && gh == h && gw == w && !view_phase_of) {
+    int hbw = 0, hbh = 0;
+    if (w % 32 == 0) { hbw = 32; hbh = 4; } else if (w == 16) { hbw = 16; hbh = 8; }
+    // group the taps by horizontal offset; each group must be three vertically consecutive taps
+    int gw_off[4], gh0[4], gcnt[4] = {0, 0, 0, 0}, gtap[4][4], ng = 0;
+    bool ok = hbw != 0 && h % hbh == 0 && h >= hbh;
+    for (int i = 0; ok && i < ntaps; ++i) {
+      int g = -1;
+      for (int j = 0; j < ng; ++j)
+        if (gw_off[j] == off_w[i]) g = j;
+      if (g < 0) {
+        if (ng == 3) { ok = false; break; }
+        g = ng++; gw_off[g] = off_w[i]; gh0[g] = off_h[i];
+      }
+      if (gcnt[g] == 3) { ok = false; break; }
+      if (off_h[i] < gh0[g]) gh0[g] = off_h[i];
+      gtap[g][gcnt[g]++] = i;
+    }
+    ok = ok && ng == 3;
+    for (int g = 0; ok && g < ng; ++g) {
+      if (gcnt[g] != 3) { ok = false; break; }
+      int ordered[3] = {-1, -1, -1};
+      for (int j = 0; j < 3; ++j) {
+        int dh = off_h[gtap[g][j]] - gh0[g];
+        if (dh < 0 || dh > 2 || ordered[dh] >= 0) { ok = false; break; }
+        ordered[dh] = wtap[gtap[g][j]];
+      }
+      for (int j = 0; ok && j < 3; ++j) p.h_wtap[g][j] = ordered[j];
+      p.h_off_w[g] = gw_off[g]; p.h_off_h0[g] = gh0[g];
+    }
+    if (ok) {
+      p.hg = 3; p.hnv = 3;
+      p.bw = hbw; p.bh = hbh; p.bni = 1;
+      p.tiles_w = w / hbw; p.tiles_h = h / hbh;
+      const long long tiles_total = (long long)p.tiles_w * p.tiles_h * n;
+      p.rows_used = 128;
+      p.bn = tc_pick_bn_occupancy(ncols_pad, tiles_total, ctx->num_sms);
+      const int ncol_tiles = ncols_pad / p.bn;
+      p.a_box_bytes = (hbh + 2) * hbw * 128;
+      p.a_halo_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
+      const int b_bytes = p.bn * TC_BK * 4;
+      // pixel tiles per CTA (they share every weight tile): as many as the 512 TMEM columns hold, while two waves of CTAs
+      // remain and the weight ring keeps >= 4 stages (a k-block of mt tiles is ~mt*bn/2 clocks of MMA; the ring has to
+      // cover the L2 latency of ~2-4 k-blocks).  The activation ring has two stages, each good for three k-blocks.
+      const int budget = 227 * 1024 - 1024 - 512;
+      const int mt_cap = ctx->tc_mt_max >= 2 ? 4 : 1;
+      p.sa_stages = 2;
+      p.mt = 1;
+      for (int m = mt_cap; m >= 2; --m) {
+        if (m * p.bn > 512 || tiles_total * ncol_tiles < 2ll * m * ctx->num_sms) continue;
+        if ((budget - p.sa_stages * m * p.a_halo_bytes) / b_bytes < 4) continue;
+        p.mt = m;
+        break;
+      }
+      p.sb_stages = (budget - p.sa_stages * p.mt * p.a_halo_bytes) / b_bytes;
+      if (p.sb_stages > 8) p.sb_stages = 8;
+      ok = p.sb_stages >= 2 && (p.a_box_bytes / 16) % (32 * TC_RWARPS) == 0;
+      if (ok) {
+        p.tiles_total = (int)tiles_total;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.mt * p.bn) p.tmem_cols *= 2;
+        CUtensorMap tm_a, tm_bh;
+        if (!make_act_map(&tm_a, in + view_off[0], kdim, w, h, n, in_sw, in_sh, in_sn, hbw, hbh + 2, 1))
+          return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A halo) failed%s", "cgan_conv_tc");
+        cuuint64_t dims[3] = {(cuuint64_t)kdim_pad, (cuuint64_t)ncols_pad, (cuuint64_t)taps_total};
+        cuuint64_t strides[2] = {(cuuint64_t)kdim_pad * 4, (cuuint64_t)ncols_pad * kdim_pad * 4};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)p.bn, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&tm_bh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) failed%s", "cgan_conv_tc");
+        size_t smem = (size_t)p.sa_stages * p.mt * p.a_halo_bytes + (size_t)p.sb_stages * b_bytes + 1024 + 512;
+        static bool halo_attr_set = false;
+        if (!halo_attr_set) {
+          CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          halo_attr_set = true;
+        }
+        dim3 grid((unsigned)((tiles_total + p.mt - 1) / p.mt), (unsigned)ncol_tiles);
+        conv_tc_halo_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_a, tm_bh, p);
+        CGAN_LAUNCHED(ctx);
+        return CGAN_OK;
+      }
+    }
+    // not eligible after all: restore the standard geometry
+    tc_geometry(n, gh, gw, &p.bw, &p.bh, &p.bni, &p.tiles_w, &p.tiles_h, &tiles_n);
+    p.rows_used = p.bw * p.bh * p.bni;
+    p.bn = tc_pick_bn_occupancy(ncols_pad, (long long)p.tiles_w * p.tiles_h * tiles_n, ctx->num_sms);
+    p.hg = p.hnv = 0;
   }
 
   AMaps tm_as;

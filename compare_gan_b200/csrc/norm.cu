@@ -335,6 +335,95 @@ __global__ void sn_bwd_kernel(float* __restrict__ dw, const float* __restrict__ 
   }
 }
 
+// ---- batched spectral norm: ONE launch runs the power iteration of every small weight of a network ----------------
+// A discriminator call site of resnet_cifar10 / SNDCGAN touches 8-13 spectrally normalised kernels of at most a few
+// hundred KB each; run separately that is ~7 tiny launches per kernel (two GEMVs with their finishing passes, two
+// normalisations, the scale, the copy of u) = hundreds of launches per training cycle.  Here one CTA per weight does the
+// whole of arch_ops.py:503-531 out of L2: t = W^T u (or W u), v = normalize(t), s = W v (or v W), u' = normalize(s),
+// sigma = <u', s>, wbar = W / sigma, u <- u', plus the copy of u' the backward needs.  Fixed summation order.
+__device__ __forceinline__ void sn_coldot(float* out, const float* __restrict__ w, const float* x, int rows, int cols, float* red) {
+  // out[c] = sum_r w[r, c] * x[r]; thread (c, l): column c of a 32..1024-wide block, row lane l
+  for (int cb = 0; cb < cols; cb += 1024) {
+    const int cw = min(1024, cols - cb);
+    int cpad = 32;
+    while (cpad < cw) cpad <<= 1;
+    const int lanes = 1024 / cpad;
+    const int c = threadIdx.x % cpad, l = threadIdx.x / cpad;
+    float acc = 0.f;
+    if (c < cw)
+      for (int r = l; r < rows; r += lanes) acc = fmaf(w[(size_t)r * cols + cb + c], x[r], acc);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (l == 0 && c < cw) {
+      float sum = 0.f;
+      for (int j = 0; j < lanes; ++j) sum += red[j * cpad + c];
+      out[cb + c] = sum;
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void sn_rowdot(float* out, const float* __restrict__ w, const float* x, int rows, int cols) {
+  // out[r] = sum_c w[r, c] * x[c]; one warp per row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < rows; r += 32) {
+    float acc = 0.f;
+    for (int c = lane; c < cols; c += 32) acc = fmaf(w[(size_t)r * cols + c], x[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[r] = acc;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float sn_normalize(float* v, int n, float eps, float* sh, float* dot_with_raw) {
+  // v <- v * rsqrt(max(sum v^2, eps)); returns via *dot_with_raw the dot product of the normalised and the raw vector
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i] * v[i];
+  s = block_sum(s, sh);
+  const float scale = 1.0f / sqrtf(fmaxf(s, eps));
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float raw = v[i], o = raw * scale;
+    v[i] = o;
+    d += o * raw;
+  }
+  d = block_sum(d, sh);
+  if (dot_with_raw) *dot_with_raw = d;
+  return scale;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+sn_batched_kernel(const cgan_sn_item* __restrict__ items, float eps, float* wbar_base, float* v_base, float* sigma_base,
+                  float* u_used_base) {
+  extern __shared__ float sn_smem[];
+  __shared__ float sh[32];
+  const cgan_sn_item it = items[blockIdx.x];
+  const int rows = it.rows, cols = it.cols;
+  const int nu = it.left ? rows : cols, nv = it.left ? cols : rows;
+  float* red = sn_smem;                 // 1024 floats
+  float* uv = red + 1024;               // u (nu floats)
+  float* vv = uv + nu;                  // v (nv floats)
+  for (int i = threadIdx.x; i < nu; i += blockDim.x) uv[i] = it.u[i];
+  __syncthreads();
+  if (it.left) sn_coldot(vv, it.w, uv, rows, cols, red); else sn_rowdot(vv, it.w, uv, rows, cols);
+  sn_normalize(vv, nv, eps, sh, nullptr);
+  __syncthreads();
+  if (it.left) sn_rowdot(uv, it.w, vv, rows, cols); else sn_coldot(uv, it.w, vv, rows, cols, red);
+  float sigma;
+  sn_normalize(uv, nu, eps, sh, &sigma);
+  __syncthreads();
+  float* v_out = v_base + it.v_off;
+  float* u_used = u_used_base + it.u_off;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) v_out[i] = vv[i];
+  for (int i = threadIdx.x; i < nu; i += blockDim.x) {
+    const float un = uv[i];
+    it.u[i] = un;
+    u_used[i] = un;
+  }
+  if (threadIdx.x == 0) sigma_base[blockIdx.x] = sigma;
+  float* wbar = wbar_base + it.wbar_off;
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) wbar[i] = it.w[i] / sigma;    // "w / norm_value" (arch_ops.py:531)
+}
+
 inline bool v4_ok(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
            reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f)) & 15) == 0;
@@ -490,6 +579,22 @@ int cgan_spectral_norm(cgan_ctx* ctx, const float* w, int rows, int cols, int le
     CGAN_LAUNCHED(ctx);
   }
   if (wbar) return cgan_scale_by_dev(ctx, wbar, w, sigma, 1.0f, 1, (int64_t)rows * cols);
+  return CGAN_OK;
+}
+
+int cgan_spectral_norm_batched(cgan_ctx* ctx, const cgan_sn_item* items_dev, int n, int max_rows_plus_cols, float eps,
+                               float* wbar_base, float* v_base, float* sigma_base, float* u_used_base) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, items_dev && n > 0 && wbar_base && v_base && sigma_base && u_used_base, "bad argument");
+  const size_t smem = (size_t)(1024 + max_rows_plus_cols) * sizeof(float);
+  CGAN_REQUIRE(ctx, smem <= 200 * 1024, "rows + cols too large for the batched kernel (use cgan_spectral_norm)");
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CGAN_CUDA(ctx, cudaFuncSetAttribute(sn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  sn_batched_kernel<<<n, 1024, smem, ctx->stream>>>(items_dev, eps, wbar_base, v_base, sigma_base, u_used_base);
+  CGAN_LAUNCHED(ctx);
   return CGAN_OK;
 }
 

@@ -46,9 +46,21 @@ _INCEPTION = {}
 
 
 def get_inception():
+  """The Inception-v3 feature extractor of the metrics.  Real weights (the frozen TF-GAN graph's tensors in this package's
+  key space, `inception/<layer>/kernel|bias`) are read from the .npz named by $CGAN_INCEPTION_NPZ; without it the
+  extractor runs on deterministic SYNTHETIC weights of the exact topology (the graph cannot be downloaded here,
+  reference eval_utils.py:41-49) — throughput is then real, the FID / IS values are not comparable with published ones."""
+  import os
   dev = K._RT["device"]
   if dev not in _INCEPTION:
-    _INCEPTION[dev] = inception.InceptionV3()
+    path = os.environ.get("CGAN_INCEPTION_NPZ")
+    weights = None
+    if path:
+      data = np.load(path)
+      weights = {k: np.asarray(data[k], np.float32) for k in data.files}
+    net = inception.InceptionV3(weights)
+    net.synthetic = weights is None
+    _INCEPTION[dev] = net
   return _INCEPTION[dev]
 
 
@@ -81,8 +93,26 @@ class FeatureAccumulator(object):
       self.n = int(cnt.item())
     sample.moments = fid_score.moments_from_sums(self.s.cpu().numpy(), self.sxx.cpu().numpy(), self.n)
     if self.keep:
-      sample.set_inception_features(torch.cat(self.acts).cpu().numpy(), torch.cat(self.logits).cpu().numpy())
+      acts, logits = torch.cat(self.acts), torch.cat(self.logits)
+      if tpu_ops.num_replicas() > 1:        # IS / KID need every sample's features: gather the shards (padded to equal length)
+        acts, logits = _gather_rows(acts), _gather_rows(logits)
+      sample.set_inception_features(acts.cpu().numpy(), logits.cpu().numpy())
     return sample
+
+
+def _gather_rows(t):
+  """all_gather of a [n_local, d] tensor whose n_local may differ by rank; rows come back in rank order."""
+  import torch.distributed as dist
+  world = dist.get_world_size()
+  n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+  counts = [torch.zeros_like(n) for _ in range(world)]
+  dist.all_gather(counts, n)
+  counts = [int(c.item()) for c in counts]
+  pad = torch.zeros(max(counts), t.shape[1], dtype=t.dtype, device=t.device)
+  pad[:t.shape[0]] = t
+  parts = [torch.zeros_like(pad) for _ in range(world)]
+  dist.all_gather(parts, pad)
+  return torch.cat([p[:c] for p, c in zip(parts, counts)])
 
 
 def inception_transform(images01):

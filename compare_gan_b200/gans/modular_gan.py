@@ -58,8 +58,9 @@ class ModularGAN(AbstractGAN):
                ema_decay=0.9999, ema_start_step=40000, g_optimizer_fn=AdamOptimizer, d_optimizer_fn=None,
                g_lr=0.0002, d_lr=None, conditional=False, fit_label_distribution=False, math_mode=0):
     super(ModularGAN, self).__init__(dataset=dataset, parameters=parameters, model_dir=model_dir)
-    if deprecated_split_disc_calls or fit_label_distribution:
-      raise NotImplementedError("deprecated_split_disc_calls / fit_label_distribution are outside the hot path")
+    if deprecated_split_disc_calls or fit_label_distribution or experimental_joint_gen_for_disc:
+      raise NotImplementedError("deprecated_split_disc_calls / fit_label_distribution / experimental_joint_gen_for_disc are "
+                                "outside the hot path (the last one changes G's batch statistics and must not be ignored)")
     self._experimental_joint_gen_for_disc = experimental_joint_gen_for_disc
     self._g_use_ema = g_use_ema
     self._ema_decay = ema_decay
@@ -186,11 +187,18 @@ class ModularGAN(AbstractGAN):
     return self
 
   # ---- one cycle (reference model_fn :512-604, unrolled) -------------------------------------------------
+  def _grad_sinks(self, prefix, params):
+    """{id(variable): its slot in the flat gradient buffer}: tape.backward lets the vjp that produces a variable's
+    gradient write it there directly (kernels._grad_out)."""
+    return {id(v): self.store.grad_view(prefix, name) for name, v in params.items()}
+
   def _apply_grads(self, prefix, flat, grads, names):
-    K.fill_(flat["grad"], 0.0)
     for name, g in zip(names, grads):
-      if g is not None:
-        K.copy_(self.store.grad_view(prefix, name), g)
+      view = self.store.grad_view(prefix, name)
+      if g is None:
+        K.fill_(view, 0.0)                      # unreachable variable: zero gradient (tf.gradients would return None)
+      elif g.ptr != view.ptr:                   # accumulated from several uses, or produced by an op without a sink
+        K.copy_(view, g)
     world = tpu_ops.num_replicas()
     if world > 1:
       tpu_ops.cross_replica_sum_(flat["grad"])
@@ -216,7 +224,8 @@ class ModularGAN(AbstractGAN):
         f = dict(self.inputs[i])
         f["generated"] = tape.DT(gen(i, False).t)       # tf.stop_gradient
         self.create_loss(f, f.get("labels"), for_discriminator=True)
-        grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add_grad)
+        grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add_grad,
+                              sinks=self._grad_sinks("discriminator", d_params))
         scale = self._apply_grads("discriminator", self.flat_d, grads, list(d_params.keys()))
         self.d_opt.apply(scale)
         K._call("copy", self.losses.ptr + 4 * i, self.d_loss.ptr, 1)
@@ -224,7 +233,8 @@ class ModularGAN(AbstractGAN):
       f = dict(self.inputs[k])                          # _train_generator (:487-510)
       f["generated"] = gen(k, True)
       self.create_loss(f, f.get("labels"), for_discriminator=False)
-      grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add_grad)
+      grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add_grad,
+                            sinks=self._grad_sinks("generator", g_params))
       scale = self._apply_grads("generator", self.flat_g, grads, list(g_params.keys()))
       self.g_opt.apply(scale, self.ema, self._ema_decay, self._ema_start_step)
       K._call("copy", self.losses.ptr + 4 * k, self.g_loss.ptr, 1)
@@ -335,7 +345,24 @@ class ModularGAN(AbstractGAN):
     return path
 
   def load_checkpoint(self, path):
-    data = {k.replace("|", "/"): v for k, v in np.load(path).items()}
+    """Restores model variables, Adam slots, EMA shadows and the step counters from this package's `.npz` or from a
+    TensorFlow V2 checkpoint written by the reference (`model.ckpt-<step>`: the prefix, its `.index` or a directory holding
+    checkpoints) — the variable names are the same key space (tf_checkpoint.py)."""
+    import os
+    if path.endswith(".npz"):
+      data = {k.replace("|", "/"): v for k, v in np.load(path).items()}
+    else:
+      from .. import tf_checkpoint
+      prefix = path[:-len(".index")] if path.endswith(".index") else path
+      if os.path.isdir(prefix):
+        prefix = tf_checkpoint.latest_checkpoint(prefix)
+        if prefix is None:
+          raise ValueError("no model.ckpt-<step>.index under %s" % path)
+      data = tf_checkpoint.load_checkpoint(prefix)
+      missing = [k for k in self.store.vars if k not in data and not k.endswith("update_accus")]
+      if missing:
+        raise ValueError("TensorFlow checkpoint %s lacks %d variables of this model, e.g. %s" % (prefix, len(missing), missing[:3]))
+      data.setdefault("global_step_disc", np.array(0, np.int64))
     self.store.load_numpy({k: v for k, v in data.items() if k in self.store.vars})
     for prefix, flat, opt in (("generator", self.flat_g, self.g_opt), ("discriminator", self.flat_d, self.d_opt)):
       m, v = opt.m.cpu(), opt.v.cpu()
@@ -349,6 +376,8 @@ class ModularGAN(AbstractGAN):
       opt.m.t.copy_(torch.from_numpy(m)); opt.v.t.copy_(torch.from_numpy(v))
       if ema is not None:
         self.ema.t.copy_(torch.from_numpy(ema))
+    # TF counts sub-steps differently on CPU/GPU (non-unrolled: one global_step per D or G update); the counters are only
+    # used for Adam's bias correction and the EMA start here
     self.g_opt.step.fill_(int(data["global_step"]))
     self.d_opt.step.fill_(int(data["global_step_disc"]))
     torch.cuda.synchronize()

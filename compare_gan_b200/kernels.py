@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .tape import DT, attach, no_record, recording
-from .tape import grad_accumulator as _grad_accumulator
+from .tape import grad_accumulator as _grad_accumulator, take_sink as _take_sink
 
 _RT = {"lib": None, "device": None, "math_mode": 0}
 
@@ -120,6 +120,19 @@ def _call(name, *args):
 
 
 # ------------------------------------------------------------------------------------ basic helpers
+
+def _grad_out(leaf, *shape):
+  """Where the gradient w.r.t. `leaf` goes: the destination tape.backward's caller offered for it (its slot in the flat
+  gradient buffer — no copy afterwards), else fresh memory."""
+  s = _take_sink(leaf)
+  if s is not None:
+    n = 1
+    for v in shape:
+      n *= v
+    if s.numel == n:
+      return s.view(*shape)
+  return empty(*shape)
+
 
 def fill_(x, value):
   _call("fill", x.ptr, float(value), x.numel)
@@ -328,8 +341,8 @@ def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME", relu=False
     if relu:
       g = act_bwd(g, yv, ACT_RELU, round_tf32=True)
     return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
-            conv2d_wgrad(d, x, g) if needs[1] else None,
-            colsum(reshape(g, -1, cout)) if (bias is not None and needs[2]) else None,
+            conv2d_wgrad(d, x, g, leaf=w) if needs[1] else None,
+            colsum(reshape(g, -1, cout), leaf=bias) if (bias is not None and needs[2]) else None,
             g if (residual is not None and needs[3]) else None]
   return attach("conv2d", y, [x, w, bias, residual], vjp)
 
@@ -348,8 +361,8 @@ def conv2d_dgrad(d, dy, w, bias=None, round_out=False):
 
   def vjp(g, needs):   # linear in dy and in w
     return [_taped_fwd(d, g, w, round_out=_grad_feeds_tc(dy)) if needs[0] else None,
-            conv2d_wgrad(d, g, dy) if needs[1] else None,
-            colsum(reshape(g, -1, cin)) if (bias is not None and needs[2]) else None]
+            conv2d_wgrad(d, g, dy, leaf=w) if needs[1] else None,
+            colsum(reshape(g, -1, cin), leaf=bias) if (bias is not None and needs[2]) else None]
   return attach("conv2d_dgrad", dx, [dy, w, bias], vjp)
 
 
@@ -358,13 +371,13 @@ def _taped_fwd(d, x, w, round_out=False):
 
   def vjp(g, needs):
     return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
-            conv2d_wgrad(d, x, g) if needs[1] else None]
+            conv2d_wgrad(d, x, g, leaf=w) if needs[1] else None]
   return attach("conv2d", y, [x, w], vjp)
 
 
-def conv2d_wgrad(d, x, dy):
-  """Filter gradient (TF Conv2DBackpropFilter); deterministic split-K."""
-  dw = empty(d.kh, d.kw, d.cin, d.cout)
+def conv2d_wgrad(d, x, dy, leaf=None):
+  """Filter gradient (TF Conv2DBackpropFilter); deterministic split-K.  `leaf`: the kernel variable, see _grad_out."""
+  dw = _grad_out(leaf, d.kh, d.kw, d.cin, d.cout)
   flags = 0
   if tf32_on():
     flags = (_lib.CONV_IN_TF32 if x.tf32 else 0) | (_lib.CONV_IN2_TF32 if dy.tf32 else 0)
@@ -393,15 +406,15 @@ def deconv2d(x, w, bias, out_hw, stride):
   return conv2d_dgrad(d, x, w, bias)
 
 
-def matmul(a, b, ta=False, tb=False):
-  """tf.matmul (arch_ops.py:548)."""
+def matmul(a, b, ta=False, tb=False, leaf=None):
+  """tf.matmul (arch_ops.py:548).  `leaf`: the variable this product is the gradient of, see _grad_out."""
   m = a.shape[1] if ta else a.shape[0]
   k = a.shape[0] if ta else a.shape[1]
   kb = b.shape[1] if tb else b.shape[0]
   n = b.shape[0] if tb else b.shape[1]
   if k != kb:
     raise ValueError("matmul: inner dimensions differ: %d vs %d" % (k, kb))
-  c = empty(m, n)
+  c = _grad_out(leaf, m, n)
   _call("gemm", int(ta), int(tb), m, n, k, 1.0, a.ptr, a.shape[1], b.ptr, b.shape[1], 0.0, c.ptr, n)
 
   def vjp(g, needs):
@@ -409,7 +422,7 @@ def matmul(a, b, ta=False, tb=False):
     if needs[0]:
       ga = matmul(b, g, tb, True) if ta else matmul(g, b, False, not tb)
     if needs[1]:
-      gb = matmul(g, a, True, ta) if tb else matmul(a, g, not ta, False)
+      gb = matmul(g, a, True, ta, leaf=b) if tb else matmul(a, g, not ta, False, leaf=b)
     return [ga, gb]
   return attach("matmul", c, [a, b], vjp)
 
@@ -437,10 +450,10 @@ def bmm(a, b, ta=False, tb=False):
   return attach("bmm", c, [a, b], vjp)
 
 
-def colsum(x2, groups=1):
-  """Per-channel sum over rows (bias / beta gradients)."""
+def colsum(x2, groups=1, leaf=None):
+  """Per-channel sum over rows (bias / beta gradients).  `leaf`: the variable this is the gradient of, see _grad_out."""
   rows, c = x2.shape
-  out = empty(c) if groups == 1 else empty(groups, c)
+  out = _grad_out(leaf, c) if groups == 1 else empty(groups, c)
   _call("colsum", out.ptr, x2.ptr, groups, rows // groups, c)
   return out   # leaf of the backward pass: never differentiated again
 
@@ -451,7 +464,7 @@ def bias_add(x, bias):
   _call("bias_add", y.ptr, x.ptr, bias.ptr, x.numel // c, c)
 
   def vjp(g, needs):
-    return [g if needs[0] else None, colsum(reshape(g, -1, c)) if needs[1] else None]
+    return [g if needs[0] else None, colsum(reshape(g, -1, c), leaf=bias) if needs[1] else None]
   return attach("bias_add", y, [x, bias], vjp)
 
 
@@ -727,9 +740,9 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
     sums = empty(2 * c)
     dgamma = dbeta = None
     if gamma is not None and needs[1]:
-      dgamma = empty(*gamma.shape)
+      dgamma = _grad_out(gamma, *gamma.shape)
     if beta is not None and needs[2]:
-      dbeta = empty(*beta.shape)
+      dbeta = _grad_out(beta, *beta.shape)
     with no_record():
       _call("bn_bwd_reduce", sums.ptr, None if dgamma is None else dgamma.ptr, None if dbeta is None else dbeta.ptr,
             g.ptr, x.ptr, rows, c, rps, mv.ptr, float(eps), None if gamma is None else gamma.ptr, int(cond))
@@ -776,9 +789,16 @@ def bn_infer(x, gamma, beta, eps, state, use_moving_averages, cond=False, relu_a
 # ------------------------------------------------------------------------------------ spectral norm
 
 def spectral_normalize(w, u, left, eps=1e-12):
-  """arch_ops.py:453-535: one power iteration, `u` (persistent state) updated in place, returns w/sigma."""
+  """arch_ops.py:453-535: one power iteration, `u` (persistent state) updated in place, returns w/sigma.  Inside a
+  `sn_batch` scope the small weights of a network are served from ONE batched launch (see SNBatch)."""
   rows = w.numel // w.shape[-1]
   cols = w.shape[-1]
+  batch = _SN_SCOPE[-1]
+  if batch is not None:
+    hit = batch.lookup(w, u, left, eps)
+    if hit is not None:
+      wbar, v, sigma, u_used = hit
+      return _sn_attach(w, wbar, rows, cols, left, u_used, v, sigma)
   v = empty(cols if left else rows)
   sigma = empty(1)
   wbar = empty(*w.shape)
@@ -786,15 +806,103 @@ def spectral_normalize(w, u, left, eps=1e-12):
   # the backward needs u AFTER this call's update; later calls overwrite u_var, so keep a copy
   u_used = empty(*u.shape)
   _call("copy", u_used.ptr, u.ptr, u.numel)
+  return _sn_attach(w, wbar, rows, cols, left, u_used, v, sigma)
 
+
+def _sn_attach(w, wbar, rows, cols, left, u_used, v, sigma):
   wbar_v = DT(wbar.t)
 
   def vjp(g, needs):
     _no_second_order("spectral_normalize")
-    dw = empty(*w.shape)
+    dw = _grad_out(w, *w.shape)
     _call("spectral_norm_bwd", dw.ptr, g.ptr, wbar_v.ptr, rows, cols, int(left), u_used.ptr, v.ptr, sigma.ptr)
     return [dw]
   return attach("spectral_norm", wbar, [w], vjp)
+
+
+_SN_SCOPE = [None]
+SN_BATCH_MAX_ELEMS = 1 << 18        # weights up to 1 MB go through the one-CTA-per-weight batched kernel
+SN_BATCH_MAX_DIMS = 12288           # rows + cols (shared-memory vectors of that CTA)
+
+
+class SNBatch(object):
+  """The spectrally normalised weights of one network (generator or discriminator), learned on its first call.  From
+  the second call on, entering the scope runs the power iteration of all SMALL weights (the 3x3x128x128 kernels of
+  resnet_cifar's discriminator, SNDCGAN's first layers, the conditional-BN projections of BigGAN) in one launch of
+  cgan_spectral_norm_batched, and `spectral_normalize` hands out views of its outputs — same arithmetic, same one
+  iteration per call site and weight (arch_ops.py:503-531), ~7 launches per weight fewer.  Large weights keep the
+  per-weight kernels, which stream them from HBM with the whole GPU."""
+
+  def __init__(self):
+    self.plan, self.keys, self.complete = [], set(), False
+    self.table, self.table_ptrs, self.results = None, None, {}
+
+  def lookup(self, w, u, left, eps):
+    rows, cols = w.numel // w.shape[-1], w.shape[-1]
+    if not self.complete:
+      small = rows * cols <= SN_BATCH_MAX_ELEMS and rows + cols <= SN_BATCH_MAX_DIMS
+      if small and id(w) not in self.keys and w.node is None:      # a raw variable (not e.g. an EMA-swapped temporary)
+        self.keys.add(id(w))
+        self.plan.append((w, u, bool(left), float(eps)))
+      return None
+    return self.results.pop(id(w), None)
+
+  def run(self):
+    """Launch the batched iteration for this call; fills self.results {id(w): (wbar, v, sigma, u_used)}."""
+    import numpy as np
+    self.results = {}
+    if not self.plan:
+      return
+    eps = self.plan[0][3]
+    ptrs = [(w.ptr, u.ptr) for w, u, _, _ in self.plan]
+    if self.table is None or self.table_ptrs != ptrs:
+      items = np.zeros(len(self.plan), dtype=[("w", "<u8"), ("u", "<u8"), ("rows", "<i4"), ("cols", "<i4"), ("left", "<i4"),
+                                              ("reserved", "<i4"), ("wbar_off", "<i8"), ("v_off", "<i8"), ("u_off", "<i8")])
+      wo = vo = uo = 0
+      self.layout = []
+      for i, (w, u, left, e) in enumerate(self.plan):
+        rows, cols = w.numel // w.shape[-1], w.shape[-1]
+        nu, nv = (rows, cols) if left else (cols, rows)
+        items[i] = (w.ptr, u.ptr, rows, cols, int(left), 0, wo, vo, uo)
+        self.layout.append((wo, vo, uo, rows, cols, nu, nv))
+        wo += (rows * cols + 63) // 64 * 64
+        vo += (nv + 63) // 64 * 64
+        uo += (nu + 63) // 64 * 64
+      self.sizes = (wo, vo, uo)
+      self.max_dims = max(l[3] + l[4] for l in self.layout)
+      self.table = torch.from_numpy(items.view(np.uint8).copy()).to(_RT["device"])
+      self.table_ptrs = ptrs
+    wo, vo, uo = self.sizes
+    wbar_all, v_all, u_all, sig_all = empty(wo), empty(vo), empty(uo), empty(len(self.plan))
+    _call("spectral_norm_batched", self.table.data_ptr(), len(self.plan), int(self.max_dims), float(eps), wbar_all.ptr,
+          v_all.ptr, sig_all.ptr, u_all.ptr)
+    for i, ((w, u, left, e), (wof, vof, uof, rows, cols, nu, nv)) in enumerate(zip(self.plan, self.layout)):
+      self.results[id(w)] = (DT(wbar_all.t[wof:wof + rows * cols].view(w.shape)), DT(v_all.t[vof:vof + nv]),
+                             DT(sig_all.t[i:i + 1]), DT(u_all.t[uof:uof + nu]))
+
+
+class sn_batch(object):
+  """`with sn_batch(state):` around one generator / discriminator call (architectures/abstract_arch.py)."""
+
+  def __init__(self, state):
+    self.state = state
+
+  def __enter__(self):
+    st = self.state
+    if st.complete and all(e == st.plan[0][3] for _, _, _, e in st.plan):
+      st.run()
+    _SN_SCOPE.append(st)
+    return st
+
+  def __exit__(self, exc_type, *a):
+    _SN_SCOPE.pop()
+    st = self.state
+    if exc_type is None and not st.complete:
+      st.complete = True              # the first call has seen every spectrally normalised weight of the network
+    leftover, st.results = st.results, {}
+    if exc_type is None and leftover:
+      raise RuntimeError("%d spectrally normalised weights were iterated by the batched launch but not used by this call: "
+                         "their u vectors advanced without a call site" % len(leftover))
 
 
 # ------------------------------------------------------------------------------------ losses / penalties

@@ -100,7 +100,9 @@ class PipelineFeeder(object):
 
 
 class TaskManager(object):
-  """Interface for managing a task (reference runner_lib.py:114-199); checkpoints are `model.ckpt-<step>.npz`."""
+  """Interface for managing a task (reference runner_lib.py:114-199); checkpoints are this package's
+  `model.ckpt-<step>.npz` or the reference's own TensorFlow checkpoints `model.ckpt-<step>.index` (+ `.data-*`), so a
+  model_dir trained by the reference can be evaluated by `continuous_eval` as is."""
 
   def __init__(self, model_dir):
     self._model_dir = model_dir
@@ -128,7 +130,8 @@ class TaskManager(object):
     last_eval = time.time()
     while True:
       ckpts = set(glob.glob(os.path.join(self.model_dir, "model.ckpt-*.npz")))
-      todo = sorted([(int(re.findall(r"ckpt-(\d+)\.npz$", c)[0]), c) for c in ckpts - evaluated])
+      ckpts |= set(glob.glob(os.path.join(self.model_dir, "model.ckpt-*.index")))
+      todo = sorted([(int(re.findall(r"ckpt-(\d+)\.(?:npz|index)$", c)[0]), c) for c in ckpts - evaluated])
       if eval_every_steps:
         todo = [(s, c) for s, c in todo if s > 0 and s % eval_every_steps == 0]
       for _, c in todo:
@@ -166,7 +169,7 @@ class TaskManagerWithCsvResults(TaskManager):
     return config
 
   def add_eval_result(self, checkpoint_path, result_dict, default_value):
-    step = re.findall(r"ckpt-(\d+)\.npz$", checkpoint_path)[0]
+    step = re.findall(r"ckpt-(\d+)\.(?:npz|index)$", checkpoint_path)[0]
     config = self._get_config_for_step(step)
     header = ["checkpoint_path", "step"] + sorted(result_dict) + sorted(config)
     write_header = not os.path.exists(self._score_file)

@@ -114,6 +114,17 @@ def _topo(roots):
 
 
 _ADD_TAKES_TENSOR = {}
+_SINKS = [None]
+
+
+def take_sink(t):
+  """During backward(..., sinks=...): the caller-provided destination for the gradient of leaf `t` (a view into a flat
+  gradient buffer), handed out ONCE — to the first vjp that produces a contribution for `t`, which then writes it there
+  instead of into fresh memory.  Later contributions are accumulated by add_fn as usual."""
+  d = _SINKS[-1]
+  if d is None or t is None:
+    return None
+  return d.pop(id(t), None)
 
 
 def grad_accumulator(fn):
@@ -122,9 +133,10 @@ def grad_accumulator(fn):
   return fn
 
 
-def backward(roots, wrt, add_fn, create_graph=False):
+def backward(roots, wrt, add_fn, create_graph=False, sinks=None):
   """roots: list of (DT, seed) with seed a DT or None (meaning d(root)/d(root)=1 for scalar-loss ops).
-  Returns the list of gradients for `wrt` (None where unreachable)."""
+  Returns the list of gradients for `wrt` (None where unreachable).  `sinks` ({id(leaf): DT}) offers destinations for
+  leaf gradients (see take_sink); a returned gradient may therefore alias its sink."""
   order = _topo([r for r, _ in roots])
   dep = set(id(w) for w in wrt)
   outs = {}                      # strong refs for the duration of this backward pass
@@ -140,7 +152,9 @@ def backward(roots, wrt, add_fn, create_graph=False):
   for r, seed in roots:
     if id(r) in dep:
       grads[id(r)] = ("seed", seed) if id(r) not in grads else grads[id(r)]
-  with record(create_graph):
+  _SINKS.append(dict(sinks) if sinks else None)
+  try:
+   with record(create_graph):
     for node in reversed(order):
       if id(node) not in outs:
         continue
@@ -164,6 +178,8 @@ def backward(roots, wrt, add_fn, create_graph=False):
           grads[id(i)] = gi
       if oid not in keep:
         del grads[oid]
+  finally:
+    _SINKS.pop()
   out = []
   for w in wrt:
     g = grads.get(id(w))

@@ -42,8 +42,10 @@ const char* cgan_last_error(cgan_ctx* ctx);
 int64_t cgan_launch_count(cgan_ctx* ctx);
 /* Tuning knobs and introspection (tests compare kernel variants bit for bit and ask which path a contraction took).
  *   CGAN_OPT_TC_MT      (set/get) max pixel tiles (conv) / work units (filter gradient) per tcgen05 CTA: 1 or 2.
+ *   CGAN_OPT_TC_HALO    (set/get) 1: 3x3 stride-1 tcgen05 convolutions fetch one (rows+2)-row activation box per kernel
+ *                       column instead of one box per tap (default); 0: one box per tap.
  *   CGAN_OPT_LAST_PATH  (get) CGAN_PATH_* taken by the most recent conv2d_fwd / dgrad / wgrad / gemm_batched call. */
-enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2 };
+enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3 };
 enum { CGAN_PATH_SIMT_FP32 = 0, CGAN_PATH_TCGEN05_TF32 = 1, CGAN_PATH_THIN_FP32 = 2 };
 int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value);
 int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value);
@@ -159,6 +161,19 @@ int cgan_bn_bwd_apply(cgan_ctx*, float* dx, const float* dy, const float* x, int
  * (:511-513,527).  u is updated in place (:516); v and sigma are outputs; wbar = w / sigma (nullable). */
 int cgan_spectral_norm(cgan_ctx*, const float* w, int rows, int cols, int left, float eps, float* u_inout, float* v_out,
                        float* sigma_out, float* wbar_out);
+/* The same for `n` weights in ONE launch (one CTA per weight; meant for the small kernels of a discriminator — resnet_cifar,
+ * SNDCGAN — where the per-weight entry point costs ~7 launches each).  `items_dev` is a device array; item i reads w / u,
+ * updates u in place and writes wbar at wbar_base + wbar_off, v at v_base + v_off, sigma at sigma_base[i] and a copy of
+ * the updated u (which the backward needs; later call sites overwrite u) at u_used_base + u_off.
+ * max_rows_plus_cols = max over items of rows + cols (shared-memory sizing). */
+typedef struct {
+  const float* w;
+  float* u;
+  int32_t rows, cols, left, reserved;
+  int64_t wbar_off, v_off, u_off;
+} cgan_sn_item;
+int cgan_spectral_norm_batched(cgan_ctx*, const cgan_sn_item* items_dev, int n, int max_rows_plus_cols, float eps,
+                               float* wbar_base, float* v_base, float* sigma_base, float* u_used_base);
 /* dw = (dwbar - <dwbar, wbar> * outer) / sigma, outer = u v^T (left) or v u^T (right); u,v constants (:521-522). */
 int cgan_spectral_norm_bwd(cgan_ctx*, float* dw, const float* dwbar, const float* wbar, int rows, int cols, int left,
                            const float* u, const float* v, const float* sigma);

@@ -70,8 +70,15 @@ def bench_convs(rows):
       t_f = timed(lambda: K.conv2d(x, w, bias, stride=stride, upsample=up))
       t_d = timed(lambda: K.conv2d_dgrad(d, dy, w))
       t_w = timed(lambda: K.conv2d_wgrad(d, x, dy))
+      # the same launches with operands flagged as already TF32-rounded by their producers (no in-kernel rounding pass)
+      x.tf32 = dy.tf32 = K.tf32_on()
+      t_fp = timed(lambda: K.conv2d(x, w, bias, stride=stride, upsample=up))
+      t_dp = timed(lambda: K.conv2d_dgrad(d, dy, w))
+      t_wp = timed(lambda: K.conv2d_wgrad(d, x, dy))
     rows.append({"kernel": label, "fwd_ms": t_f, "dgrad_ms": t_d, "wgrad_ms": t_w, "gflop": flop / 1e9,
                  "fwd_tflops": flop / t_f / 1e9, "dgrad_tflops": flop / t_d / 1e9, "wgrad_tflops": flop / t_w / 1e9,
+                 "fwd_pre_ms": t_fp, "dgrad_pre_ms": t_dp, "wgrad_pre_ms": t_wp,
+                 "fwd_pre_tflops": flop / t_fp / 1e9, "dgrad_pre_tflops": flop / t_dp / 1e9, "wgrad_pre_tflops": flop / t_wp / 1e9,
                  "fwd_hbm_gbs": bytes_io / t_f / 1e6})
     del x, w, dy
     torch.cuda.empty_cache()
@@ -99,7 +106,7 @@ def bench_memory_bound(rows):
 
   def bn_fwd_bwd():
     y = K.bn_train(xr, gr, br, 1e-5, relu_after=True)
-    tape.backward([(y, g)], [xr, gr, br], K.add)
+    tape.backward([(y, g)], [xr, gr, br], K.add_grad)
   t = timed(bn_fwd_bwd)
   rows.append({"kernel": "bn_train+relu fwd+bwd (3 + ~5 passes)", "ms": t, "algorithmic_gbs": 8 * nbytes / t / 1e6, "passes": 8})
 
@@ -115,8 +122,11 @@ def main():
   bench_memory_bound(rows)
   for r in rows:
     if "fwd_ms" in r:
-      print("%-46s %8.1f GF  fwd %7.3f ms %6.1f TF/s | dgrad %7.3f ms %6.1f TF/s | wgrad %7.3f ms %6.1f TF/s" % (
-          r["kernel"], r["gflop"], r["fwd_ms"], r["fwd_tflops"], r["dgrad_ms"], r["dgrad_tflops"], r["wgrad_ms"], r["wgrad_tflops"]))
+      print("%-46s %8.1f GF  fwd %7.3f ms %6.1f TF/s (pre-rounded %7.3f ms %6.1f) | dgrad %7.3f ms %6.1f TF/s (%7.3f ms %6.1f) | "
+            "wgrad %7.3f ms %6.1f TF/s (%7.3f ms %6.1f)" % (
+                r["kernel"], r["gflop"], r["fwd_ms"], r["fwd_tflops"], r["fwd_pre_ms"], r["fwd_pre_tflops"], r["dgrad_ms"],
+                r["dgrad_tflops"], r["dgrad_pre_ms"], r["dgrad_pre_tflops"], r["wgrad_ms"], r["wgrad_tflops"], r["wgrad_pre_ms"],
+                r["wgrad_pre_tflops"]))
     else:
       print("%-62s %7.3f ms  %7.0f GB/s algorithmic" % (r["kernel"], r["ms"], r["algorithmic_gbs"]))
   print(json.dumps(rows))

@@ -73,10 +73,10 @@ class EmulatedLib(object):
     return self.launches
 
   def get_option(self, key):
-    return {1: 2, 2: self.last_path}[key]
+    return {1: 2, 2: self.last_path, 3: 1}[key]
 
   def set_option(self, key, value):
-    assert key == 1 and value in (1, 2)
+    assert (key == 1 and value in (1, 2)) or (key == 3 and value in (0, 1))
 
   def call(self, name, *args):
     self.launches += 1
@@ -88,7 +88,7 @@ class EmulatedLib(object):
     self.math_mode = mode
 
   def cgan_ctx_set_option(self, key, value):
-    assert key == 1 and value in (1, 2)
+    self.set_option(key, value)
 
   def cgan_ctx_get_option(self, key, out):
     out._obj.value = self.get_option(key)
@@ -355,6 +355,19 @@ class EmulatedLib(object):
     f32(sigma_out, 1)[0] = sigma
     if wbar_out is not None:
       f32(wbar_out, rows * cols)[:] = (W / sigma).ravel()
+
+  def cgan_spectral_norm_batched(self, items, n, max_dims, eps, wbar_base, v_base, sigma_base, u_used_base):
+    raw = np.ctypeslib.as_array((ctypes.c_uint8 * (56 * n)).from_address(int(items)))
+    rec = raw.view(np.dtype([("w", "<u8"), ("u", "<u8"), ("rows", "<i4"), ("cols", "<i4"), ("left", "<i4"), ("reserved", "<i4"),
+                             ("wbar_off", "<i8"), ("v_off", "<i8"), ("u_off", "<i8")]))
+    for i in range(n):
+      r = rec[i]
+      rows, cols, left = int(r["rows"]), int(r["cols"]), int(r["left"])
+      assert rows + cols <= max_dims
+      nu = rows if left else cols
+      self.cgan_spectral_norm(int(r["w"]), rows, cols, left, eps, int(r["u"]), v_base + 4 * int(r["v_off"]),
+                              sigma_base + 4 * i, wbar_base + 4 * int(r["wbar_off"]))
+      f32(u_used_base + 4 * int(r["u_off"]), nu)[:] = f32(int(r["u"]), nu)
 
   def cgan_spectral_norm_bwd(self, dw, dwbar, wbar, rows, cols, left, u, v, sigma):
     g = f32(dwbar, rows * cols).reshape(rows, cols).astype(np.float64)

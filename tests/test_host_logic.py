@@ -140,8 +140,9 @@ def test_reference_arm_prints_contract_line():
   import subprocess
   import sys
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, CGAN_REF_BATCH="4", CGAN_REF_SKIP_EVAL="1")      # the contract, not the number: a tiny sample
   out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=root)
+                       capture_output=True, text=True, timeout=900, cwd=root, env=env)
   assert out.returncode == 0, out.stderr[-2000:]
   line = json.loads(out.stdout.strip().splitlines()[-1])
   for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
