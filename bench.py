@@ -442,12 +442,15 @@ def cpu_baseline_leg(args, sample_cycles=2, batch=None):
   import torch
   from oracle import gan as ogan, nets as onets
   batch = batch or int(os.environ.get("CGAN_REF_BATCH", "64"))       # (tests shrink the sample; the bench never sets this)
-  cores = os.cpu_count() or 1
-  try:
-    cores = len(os.sched_getaffinity(0))
-  except Exception:
-    pass
-  torch.set_num_threads(max(1, cores))
+  # torch's own default is one thread per physical core; torchrun exports OMP_NUM_THREADS=1, which leaves the CPU arm on
+  # ONE thread — undo that (logical-CPU counts oversubscribe MKL badly: 128 threads on a 64-core host ran 20x slower)
+  if torch.get_num_threads() <= 1:
+    logical = os.cpu_count() or 2
+    try:
+      logical = len(os.sched_getaffinity(0))
+    except Exception:
+      pass
+    torch.set_num_threads(max(1, logical // 2))
   cfg = onets.Cfg(architecture="resnet_cifar_arch", image_shape=(32, 32, 3), g_bn="batch_norm", d_sn=True, g_sn=False,
                   bn_decay=0.9, bn_eps=1e-5)
   k = 5

@@ -18,8 +18,12 @@ struct cgan_ctx {
   int tc_mt_max;       // tcgen05 kernels: max tiles per CTA sharing one operand tile (CGAN_OPT_TC_MT / env CGAN_TC_MT, default 2)
   int tc_halo;         // 3x3 stride-1 tcgen05 convolutions use the halo variant (CGAN_OPT_TC_HALO / env CGAN_TC_HALO, default 1)
   int last_path;       // CGAN_PATH_* of the most recent contraction (cgan_ctx_get_option(CGAN_OPT_LAST_PATH))
+  unsigned* counters;  // CGAN_NUM_COUNTERS zero-initialised tickets for single-launch two-stage reductions (norm.cu)
+  void* p2p;           // peer-memory all-reduce state (p2p.cu), null until cgan_p2p_local_handle
   char err[512];
 };
+
+constexpr int CGAN_NUM_COUNTERS = 1 << 18;
 
 static inline int cgan_fail(cgan_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "") {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
@@ -100,6 +104,9 @@ struct TcExtra {
   const float* residual;    // + residual (output geometry), before the activation
   const float* mask;        // (leaky-)ReLU backward fused into the epilogue: out = mask > 0 ? v : mask_leak * v
   float mask_leak;
+  int nphases;              // > 1: several sub-pixel phases in one launch (tap list = concatenation, see cgan_conv_tc)
+  int ph_tap0[5];
+  long long ph_base[4];
 };
 
 // internal (C++ linkage) entry points shared between translation units

@@ -14,7 +14,8 @@ int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld
                             float mask_leak, int relu, int round_out);
 bool cgan_fwd_thin_ok(const cgan_conv_desc* d);
 int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int relu,
-                  int ldy);
+                  int ldy, int round_out);
+bool cgan_fwd_thin3_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw, int x_tf32, int dy_tf32);
@@ -120,13 +121,14 @@ int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, c
     // conv over the zero-inserted 2x upsampled input (resnet_ops.py:35-56, 122-130) as four sub-pixel phases: output
     // pixel (2i+a, 2j+b) only sees the taps whose virtual input coordinate 2i+a+kh-pad is even -> real pixel i+dh.
     // The weights are prepared once for the four launches.
-    float* wprep = nullptr;
-    int rc = cgan_tc_prep_weights(ctx, w, d->kh * d->kw, 1, d->cout, d->cin, &wprep);
-    if (rc) return rc;
-    ex.wprep = wprep;
+    // One launch (grid.z = phase), one weight preparation.
+    int nt = 0;
+    ex.nphases = 4;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
-        int nt = 0;
+        const int ph = a * 2 + b;
+        ex.ph_tap0[ph] = nt;
+        ex.ph_base[ph] = ((long long)a * d->ow + b) * d->cout;
         for (int kh = 0; kh < d->kh; ++kh) {
           int vh = a + kh - d->pad_t;
           if (vh & 1) continue;
@@ -137,15 +139,12 @@ int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, c
             wt[nt] = kh * d->kw + kw; ++nt;
           }
         }
-        long long base = ((long long)a * d->ow + b) * d->cout;
-        if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
-        rc = cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
-                          d->h, d->w, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
-                          (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, base, relu, nullptr, 0,
-                          &ex);
-        if (rc) return rc;
+        if (nt == ex.ph_tap0[ph]) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty sub-pixel phase%s", "cgan_conv2d_fwd");
       }
-    return CGAN_OK;
+    ex.ph_tap0[4] = nt;
+    return cgan_conv_tc(ctx, x, 1, &zero, d->cin, (long long)d->w * d->cin, (long long)d->h * d->w * d->cin, d->n,
+                        d->h, d->w, d->h, d->w, d->cin, w, d->kh * d->kw, 1, d->cout, nt, oh, ow, wt, nullptr, bias, y,
+                        (long long)d->oh * d->ow * d->cout, 2ll * d->ow * d->cout, 2ll * d->cout, 0, relu, nullptr, 0, &ex);
   }
   // stride 2 (SNDCGAN D, sndcgan.py:109-121): the input is read through its four (row, column) parity phases, each a
   // strided TMA view of the output's spatial size; tap (kh,kw) lands in phase ((kh-pad_t)&1, (kw-pad_l)&1).
@@ -171,11 +170,13 @@ int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, c
                         bias, y, (long long)d->oh * d->ow * ldy, (long long)d->ow * ldy, ldy, 0, relu, hw, 0, &ex);
   }
   // exact-fp32 paths: residual / mask / rounding are applied by one extra pointwise pass
-  const bool post = ep && (ep->residual || ep->mask || (ep->flags & CGAN_CONV_ROUND_OUT));
+  bool post = ep && (ep->residual || ep->mask || (ep->flags & CGAN_CONV_ROUND_OUT));
   int rc;
   if (cgan_fwd_thin_ok(d)) {
     ctx->last_path = CGAN_PATH_THIN_FP32;
-    rc = cgan_fwd_thin(ctx, d, x, w, bias, y, post ? 0 : relu, ldy);
+    const bool fused = post && !ep->residual && !ep->mask && cgan_fwd_thin3_ok(d);   // ReLU + rounding in the 3x3 kernel itself
+    if (fused) post = false;
+    rc = cgan_fwd_thin(ctx, d, x, w, bias, y, post ? 0 : relu, ldy, fused ? 1 : 0);
   } else {
     ctx->last_path = CGAN_PATH_SIMT_FP32;
     rc = cgan_conv2d_fwd_simt(ctx, d, x, w, bias, y, post ? 0 : relu, ldy);
@@ -241,14 +242,14 @@ int cgan_conv2d_dgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy
       d->oh == d->h / 2 && d->ow == d->w / 2 && d->kh >= 2 && d->kw >= 2 &&
       cgan_tc_shape_ok(d->n, d->oh, d->ow, d->cout, d->cin) && ptr_ok && d->cin % 4 == 0) {
     const long long zero = 0;
-    float* wprep = nullptr;
-    int rc = cgan_tc_prep_weights(ctx, w, d->kh * d->kw, 0, d->cin, d->cout, &wprep);
-    if (rc) return rc;
-    ex.wprep = wprep;
     ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+    int oh[32], ow[32], wt[32], nt = 0;
+    ex.nphases = 4;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
-        int oh[16], ow[16], wt[16], nt = 0;
+        const int ph = a * 2 + b;
+        ex.ph_tap0[ph] = nt;
+        ex.ph_base[ph] = ((long long)a * d->w + b) * d->cin;
         for (int kh = 0; kh < d->kh; ++kh) {
           int th = a + d->pad_t - kh;
           if (th & 1) continue;
@@ -258,15 +259,12 @@ int cgan_conv2d_dgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy
             oh[nt] = th / 2; ow[nt] = tw / 2; wt[nt] = kh * d->kw + kw; ++nt;
           }
         }
-        if (nt == 0) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty phase%s", "cgan_conv2d_dgrad");
-        rc = cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
-                          d->n, d->oh, d->ow, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr,
-                          bias,
-                          dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin,
-                          ((long long)a * d->w + b) * d->cin, relu, nullptr, 0, &ex);
-        if (rc) return rc;
+        if (nt == ex.ph_tap0[ph]) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: empty phase%s", "cgan_conv2d_dgrad");
       }
-    return CGAN_OK;
+    ex.ph_tap0[4] = nt;
+    return cgan_conv_tc(ctx, dy, 1, &zero, d->cout, (long long)d->ow * d->cout, (long long)d->oh * d->ow * d->cout,
+                        d->n, d->oh, d->ow, d->oh, d->ow, d->cout, w, d->kh * d->kw, 0, d->cin, nt, oh, ow, wt, nullptr,
+                        bias, dx, (long long)d->h * d->w * d->cin, 2ll * d->w * d->cin, 2ll * d->cin, 0, relu, nullptr, 0, &ex);
   }
   ctx->last_path = CGAN_PATH_SIMT_FP32;
   int rc = cgan_conv2d_dgrad_simt(ctx, d, dy, w, dx);

@@ -59,6 +59,11 @@ struct TcParams {
   // halo mode (conv_tc_halo_kernel): the taps come in `hg` groups of `hnv` vertically consecutive taps that share their
   // horizontal offset; one TMA box of bh + hnv - 1 rows serves all taps of a group (the vertical shift is a descriptor
   // offset of bw rows), so the activation operand crosses L2 -> smem `hg` times per channel chunk instead of hg * hnv
+  // sub-pixel phases merged into one launch (blockIdx.z): phase ph owns the taps [ph_tap0[ph], ph_tap0[ph+1]) and writes
+  // at element offset ph_base[ph] (a convolution over a zero-inserted input, a stride-2 input gradient)
+  int nphases;
+  int ph_tap0[5];
+  long long ph_base[4];
   int hg, hnv;
   int h_off_w[4], h_off_h0[4], h_wtap[4][4];
   int a_halo_bytes;                 // smem footprint of one tile's halo box (1024-aligned)
@@ -93,7 +98,7 @@ __device__ __forceinline__ void tc_tile_origin(const TcParams& p, int t, int& ow
 // Epilogue of warps 2..9: tcgen05.ld the accumulators of this CTA's tiles, apply bias / residual / ReLU / mask / TF32
 // rounding, store.  TMEM lane quarter is fixed by (warp id % 4); row of the tile = TMEM lane.
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int tile0, int nt_here, int nb0, int warp,
-                                            int lane) {
+                                            int lane, long long out_base) {
   const int quarter = warp & 3;
   const int m = quarter * 32 + lane;
   const int wi = m % p.bw;
@@ -104,7 +109,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     tc_tile_origin(p, tile0 + tl, ow0, oh0, n0);
     // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
     const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
-    float* orow = p.out + p.base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
+    float* orow = p.out + out_base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
                   (long long)(ow0 + wi) * p.s_w + nb0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * p.bn);
     // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
@@ -171,7 +176,8 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = p.ntaps * p.kchunks;
+  const int tap0 = p.ph_tap0[blockIdx.z];
+  const int num_kb = (p.ph_tap0[blockIdx.z + 1] - tap0) * p.kchunks;
 
   // this CTA's pixel tiles: [tile0, tile0 + nt_here).  They all multiply the same weight tile, which is therefore
   // fetched from L2 once per k-block for mt*128 pixels: the kernel is bound by L2->SM bytes per MMA, not by HBM.
@@ -210,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+        const int tl = kb / p.kchunks, kc = kb - tl * p.kchunks, tap = tap0 + tl;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
@@ -279,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane);
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.ph_base[blockIdx.z]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -428,7 +434,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane);
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.base);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -533,6 +539,8 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                  int ncols, int ntaps, const int* off_h, const int* off_w, const int* wtap, const int* amap,
                  const float* bias, float* out, long long s_n, long long s_h, long long s_w, long long base, int relu,
                  const int* view_phase_of, int wimg_stride, const TcExtra* ex) {
+  // ex->nphases > 1: the `ntaps` taps are the concatenation of the tap lists of nphases sub-pixel phases
+  // (ex->ph_tap0[0..nphases]), phase ph writing at element offset ex->ph_base[ph] instead of `base`; one launch, grid.z
   // wimg_stride != 0: batched GEMM — image i multiplies weight slice wtap + i*wimg_stride (needs one image per tile)
   // view_phase_of: {H, W} of the tensor whose four stride-2 parity phases the views are (nullptr: all views h x w)
   EncodeTiledFn enc = get_encode();
@@ -557,6 +565,15 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   if (ex) {
     p.round_out = ex->round_out; p.residual = ex->residual; p.mask = ex->mask; p.mask_leak = ex->mask_leak;
   }
+  p.nphases = 1;
+  p.ph_tap0[0] = 0; p.ph_tap0[1] = ntaps;
+  p.ph_base[0] = base;
+  if (ex && ex->nphases > 1) {
+    if (ex->nphases > 4) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: more than four phases%s", "cgan_conv_tc");
+    p.nphases = ex->nphases;
+    for (int i = 0; i <= ex->nphases; ++i) p.ph_tap0[i] = ex->ph_tap0[i];
+    for (int i = 0; i < ex->nphases; ++i) p.ph_base[i] = ex->ph_base[i];
+  }
   p.wimg_stride = wimg_stride;
   if (wimg_stride != 0 && p.bni != 1)
     return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: batched GEMM needs >= 128 rows per matrix%s", "cgan_conv_tc");
@@ -574,7 +591,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   }
 
   // ---- halo variant: three taps of a kernel column share one (bh+2)-row activation box --------------------------------
-  if (ctx->tc_halo && nviews == 1 && wimg_stride == 0 && ntaps == 9 && gh == h && gw == w && !view_phase_of) {
+  if (ctx->tc_halo && p.nphases == 1 && nviews == 1 && wimg_stride == 0 && ntaps == 9 && gh == h && gw == w && !view_phase_of) {
     int hbw = 0, hbh = 0;
     if (w % 32 == 0) { hbw = 32; hbh = 4; } else if (w == 16) { hbw = 16; hbh = 8; }
     // group the taps by horizontal offset; each group must be three vertically consecutive taps
@@ -694,7 +711,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   const int ncol_tiles = ncols_pad / p.bn;
   p.tiles_total = (int)tiles_total;
   p.mt = 1;
-  if (ctx->tc_mt_max >= 2 && tiles_total * ncol_tiles >= 4ll * ctx->num_sms &&
+  if (ctx->tc_mt_max >= 2 && tiles_total * ncol_tiles * p.nphases >= 4ll * ctx->num_sms &&
       (wimg_stride == 0 || (p.tiles_w * p.tiles_h) % 2 == 0))
     p.mt = 2;
   const bool two_ctas = p.mt * p.bn <= 256;
@@ -710,7 +727,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
     CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((tiles_total + p.mt - 1) / p.mt), (unsigned)ncol_tiles);
+  dim3 grid((unsigned)((tiles_total + p.mt - 1) / p.mt), (unsigned)ncol_tiles, (unsigned)p.nphases);
   conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tm_as, tm_b, p);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;

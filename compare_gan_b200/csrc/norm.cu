@@ -47,11 +47,16 @@ struct BnBwdF {         // v0 = sum dy*xhat, v1 = sum dy
   }
 };
 
-// partial[((g*chunks + chunk)*NV + v)*C + c]
+// partial[((g*chunks + chunk)*NV + v)*C + c].  With `counters` the LAST chunk-block of each (column block, group) to finish
+// also does the second stage — the fixed-order sum over the chunk partials that colreduce_final_kernel otherwise does in a
+// launch of its own (same order, same result): every block publishes its partials (threadfence), takes a ticket, and the
+// holder of ticket chunks-1 reads them all back.  The counter is reset by that block, so launches (and graph replays)
+// always start from zero.
 template <class F, int NV>
 __global__ void colreduce_kernel(F f, float* __restrict__ partial, long long rows_per_group, int C,
-                                 long long rows_per_chunk, int chunks) {
+                                 long long rows_per_chunk, int chunks, unsigned* counters, float scale, float* out0, float* out1) {
   __shared__ float sh[NV][CR_Y][CR_X + 1];
+  __shared__ unsigned s_ticket;
   const int c = blockIdx.x * CR_X + threadIdx.x;
   const int chunk = blockIdx.y, g = blockIdx.z;
   float acc[NV];
@@ -80,6 +85,33 @@ __global__ void colreduce_kernel(F f, float* __restrict__ partial, long long row
       partial[(((long long)g * chunks + chunk) * NV + v) * C + c] = s;
     }
   }
+  if (!counters) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(&counters[(size_t)g * gridDim.x + blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(chunks - 1)) return;
+  __threadfence();
+  float* outs[2] = {out0, out1};
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float s = 0.f;
+    if (c < C && outs[v])
+      for (int k = threadIdx.y; k < chunks; k += CR_Y) s += __ldcg(&partial[(((long long)g * chunks + k) * NV + v) * C + c]);
+    sh[v][threadIdx.y][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!outs[v]) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < CR_Y; ++y) s += sh[v][y][threadIdx.x];
+      outs[v][(long long)g * C + c] = s * scale;
+    }
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) counters[(size_t)g * gridDim.x + blockIdx.x] = 0u;
 }
 
 // out_v[g*C + c] = scale * sum_chunk partial.  Block = 32 columns x 8 chunk lanes: the (up to ~150) partials of a column
@@ -131,7 +163,13 @@ int colreduce(cgan_ctx* ctx, F f, int groups, long long rows_per_group, int C, f
   if (rc) return rc;
   float* partial = reinterpret_cast<float*>(ws);
   dim3 grid(cblocks, (unsigned)chunks, groups), block(CR_X, CR_Y);
-  colreduce_kernel<F, NV><<<grid, block, 0, ctx->stream>>>(f, partial, rows_per_group, C, rpc, (int)chunks);
+  if (ctx->counters && (long long)cblocks * groups <= CGAN_NUM_COUNTERS) {     // one launch: the last block per column block finishes
+    colreduce_kernel<F, NV><<<grid, block, 0, ctx->stream>>>(f, partial, rows_per_group, C, rpc, (int)chunks, ctx->counters, scale,
+                                                             out0, out1);
+    CGAN_LAUNCHED(ctx);
+    return CGAN_OK;
+  }
+  colreduce_kernel<F, NV><<<grid, block, 0, ctx->stream>>>(f, partial, rows_per_group, C, rpc, (int)chunks, nullptr, scale, out0, out1);
   CGAN_LAUNCHED(ctx);
   long long tot = (long long)groups * C;
   colreduce_final_kernel<NV><<<cdiv(tot, 32), dim3(32, 8), 0, ctx->stream>>>(partial, groups, (int)chunks, C, scale, out0, out1);

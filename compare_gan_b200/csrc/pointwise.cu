@@ -29,6 +29,11 @@ int cgan_ctx_create(cgan_ctx** out, int device) {
   c->tc_halo = 1;
   if (const char* e = getenv("CGAN_TC_HALO")) c->tc_halo = atoi(e) ? 1 : 0;
   c->stream = 0;
+  if (cudaMalloc(reinterpret_cast<void**>(&c->counters), CGAN_NUM_COUNTERS * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(c->counters, 0, CGAN_NUM_COUNTERS * sizeof(unsigned)) != cudaSuccess) {
+    c->counters = nullptr;          // reductions fall back to their two-launch form
+    cudaGetLastError();
+  }
   *out = c;
   return CGAN_OK;
 }
@@ -36,6 +41,7 @@ int cgan_ctx_create(cgan_ctx** out, int device) {
 int cgan_ctx_destroy(cgan_ctx* ctx) {
   if (!ctx) return CGAN_ERR_ARG;
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->counters) cudaFree(ctx->counters);
   delete ctx;
   return CGAN_OK;
 }

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .tape import DT, attach, no_record, recording
-from .tape import grad_accumulator as _grad_accumulator, take_sink as _take_sink
+from .tape import grad_accumulator as _grad_accumulator, take_sink as _take_sink, sole_consumer as _sole_consumer
 
 _RT = {"lib": None, "device": None, "math_mode": 0}
 
@@ -52,6 +52,17 @@ def _trace(kind, key, a_pre=False, b_pre=False, b_is_weight=True):
     prev = CONV_TRACE.setdefault((kind,) + tuple(key), rec)
     if prev != rec:
       raise AssertionError("contraction %s %s ran as %s and as %s" % (kind, key, prev, rec))
+
+
+def _fusable_relu(x):
+  """(ref, leak) when the gradient w.r.t. `x` can take the (leaky-)ReLU mask of x's producer in the epilogue of the
+  contraction that computes it: x is a ReLU output and this contraction is its only consumer in the running backward."""
+  r = getattr(x, "relu_of", None)
+  return r if (r is not None and _sole_consumer(x)) else None
+
+
+def _premasked(g, y_id):
+  return getattr(g, "premasked_for", None) == y_id
 
 
 def _desc_key(d):
@@ -336,27 +347,35 @@ def conv2d(x, w, bias=None, stride=1, upsample=False, padding="SAME", relu=False
     for fn in RELU_OBSERVERS:
       fn(y.t > 0)
   yv = DT(y.t) if relu else None        # y > 0  <=>  pre-activation > 0
+  if relu:
+    y.relu_of = (yv, 0.0)
+  y_id = id(y)
 
   def vjp(g, needs):
-    if relu:
+    if relu and not _premasked(g, y_id):
       g = act_bwd(g, yv, ACT_RELU, round_tf32=True)
-    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
+    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x), relu_mask=_fusable_relu(x), mask_for=x) if needs[0] else None,
             conv2d_wgrad(d, x, g, leaf=w) if needs[1] else None,
             colsum(reshape(g, -1, cout), leaf=bias) if (bias is not None and needs[2]) else None,
             g if (residual is not None and needs[3]) else None]
   return attach("conv2d", y, [x, w, bias, residual], vjp)
 
 
-def conv2d_dgrad(d, dy, w, bias=None, round_out=False):
-  """Input gradient of conv2d == tf.nn.conv2d_transpose (+ bias, arch_ops.py:588-592)."""
+def conv2d_dgrad(d, dy, w, bias=None, round_out=False, relu_mask=None, mask_for=None):
+  """Input gradient of conv2d == tf.nn.conv2d_transpose (+ bias, arch_ops.py:588-592).  `relu_mask` = (ref, leak): the
+  result is the gradient w.r.t. a (leaky-)ReLU output `mask_for`; that ReLU's backward (g * [ref > 0 ? 1 : leak]) is applied
+  in this kernel's epilogue and the result is tagged so the ReLU's own vjp passes it through."""
   dx = empty(d.n, d.h, d.w, d.cin)
   rnd = bool(round_out) and tf32_on()
-  ep = _epilogue(bias, round_out=rnd, in_tf32=dy.tf32 and tf32_on())
+  mref, mleak = relu_mask if relu_mask is not None else (None, 0.0)
+  ep = _epilogue(bias, mask=mref, mask_leak=mleak, round_out=rnd, in_tf32=dy.tf32 and tf32_on())
   _call("conv2d_dgrad_ex", ctypes.byref(d), dy.ptr, w.ptr, ctypes.byref(ep), dx.ptr)
   _trace("dgrad", _desc_key(d), dy.tf32)
   dx.tf32 = rnd
+  if mref is not None:
+    dx.premasked_for = id(mask_for)
   if CONV_CHECK is not None:
-    CONV_CHECK("dgrad", d=d, dy=dy, w=w, bias=bias, round_out=rnd, out=dx)
+    CONV_CHECK("dgrad", d=d, dy=dy, w=w, bias=bias, round_out=rnd, mask=mref, mask_leak=mleak, out=dx)
   cin = d.cin
 
   def vjp(g, needs):   # linear in dy and in w
@@ -370,7 +389,7 @@ def _taped_fwd(d, x, w, round_out=False):
   y = _conv_fwd_raw(d, x, w, None, round_out=round_out)
 
   def vjp(g, needs):
-    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x)) if needs[0] else None,
+    return [conv2d_dgrad(d, g, w, round_out=_grad_feeds_tc(x), relu_mask=_fusable_relu(x), mask_for=x) if needs[0] else None,
             conv2d_wgrad(d, x, g, leaf=w) if needs[1] else None]
   return attach("conv2d", y, [x, w], vjp)
 
@@ -486,7 +505,15 @@ def act(x, kind, leak=0.0, round_tf32=False):
   # a closure must never hold its own output DT (that would be a DT -> node -> closure -> DT reference cycle and delay
   # freeing the stash until a cyclic GC pass): wrap the storage in a fresh, tape-less DT instead
   ref = x if kind in (ACT_RELU, ACT_LRELU) else DT(y.t)
-  return attach("act%d" % kind, y, [x], lambda g, needs: [act_bwd(g, ref, kind, leak, round_tf32=_grad_feeds_tc(x))])
+  if kind in (ACT_RELU, ACT_LRELU):
+    y.relu_of = (DT(x.t), float(leak) if kind == ACT_LRELU else 0.0)
+  y_id = id(y)
+
+  def vjp(g, needs):
+    if _premasked(g, y_id):
+      return [g]                      # the producing contraction applied this activation's mask in its epilogue
+    return [act_bwd(g, ref, kind, leak, round_tf32=_grad_feeds_tc(x))]
+  return attach("act%d" % kind, y, [x], vjp)
 
 
 def act_bwd(g, ref, kind, leak=0.0, round_tf32=False):
@@ -729,13 +756,16 @@ def bn_train(x, gamma, beta, eps, state=None, decay=0.999, cond=False, relu_afte
   y.tf32 = rnd
 
   yv = DT(y.t) if relu_after else None
+  if relu_after:
+    y.relu_of = (yv, 0.0)
+  y_id = id(y)
   if relu_after and RELU_OBSERVERS:
     for fn in RELU_OBSERVERS:
       fn(y.t > 0)
 
   def vjp(g, needs):
     _no_second_order("bn_train")
-    if relu_after:
+    if relu_after and not _premasked(g, y_id):
       g = act_bwd(g, yv, ACT_RELU)    # y>0 <=> pre-activation>0
     sums = empty(2 * c)
     dgamma = dbeta = None

@@ -16,7 +16,7 @@ import torch
 
 class DT(object):
   """Device tensor: float32 (or int32 labels), C-contiguous; 4-D tensors are NHWC."""
-  __slots__ = ("t", "node", "req", "tf32", "__weakref__")
+  __slots__ = ("t", "node", "req", "tf32", "relu_of", "premasked_for", "__weakref__")
 
   def __init__(self, t, req=False):
     assert t.is_contiguous()
@@ -26,6 +26,11 @@ class DT(object):
     # True when a kernel stored this tensor rounded to the nearest TF32 value (math_mode 1): tensor-core contractions
     # that read it skip their operand-rounding pass (include/cgan_b200.h, CGAN_CONV_IN_TF32)
     self.tf32 = False
+    # fusion of a (leaky-)ReLU backward into the epilogue of the contraction that produces its incoming gradient:
+    # relu_of = (ref, leak) marks this tensor as the output of a (leaky-)ReLU whose gradient mask is sign(ref);
+    # premasked_for = id(tensor) marks a gradient that already carries that tensor's mask (kernels.conv2d_dgrad)
+    self.relu_of = None
+    self.premasked_for = None
 
   @property
   def shape(self):
@@ -115,6 +120,13 @@ def _topo(roots):
 
 _ADD_TAKES_TENSOR = {}
 _SINKS = [None]
+_CONSUMERS = [None]
+
+
+def sole_consumer(t):
+  """True while a backward pass runs and exactly one differentiated op consumed `t` (its gradient has one contribution)."""
+  d = _CONSUMERS[-1]
+  return d is not None and d.get(id(t), 0) == 1
 
 
 def take_sink(t):
@@ -153,6 +165,13 @@ def backward(roots, wrt, add_fn, create_graph=False, sinks=None):
     if id(r) in dep:
       grads[id(r)] = ("seed", seed) if id(r) not in grads else grads[id(r)]
   _SINKS.append(dict(sinks) if sinks else None)
+  ncons = {}
+  for node in order:
+    if id(node) in outs and id(outs[id(node)]) in dep:
+      for i in node.inputs:
+        if i is not None and id(i) in dep:
+          ncons[id(i)] = ncons.get(id(i), 0) + 1
+  _CONSUMERS.append(None if create_graph else ncons)
   try:
    with record(create_graph):
     for node in reversed(order):
@@ -180,6 +199,7 @@ def backward(roots, wrt, add_fn, create_graph=False, sinks=None):
         del grads[oid]
   finally:
     _SINKS.pop()
+    _CONSUMERS.pop()
   out = []
   for w in wrt:
     g = grads.get(id(w))

@@ -21,10 +21,59 @@ def num_replicas():
   return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
+_P2P = {"state": None, "max": 0}       # None: not tried yet; True: peer buffers connected; False: unavailable (NCCL only)
+
+
+def _p2p_ready():
+  """Connects the NVLink peer buffers of the ranks once (include/cgan_b200.h, cgan_p2p_*): each rank publishes a cudaIpc
+  handle, the handles are all-gathered over the process group.  Any failure leaves the NCCL path in charge."""
+  import ctypes
+  import os
+  if _P2P["state"] is None:
+    _P2P["state"] = False
+    if os.environ.get("CGAN_P2P", "1") != "0" and dist.get_backend() == "nccl" and K._RT["lib"] is not None \
+        and not getattr(K._RT["lib"], "emulated", False):
+      # every rank goes through the same sequence of collectives whatever fails locally, so no rank is left waiting
+      lib = K._RT["lib"]
+      world, rank = dist.get_world_size(), dist.get_rank()
+      handle, ok, why = (ctypes.c_ubyte * 64)(), 1.0, ""
+      try:
+        lib.call("p2p_local_handle", world, handle)
+      except Exception as e:
+        ok, why = 0.0, str(e)[:200]
+      mine = torch.tensor(list(handle), dtype=torch.uint8, device=K._RT["device"])
+      parts = [torch.zeros_like(mine) for _ in range(world)]
+      dist.all_gather(parts, mine)
+      flag = torch.tensor([ok], device=K._RT["device"])
+      dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+      if flag.item() > 0:
+        try:
+          blob = b"".join(p.cpu().numpy().tobytes() for p in parts)
+          buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+          lib.call("p2p_connect", rank, world, buf)
+        except Exception as e:      # no peer access (different nodes, MIG, ...)
+          ok, why = 0.0, str(e)[:200]
+        flag = torch.tensor([ok], device=K._RT["device"])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks or none
+      if flag.item() > 0:
+        _P2P["max"] = int(lib.fn["cgan_p2p_max_floats"]())
+        _P2P["state"] = True
+      elif why:
+        import logging
+        logging.warning("peer-memory all-reduce unavailable (%s); NCCL carries the BN moments too", why)
+  return _P2P["state"]
+
+
 def cross_replica_sum_(x):
-  """In-place all-reduce(sum) of a device tensor (tf.contrib.tpu.cross_replica_sum, tpu_ops.py:70,90)."""
+  """In-place all-reduce(sum) of a device tensor (tf.contrib.tpu.cross_replica_sum, tpu_ops.py:70,90).  Small float32
+  vectors (the [2C] batch-norm exchanges) go through the one-kernel NVLink peer-memory all-reduce, everything else
+  (the flat gradient buffers) through NCCL."""
   if num_replicas() > 1:
-    dist.all_reduce(x.t, op=dist.ReduceOp.SUM)
+    t = x.t
+    if t.is_cuda and t.dtype == torch.float32 and _p2p_ready() and t.numel() <= _P2P["max"]:
+      K._call("allreduce_small", x.ptr, t.numel())
+    else:
+      dist.all_reduce(t, op=dist.ReduceOp.SUM)
   return x
 
 

@@ -235,6 +235,18 @@ int cgan_cov_accumulate(cgan_ctx*, const float* act, int n, int d, double* sum, 
  * when `inception_scale` (eval_utils.py:157-175). */
 int cgan_resize_bilinear(cgan_ctx*, float* y, const float* x, int n, int h, int w, int c, int oh, int ow, int inception_scale);
 
+/* ---- cross-replica exchange of small vectors (tpu/tpu_ops.py:75-125: cross_replica_mean / cross_replica_moments) ---- */
+/* One process per GPU on one node.  Every rank allocates a communication buffer and publishes its cudaIpc handle
+ * (cgan_p2p_local_handle -> 64 bytes), the host code all-gathers the handles (torch.distributed) and hands all of them
+ * to cgan_p2p_connect, which maps the peers' buffers.  cgan_allreduce_small then sums x[0..n) over the ranks IN PLACE
+ * with one kernel launch over NVLink peer memory (n <= cgan_p2p_max_floats()): every rank stores its vector into every
+ * peer's buffer, flags it, waits for the others' flags and adds the vectors in rank order — bit-identical results on all
+ * ranks, capturable into a CUDA graph.  Gradients (MBs) stay on NCCL (gans/modular_gan.py:606-616). */
+int cgan_p2p_max_floats(void);
+int cgan_p2p_local_handle(cgan_ctx*, int world, void* host_handle64);
+int cgan_p2p_connect(cgan_ctx*, int rank, int world, const void* host_handles);
+int cgan_allreduce_small(cgan_ctx*, float* x, int n);
+
 /* ---- input pipeline (ImageDatasetV2.train_input_fn, datasets.py:261-291; host side, no GPU work) ---- */
 /* The tf.data chain of the reference: repeat() -> shuffle(buffer, seed) -> batch(drop_remainder=True) -> prefetch, with
  * _parse_fn's uint8 -> float32 / 255 (datasets.py:225-227), run by a producer thread into a ring of `ring` batch buffers

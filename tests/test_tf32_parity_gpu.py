@@ -202,6 +202,8 @@ class _InSitu(object):
           ref = ref[:, ::2, ::2, :]
         if kw["bias"] is not None:
           ref = ref + t(kw["bias"])
+        if kw.get("mask") is not None:
+          ref = torch.where(t(kw["mask"]) > 0, ref, float(kw["mask_leak"]) * ref)
         if kw["round_out"]:
           ref = T.rna_tf32(ref)
       else:
