@@ -295,6 +295,159 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------------
+// The per-tap kernel above is bound by the shared-memory pipe of the SM: per k-block and CTA the TMA engine writes
+// mt*16 KB + bn*128 B while the tensor core reads every operand byte again (the weight tile once per pixel tile) —
+// ~160 B/clk against 128 B/clk at bn = 256, ~220 B/clk at bn = 128.  Here two CTAs of a cluster (the two SMs of a TPC)
+// share every weight tile: each CTA loads and holds HALF of its rows, one tcgen05.mma.cta_group::2 of M = 256 multiplies
+// the pixel tiles of both CTAs with the whole tile, so both the TMA fill and the UMMA reads of the weight operand halve
+// per SM.  Protocol (see tc_common.cuh): both CTAs run a TMA producer whose loads complete on the LEADER's `full`
+// barrier (count 2: the leader's expect_tx arrive for the bytes of both CTAs + the peer's remote arrive), the leader's
+// MMA warp issues for both and commits `empty` / `tmem_full` with a multicast arrive to both CTAs, each CTA's epilogue
+// warps drain their own TMEM half.  Operands that still need rounding are rounded by each CTA's warps 2..9 in its own
+// shared memory; they arrive on the leader's `ready` barrier (count 2 x 8 warps).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_half_bytes = (p.bn / 2) * TC_BK * 4;
+  const int a_bytes = p.mt * TC_A_BYTES;
+  const int stage_bytes = a_bytes + b_half_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* ready_bar = full_bar + p.stages;
+  uint64_t* empty_bar = ready_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int tap0 = p.ph_tap0[blockIdx.z];
+  const int num_kb = (p.ph_tap0[blockIdx.z + 1] - tap0) * p.kchunks;
+  const int tile0 = blockIdx.x * p.mt;          // tiles beyond tiles_total are all-zero boxes whose rows are never stored
+  const int nb0 = blockIdx.y * p.bn;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_as.m[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full_bar[s], p.round_a ? 1 : 2);      // pair mode: leader's expect_tx arrive + the peer's arrive
+        mbar_init(&ready_bar[s], 2 * TC_RWARPS);         // the rounding warps of both CTAs
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                    // barriers of both CTAs initialised before any remote arrive / TMA
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own pixel tiles + own half of the weight tile, completing on the leader's barrier =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tl = kb / p.kchunks, kc = kb - tl * p.kchunks, tap = tap0 + tl;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        const uint32_t own_bytes = (uint32_t)(p.mt * p.rows_used * TC_BK * 4 + b_half_bytes);
+        int ow0, oh0, n0;
+        if (p.round_a) {
+          // the operand is rounded in shared memory first: every CTA completes its loads on its OWN barrier, its rounding
+          // warps wait there and then arrive on the leader's `ready` barrier, which is what the MMA warp waits for
+          mbar_expect_tx(&full_bar[stage], own_bytes);
+          for (int i = 0; i < p.mt; ++i) {
+            tc_tile_origin(p, tile0 + i, ow0, oh0, n0);
+            tma_load_4d(sa + i * TC_A_BYTES, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap],
+                        oh0 + p.off_h[tap], n0);
+          }
+          tma_load_3d(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0 + (int)rank * (p.bn / 2), p.wtap[tap]);
+        } else {
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * own_bytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          for (int i = 0; i < p.mt; ++i) {
+            tc_tile_origin(p, tile0 + i, ow0, oh0, n0);
+            tma_load_4d_pair(sa + i * TC_A_BYTES, &tm_as.m[p.amap[tap]], &full_bar[stage], kc * TC_BK, ow0 + p.off_w[tap],
+                             oh0 + p.off_h[tap], n0);
+          }
+          tma_load_3d_pair(sb, &tm_b, &full_bar[stage], kc * TC_BK, nb0 + (int)rank * (p.bn / 2), p.wtap[tap]);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader only, for both CTAs =====
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(p.round_a ? &ready_bar[stage] : &full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int i = 0; i < p.mt; ++i) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k)
+              umma_tf32_pair(tmem_base + (uint32_t)(i * p.bn), make_desc(a_addr + i * TC_A_BYTES + k * 32), make_desc(b_addr + k * 32),
+                             idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== warps 2..9: round the own A tiles (operand not pre-rounded), then the epilogue of the own tiles =====
+    const int q = threadIdx.x - 64;
+    if (p.round_a) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);              // this CTA's own loads (local completion in rounding mode)
+        uint32_t a4 = smem_u32(smem + stage * stage_bytes) + q * 16;
+        for (int tl = 0; tl < p.mt; ++tl, a4 += TC_A_BYTES) {
+          float4 v[TC_A_BYTES / 16 / (32 * TC_RWARPS)];
+#pragma unroll
+          for (int i = 0; i < TC_A_BYTES / 16 / (32 * TC_RWARPS); ++i) v[i] = lds128(a4 + i * (512 * TC_RWARPS));
+#pragma unroll
+          for (int i = 0; i < TC_A_BYTES / 16 / (32 * TC_RWARPS); ++i) {
+            v[i].x = rna_tf32(v[i].x); v[i].y = rna_tf32(v[i].y); v[i].z = rna_tf32(v[i].z); v[i].w = rna_tf32(v[i].w);
+            sts128(a4 + i * (512 * TC_RWARPS), v[i]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&ready_bar[stage], 0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_epilogue(p, tmem_base, tile0, p.mt, nb0, warp, lane, p.ph_base[blockIdx.z]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                                    // the peer's TMEM / barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ---- halo variant ------------------------------------------------------------------------------------------------
 // 3x3 stride-1 convolutions (forward and input gradient) are bound by the L2 -> shared-memory operand feed, not by the
 // tensor pipe: per 32-channel k-block a CTA pulls 16 KB of activations per pixel tile for every one
@@ -591,7 +744,12 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   }
 
   // ---- halo variant: three taps of a kernel column share one (bh+2)-row activation box --------------------------------
-  if (ctx->tc_halo && p.nphases == 1 && nviews == 1 && wimg_stride == 0 && ntaps == 9 && gh == h && gw == w && !view_phase_of) {
+  // Measured (round 2, profiles/r2_microbench.txt): with a pre-rounded operand the per-tap kernel is bound by the
+  // shared-memory pipe (TMA fills + UMMA operand reads), not by the L2 feed, and the halo variant (one CTA per SM) is no
+  // faster (256 -> 256) or slower (128 -> 128, which runs two per-tap CTAs per SM); it wins 8 % when the operand still
+  // has to be rounded in shared memory (half the rounding work).  CGAN_OPT_TC_HALO = 2 forces it everywhere (tests).
+  const bool halo_wanted = ctx->tc_halo == 2 || (ctx->tc_halo == 1 && p.round_a && ncols_pad >= 256);
+  if (halo_wanted && p.nphases == 1 && nviews == 1 && wimg_stride == 0 && ntaps == 9 && gh == h && gw == w && !view_phase_of) {
     int hbw = 0, hbh = 0;
     if (w % 32 == 0) { hbw = 32; hbh = 4; } else if (w == 16) { hbw = 16; hbh = 8; }
     // group the taps by horizontal offset; each group must be three vertically consecutive taps
@@ -702,6 +860,57 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) failed%s", "cgan_conv_tc");
   }
+  // ---- CTA-pair variant: two SMs share every weight tile (cta_group::2) --------------------------------------------------
+  if (ctx->tc_pair && wimg_stride == 0 && ncols_pad % 64 == 0) {
+    const long long tiles_total = (long long)p.tiles_w * p.tiles_h * tiles_n;
+    TcParams q = p;
+    q.bn = tc_pick_bn(ncols_pad);                 // widest column tile: the pair is about weight-tile reuse
+    const int ncol_tiles = ncols_pad / q.bn;
+    q.mt = 1;
+    for (int m = 4; m >= 2; --m)
+      if (m * q.bn <= 512 && tiles_total * ncol_tiles * q.nphases >= 2ll * m * ctx->num_sms) { q.mt = m; break; }
+    if (ctx->tc_mt_max < 2) q.mt = 1;
+    const long long groups = (tiles_total + q.mt - 1) / q.mt;
+    if (q.bn % 32 == 0 && q.bn >= 64 && groups * ncol_tiles * q.nphases >= ctx->num_sms) {
+      const size_t stage_bytes = (size_t)q.mt * TC_A_BYTES + (size_t)(q.bn / 2) * TC_BK * 4;
+      q.stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
+      if (q.stages > 6) q.stages = 6;
+      if (q.stages >= 3) {
+        q.tiles_total = (int)tiles_total;
+        q.tmem_cols = 32;
+        while (q.tmem_cols < q.mt * q.bn) q.tmem_cols *= 2;
+        AMaps tma;
+        memset(&tma, 0, sizeof(tma));
+        for (int v = 0; v < 4; ++v) {
+          int vv = v < nviews ? v : 0;
+          int vh = h, vw = w;
+          if (nviews == 4 && view_phase_of) { vh = (view_phase_of[0] - (vv >> 1) + 1) / 2; vw = (view_phase_of[1] - (vv & 1) + 1) / 2; }
+          if (vh < 1 || vw < 1) { vh = h; vw = w; vv = 0; }
+          if (!make_act_map(&tma.m[v], in + view_off[vv], kdim, vw, vh, n, in_sw, in_sh, in_sn, q.bw, q.bh, q.bni))
+            return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) failed%s", "cgan_conv_tc");
+        }
+        CUtensorMap tmb;
+        cuuint64_t dims[3] = {(cuuint64_t)kdim_pad, (cuuint64_t)ncols_pad, (cuuint64_t)taps_total};
+        cuuint64_t strides[2] = {(cuuint64_t)kdim_pad * 4, (cuuint64_t)ncols_pad * kdim_pad * 4};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(q.bn / 2), 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&tmb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, wt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B half) failed%s", "cgan_conv_tc");
+        size_t smem = (size_t)q.stages * stage_bytes + 1024 + 512;
+        static bool pair_attr_set = false;
+        if (!pair_attr_set) {
+          CGAN_CUDA(ctx, cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          pair_attr_set = true;
+        }
+        dim3 grid((unsigned)((groups + 1) / 2 * 2), (unsigned)ncol_tiles, (unsigned)q.nphases);
+        conv_tc_pair_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(tma, tmb, q);
+        CGAN_LAUNCHED(ctx);
+        return CGAN_OK;
+      }
+    }
+  }
+
   // Two CTAs per SM (each owns 256 of the 512 TMEM columns): one CTA's epilogue and prologue overlap the other's main
   // loop, which matters for the short-K convolutions (3x3x128: 36 k-blocks).  ~110 KB of smem each.
   // Pixel tiles per CTA: with mt = 2 the weight tile is fetched once for 256 pixels, which cuts the L2->SM bytes per MMA by

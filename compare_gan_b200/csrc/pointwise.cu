@@ -26,6 +26,8 @@ int cgan_ctx_create(cgan_ctx** out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->tc_mt_max = 2;
   if (const char* e = getenv("CGAN_TC_MT")) c->tc_mt_max = atoi(e) >= 2 ? 2 : 1;
+  c->tc_pair = 0;
+  if (const char* e = getenv("CGAN_TC_PAIR")) c->tc_pair = atoi(e) ? 1 : 0;
   c->tc_halo = 1;
   if (const char* e = getenv("CGAN_TC_HALO")) c->tc_halo = atoi(e) ? 1 : 0;
   c->stream = 0;
@@ -72,8 +74,12 @@ int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value) {
       CGAN_REQUIRE(ctx, value == 1 || value == 2, "CGAN_OPT_TC_MT must be 1 or 2");
       ctx->tc_mt_max = (int)value;
       return CGAN_OK;
+    case CGAN_OPT_TC_PAIR:
+      CGAN_REQUIRE(ctx, value == 0 || value == 1, "CGAN_OPT_TC_PAIR must be 0 or 1");
+      ctx->tc_pair = (int)value;
+      return CGAN_OK;
     case CGAN_OPT_TC_HALO:
-      CGAN_REQUIRE(ctx, value == 0 || value == 1, "CGAN_OPT_TC_HALO must be 0 or 1");
+      CGAN_REQUIRE(ctx, value >= 0 && value <= 2, "CGAN_OPT_TC_HALO must be 0, 1 or 2");
       ctx->tc_halo = (int)value;
       return CGAN_OK;
     default:
@@ -88,6 +94,7 @@ int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value) {
     case CGAN_OPT_TC_MT: *host_value = ctx->tc_mt_max; return CGAN_OK;
     case CGAN_OPT_LAST_PATH: *host_value = ctx->last_path; return CGAN_OK;
     case CGAN_OPT_TC_HALO: *host_value = ctx->tc_halo; return CGAN_OK;
+    case CGAN_OPT_TC_PAIR: *host_value = ctx->tc_pair; return CGAN_OK;
     default:
       return cgan_fail(ctx, CGAN_ERR_ARG, "%s: unknown option%s", "cgan_ctx_get_option");
   }
@@ -240,6 +247,49 @@ __global__ void conv_post_kernel(float* __restrict__ y, long long rows, int c, i
     if (round_out) v = rna_tf32_(v);
     y[o] = v;
   }
+}
+// y = images rotated by k * 90 degrees as gans/utils.py:38-49 composes them from transposes and flips (square images):
+// k=1: y[i][j] = x[j][h-1-i];  k=2: y[i][j] = x[h-1-i][w-1-j];  k=3: y[i][j] = x[h-1-j][i]
+__global__ void rot90_kernel(float* __restrict__ y, const float* __restrict__ x, int n, int hw, int c, int k) {
+  const long long tot = (long long)n * hw * hw * c;
+  EW_LOOP(i, tot) {
+    const int ch = (int)(i % c);
+    long long t = i / c;
+    const int j = (int)(t % hw); t /= hw;
+    const int r = (int)(t % hw);
+    const long long img = t / hw;
+    int sr, sc;
+    if (k == 1) { sr = j; sc = hw - 1 - r; }
+    else if (k == 2) { sr = hw - 1 - r; sc = hw - 1 - j; }
+    else { sr = hw - 1 - j; sc = r; }
+    y[i] = x[((img * hw + sr) * hw + sc) * c + ch];
+  }
+}
+// rotation self-supervision loss (gans/ssgan.py:205-213): rows = 4 * m logits rows, row r carries label r / m;
+// loss = -mean_r log(softmax(logits_r)[label_r] + 1e-10); dlogits (nullable) = d loss / d logits.  One block.
+__global__ void rotation_loss_kernel(float* loss, float* dlogits, const float* __restrict__ logits, int rows, int nrot) {
+  __shared__ float sh[32];
+  const int m = rows / nrot;
+  float acc = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* z = logits + (long long)r * nrot;
+    float mx = z[0];
+    for (int q = 1; q < nrot; ++q) mx = fmaxf(mx, z[q]);
+    float den = 0.f;
+    for (int q = 0; q < nrot; ++q) den += expf(z[q] - mx);
+    const int lab = r / m;
+    const float py = expf(z[lab] - mx) / den;
+    acc += -logf(py + 1e-10f);
+    if (dlogits) {
+      const float coef = -(py / (py + 1e-10f)) / rows;          // d(-log(p_y + eps)) / dz_q = -(p_y / (p_y + eps)) (delta_qy - p_q)
+      for (int q = 0; q < nrot; ++q) {
+        const float pq = expf(z[q] - mx) / den;
+        dlogits[(long long)r * nrot + q] = coef * ((q == lab ? 1.f : 0.f) - pq);
+      }
+    }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *loss = acc / rows;
 }
 __global__ void add_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, long long n, int rnd) {
   const long long n4 =
@@ -708,6 +758,17 @@ int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld
   return CGAN_OK;
 }
 
+int cgan_rot90(cgan_ctx* ctx, float* y, const float* x, int n, int hw, int c, int k) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, y && x && n > 0 && hw > 0 && c > 0 && k >= 1 && k <= 3, "bad argument");
+  rot90_kernel<<<ew_grid(ctx, (long long)n * hw * hw * c), 256, 0, ctx->stream>>>(y, x, n, hw, c, k);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_rotation_loss(cgan_ctx* ctx, float* loss_out, float* dlogits, const float* logits, int rows, int num_rotations) {
+  NONNULL(ctx);
+  CGAN_REQUIRE(ctx, loss_out && logits && rows > 0 && num_rotations > 0 && rows % num_rotations == 0, "rows must be a multiple of num_rotations");
+  rotation_loss_kernel<<<1, 256, 0, ctx->stream>>>(loss_out, dlogits, logits, rows, num_rotations);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
 int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n) { return cgan_add_tf32(ctx, y, a, b, n, 0); }
 int cgan_add_tf32(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n, int round_tf32) {
   NONNULL(ctx); CGAN_REQUIRE(ctx, y && a && b && n >= 0, "bad argument");

@@ -220,26 +220,21 @@ __device__ __forceinline__ void thin3_stage(float (*xs)[Thin3<CIN>::M4], const f
   }
 }
 
-// Compute layout of the two kernels below: a CTA is 4 warps; warp w takes the pixels pi = w, w + 4, ... of the staged
-// chunk, lane l the output channels l, l + 32, ... (CPT of them, up to 4 = 128 channels per CTA column).  One LDS.128 of a
-// receptive-field record then feeds 4 x CPT FMAs: with one channel per thread the kernels were bound by the shared-memory
-// pipe (a broadcast LDS.128 still costs four wavefronts), with four they are bound by the FP32 pipe / the HBM stream.
-template <int CIN, int CPT>
-__global__ void __launch_bounds__(128, (CPT >= 3) ? 3 : 6)
+// (A variant with four output channels per thread — one LDS.128 feeding 16 FMAs — was measured in round 2: 160 registers per
+// thread cut the occupancy to 3 CTAs per SM and it ran 20-35 % SLOWER than one channel per thread, which is bound by the
+// FP32 pipe (27 FFMAs per pixel and channel = ~100 us for 512x32x32x128 outputs) plus the staging phases.)
+template <int CIN>
+__global__ void __launch_bounds__(128, 8)
 fwd_thin3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                  const Thin3Params p, int relu, int round_out) {
   constexpr int M = Thin3<CIN>::M, M4 = Thin3<CIN>::M4;
   __shared__ __align__(16) float xs[THIN_PB][M4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co0 = blockIdx.y * (32 * CPT) + lane;
-  float wr[CPT][M4], b[CPT];
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < p.cout;
+  float wr[M4];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    const int co = co0 + 32 * j;
-#pragma unroll
-    for (int m = 0; m < M4; ++m) wr[j][m] = (co < p.cout && m < M) ? w[(size_t)m * p.cout + co] : 0.f;
-    b[j] = (co < p.cout && bias) ? bias[co] : 0.f;
-  }
+  for (int m = 0; m < M4; ++m) wr[m] = (co_ok && m < M) ? w[(size_t)m * p.cout + co] : 0.f;
+  const float b = (co_ok && bias) ? bias[co] : 0.f;
   const int c0 = blockIdx.x * p.chunks_per_block, c1 = min(p.nchunks, c0 + p.chunks_per_block);
   for (int c = c0; c < c1; ++c) {
     const int rowid = c / p.chunks_per_row, ow0 = (c - rowid * p.chunks_per_row) * THIN_PB;
@@ -248,53 +243,39 @@ fwd_thin3_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     __syncthreads();
     thin3_stage<CIN>(xs, x, p, img, oh, ow0, nb);
     __syncthreads();
-    float* yrow = y + ((size_t)rowid * p.ow + ow0) * p.ld;
-    for (int pi = warp; pi < nb; pi += 4) {
-      float acc[CPT];
+    if (co_ok) {
+      float* yrow = y + ((size_t)rowid * p.ow + ow0) * p.ld + co;
+#pragma unroll 2
+      for (int pi = 0; pi < nb; ++pi) {
+        float xv[M4];
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) acc[j] = b[j];
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
+        float acc = b;
 #pragma unroll
-      for (int m = 0; m < M4; m += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(&xs[pi][m]);
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-          acc[j] = fmaf(xv.x, wr[j][m], acc[j]);
-          acc[j] = fmaf(xv.y, wr[j][m + 1], acc[j]);
-          acc[j] = fmaf(xv.z, wr[j][m + 2], acc[j]);
-          acc[j] = fmaf(xv.w, wr[j][m + 3], acc[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int co = co0 + 32 * j;
-        float v = acc[j];
-        if (relu) v = fmaxf(v, 0.f);
-        if (round_out) {
+        for (int m = 0; m < M; ++m) acc = fmaf(xv[m], wr[m], acc);
+        if (relu) acc = fmaxf(acc, 0.f);
+        if (round_out) {                     // the consumer is a tensor-core convolution: store TF32-representable values
           uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-          v = __uint_as_float(u);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(acc));
+          acc = __uint_as_float(u);
         }
-        if (co < p.cout) yrow[(size_t)pi * p.ld + co] = v;
+        yrow[(size_t)pi * p.ld] = acc;
       }
     }
   }
 }
 
-// dW partial per CTA: lane = output channel (CPT of them), acc[j][m] over m = (tap, ci); dY is read exactly once, in
-// 128-byte rows.  The four warps of a CTA walk different pixels; their partial tiles are summed through shared memory.
-template <int CIN, int CPT>
-__global__ void __launch_bounds__(128, (CPT >= 3) ? 3 : 6)
+// dW partial per CTA: thread = output channel, acc[m] over m = (tap, ci); dY is read exactly once, in 128-byte rows
+template <int CIN>
+__global__ void __launch_bounds__(128, 6)
 wgrad_thin3_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, const Thin3Params p) {
   constexpr int M = Thin3<CIN>::M, M4 = Thin3<CIN>::M4;
   __shared__ __align__(16) float xs[THIN_PB][M4];
-  __shared__ float red[3][32 * CPT];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co0 = blockIdx.y * (32 * CPT) + lane;
-  float acc[CPT][M4];
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < p.cout;
+  float acc[M];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j)
-#pragma unroll
-    for (int m = 0; m < M4; ++m) acc[j][m] = 0.f;
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
   const int c0 = blockIdx.x * p.chunks_per_block, c1 = min(p.nchunks, c0 + p.chunks_per_block);
   for (int c = c0; c < c1; ++c) {
     const int rowid = c / p.chunks_per_row, ow0 = (c - rowid * p.chunks_per_row) * THIN_PB;
@@ -303,39 +284,22 @@ wgrad_thin3_kernel(const float* __restrict__ x, const float* __restrict__ dy, fl
     __syncthreads();
     thin3_stage<CIN>(xs, x, p, img, oh, ow0, nb);
     __syncthreads();
-    const float* grow = dy + ((size_t)rowid * p.ow + ow0) * p.cout;
-    for (int pi = warp; pi < nb; pi += 4) {
-      float g[CPT];
+    if (co_ok) {
+      const float* grow = dy + ((size_t)rowid * p.ow + ow0) * p.cout + co;
+#pragma unroll 2
+      for (int pi = 0; pi < nb; ++pi) {
+        const float g = __ldg(grow + (size_t)pi * p.cout);
+        float xv[M4];
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) g[j] = (co0 + 32 * j < p.cout) ? __ldg(grow + (size_t)pi * p.cout + co0 + 32 * j) : 0.f;
+        for (int m = 0; m < M4; m += 4) *reinterpret_cast<float4*>(&xv[m]) = *reinterpret_cast<const float4*>(&xs[pi][m]);
 #pragma unroll
-      for (int m = 0; m < M4; m += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(&xs[pi][m]);
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-          acc[j][m] = fmaf(xv.x, g[j], acc[j][m]);
-          acc[j][m + 1] = fmaf(xv.y, g[j], acc[j][m + 1]);
-          acc[j][m + 2] = fmaf(xv.z, g[j], acc[j][m + 2]);
-          acc[j][m + 3] = fmaf(xv.w, g[j], acc[j][m + 3]);
-        }
+        for (int m = 0; m < M; ++m) acc[m] = fmaf(xv[m], g, acc[m]);
       }
     }
   }
-  // sum the four warps' tiles in a fixed order (warp 0 + 1 + 2 + 3), one m at a time, and write the CTA's partial tile
+  if (co_ok) {
 #pragma unroll
-  for (int m = 0; m < M; ++m) {
-    __syncthreads();
-    if (warp > 0)
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) red[warp - 1][j * 32 + lane] = acc[j][m];
-    __syncthreads();
-    if (warp == 0)
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int co = co0 + 32 * j;
-        const float v = ((acc[j][m] + red[0][j * 32 + lane]) + red[1][j * 32 + lane]) + red[2][j * 32 + lane];
-        if (co < p.cout) partial[((size_t)blockIdx.x * M + m) * p.cout + co] = v;
-      }
+    for (int m = 0; m < M; ++m) partial[((size_t)blockIdx.x * M + m) * p.cout + co] = acc[m];
   }
 }
 
@@ -384,9 +348,8 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
   if (p.npix >= (1ll << 31)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: more than 2^31 output pixels%s", "cgan_wgrad_thin");
   if (d->cin <= 4 && d->kh == 3 && d->kw == 3) {
     Thin3Params q;
-    const int cpt = d->cout >= 128 ? 4 : (d->cout + 31) / 32;         // output channels per thread (lane + 32 j)
-    const int co_blocks = (d->cout + 32 * cpt - 1) / (32 * cpt);
-    if (thin3_params(d, ctx->num_sms, cpt >= 3 ? 6 : 12, co_blocks, &q)) {
+    const int co_blocks = (d->cout + 127) / 128;
+    if (thin3_params(d, ctx->num_sms, 6, co_blocks, &q)) {
       const int blocks = (q.nchunks + q.chunks_per_block - 1) / q.chunks_per_block;
       const long long wn = 9ll * d->cin * d->cout;
       void* ws = nullptr;
@@ -394,14 +357,12 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
       if (rc) return rc;
       float* partial = reinterpret_cast<float*>(ws);
       dim3 grid(blocks, co_blocks);
-#define CGAN_THIN_WG(CI, CP) wgrad_thin3_kernel<CI, CP><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q)
-#define CGAN_THIN_WG_CI(CP)                                                                                          \
-  switch (d->cin) { case 1: CGAN_THIN_WG(1, CP); break; case 2: CGAN_THIN_WG(2, CP); break; case 3: CGAN_THIN_WG(3, CP); break; \
-                    default: CGAN_THIN_WG(4, CP); break; }
-      switch (cpt) { case 1: CGAN_THIN_WG_CI(1) break; case 2: CGAN_THIN_WG_CI(2) break; case 3: CGAN_THIN_WG_CI(3) break;
-                     default: CGAN_THIN_WG_CI(4) break; }
-#undef CGAN_THIN_WG_CI
-#undef CGAN_THIN_WG
+      switch (d->cin) {
+        case 1: wgrad_thin3_kernel<1><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        case 2: wgrad_thin3_kernel<2><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        case 3: wgrad_thin3_kernel<3><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+        default: wgrad_thin3_kernel<4><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, q); break;
+      }
       CGAN_LAUNCHED(ctx);
       thin_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, blocks);
       CGAN_LAUNCHED(ctx);
@@ -457,19 +418,17 @@ int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const 
   p.npix = (long long)d->n * d->oh * d->ow;
   if (d->kh == 3 && d->kw == 3) {
     Thin3Params q;
-    const int cpt = d->cout >= 128 ? 4 : (d->cout + 31) / 32;
-    const int co_blocks3 = (d->cout + 32 * cpt - 1) / (32 * cpt);
-    if (thin3_params(d, ctx->num_sms, cpt >= 3 ? 6 : 12, co_blocks3, &q)) {
+    const int threads3 = d->cout >= 128 ? 128 : ((d->cout + 31) / 32 * 32);
+    const int co_blocks3 = (d->cout + threads3 - 1) / threads3;
+    if (thin3_params(d, ctx->num_sms, 8 * 128 / threads3, co_blocks3, &q)) {
       q.ld = ldy;
       dim3 grid((q.nchunks + q.chunks_per_block - 1) / q.chunks_per_block, co_blocks3);
-#define CGAN_THIN_FW(CI, CP) fwd_thin3_kernel<CI, CP><<<grid, 128, 0, ctx->stream>>>(x, w, bias, y, q, relu, round_out)
-#define CGAN_THIN_FW_CI(CP)                                                                                          \
-  switch (d->cin) { case 1: CGAN_THIN_FW(1, CP); break; case 2: CGAN_THIN_FW(2, CP); break; case 3: CGAN_THIN_FW(3, CP); break; \
-                    default: CGAN_THIN_FW(4, CP); break; }
-      switch (cpt) { case 1: CGAN_THIN_FW_CI(1) break; case 2: CGAN_THIN_FW_CI(2) break; case 3: CGAN_THIN_FW_CI(3) break;
-                     default: CGAN_THIN_FW_CI(4) break; }
-#undef CGAN_THIN_FW_CI
-#undef CGAN_THIN_FW
+      switch (d->cin) {
+        case 1: fwd_thin3_kernel<1><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu, round_out); break;
+        case 2: fwd_thin3_kernel<2><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu, round_out); break;
+        case 3: fwd_thin3_kernel<3><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu, round_out); break;
+        default: fwd_thin3_kernel<4><<<grid, threads3, 0, ctx->stream>>>(x, w, bias, y, q, relu, round_out); break;
+      }
       CGAN_LAUNCHED(ctx);
       return CGAN_OK;
     }

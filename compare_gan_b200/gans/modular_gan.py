@@ -169,11 +169,7 @@ class ModularGAN(AbstractGAN):
       self.inputs.append(f)
     self.losses = tape.DT(torch.zeros(k + 1, device=dev))
     with V.use(self.store), tape.no_record():
-      f = self.inputs[0]
-      sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
-      gen = self.generator(f["z"], y=sy, is_training=True)
-      all_y = K.concat_rows(sy, sy) if self.conditional else None
-      self.discriminator(K.concat_rows(f["images"], gen), y=all_y, is_training=True)
+      self._build_networks(self.inputs[0])
     self.flat_g = self.store.pack("generator")
     self.flat_d = self.store.pack("discriminator")
     self.store.reset_to_init()          # graph construction runs no ops: undo BN/u_var side effects
@@ -185,6 +181,14 @@ class ModularGAN(AbstractGAN):
     self._built_batch = b
     torch.cuda.synchronize()
     return self
+
+  def _build_networks(self, f):
+    """One dry generator / discriminator call that creates every variable (like TF graph construction)."""
+    sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
+    gen = self.generator(f["z"], y=sy, is_training=True)
+    all_y = K.concat_rows(sy, sy) if self.conditional else None
+    self.discriminator(K.concat_rows(f["images"], gen), y=all_y, is_training=True)
+    return gen, all_y
 
   # ---- one cycle (reference model_fn :512-604, unrolled) -------------------------------------------------
   def _grad_sinks(self, prefix, params):
@@ -389,3 +393,6 @@ class ModularGAN(AbstractGAN):
     self.store.load_numpy(state)
     if self.ema is not None:
       self.ema.t.copy_(self.flat_g["param"].t)
+
+
+from . import ssgan  # noqa: E402,F401  (registers @SSGAN with gin wherever ModularGAN is importable)

@@ -35,6 +35,13 @@ def tf32_on():
   return _RT["math_mode"] == 1
 
 
+def _arith(a_pre=False, b_pre=False, b_is_weight=True):
+  """(path, first operand TF32-rounded, second operand TF32-rounded) of the contraction that just ran."""
+  path = _lib.PATH_NAMES[_RT["lib"].get_option(_lib.OPT_LAST_PATH)]
+  tc = path == "tcgen05_tf32"
+  return (path, bool(tc or (a_pre and tf32_on())), bool(tc or (b_pre and tf32_on() and not b_is_weight)))
+
+
 def _no_second_order(name):
   """Called by the vjps that launch raw (untaped) kernels: under tape.backward(create_graph=True) their output would
   silently lack its dependence on the incoming gradient and the stashed tensors."""
@@ -49,9 +56,13 @@ def _trace(kind, key, a_pre=False, b_pre=False, b_is_weight=True):
     path = _lib.PATH_NAMES[_RT["lib"].get_option(_lib.OPT_LAST_PATH)]
     tc = path == "tcgen05_tf32"
     rec = (path, bool(tc or (a_pre and tf32_on())), bool(tc or (b_pre and tf32_on() and not b_is_weight)))
-    prev = CONV_TRACE.setdefault((kind,) + tuple(key), rec)
+    k = (kind,) + tuple(key)
+    prev = CONV_TRACE.setdefault(k, rec)
     if prev != rec:
-      raise AssertionError("contraction %s %s ran as %s and as %s" % (kind, key, prev, rec))
+      # the same shape ran with differently prepared operands (e.g. an exact-fp32 filter gradient whose dy was stored
+      # TF32-rounded for one layer and not for another): keep the union — the emulating oracle is a yard-stick for what
+      # TF32 evaluation loses, the per-call truth goes to CONV_CHECK
+      CONV_TRACE[k] = (prev[0] if prev[0] == rec[0] else "tcgen05_tf32", prev[1] or rec[1], prev[2] or rec[2])
 
 
 def _fusable_relu(x):
@@ -225,6 +236,29 @@ def slice_rows(x, lo, hi):
   return attach("slice_rows", y, [x], vjp)
 
 
+def rot90(x, k):
+  """Images rotated by k * 90 degrees (gans/utils.py:38-49, rotate_images); k in 1..3, square NHWC."""
+  n, h, w, c = x.shape
+  if h != w:
+    raise ValueError("rot90 needs square images, got %dx%d" % (h, w))
+  k = int(k) % 4
+  if k == 0:
+    return x
+  y = empty(n, h, w, c)
+  _call("rot90", y.ptr, x.ptr, n, h, c, k)
+  return attach("rot90", y, [x], lambda g, needs: [rot90(g, 4 - k)])       # a permutation: the adjoint is the inverse
+
+
+def rotation_loss(logits, num_rotations=4):
+  """-mean log(softmax(logits)[r // m] + 1e-10) over the 4*m rows (gans/ssgan.py:205-213); a one-element device tensor."""
+  rows, nrot = logits.shape
+  if nrot != num_rotations or rows % nrot:
+    raise ValueError("rotation_loss: logits must be [num_rotations * m, num_rotations], got %s" % (logits.shape,))
+  loss, dl = empty(1), empty(rows, nrot)
+  _call("rotation_loss", loss.ptr, dl.ptr, logits.ptr, rows, nrot)
+  return attach("rotation_loss", loss, [logits], lambda g, needs: [_scale_by(dl, g)])
+
+
 def concat_cols(a, b):
   """tf.concat([a, b], axis=1) for rank-2 tensors (resnet_biggan.py:254)."""
   n, ca, cb = a.shape[0], a.shape[1], b.shape[1]
@@ -286,7 +320,7 @@ def _conv_fwd_raw(d, x, w, bias, relu=False, residual=None, round_out=False):
   _trace("fwd", _desc_key(d), x.tf32)
   y.tf32 = rnd
   if CONV_CHECK is not None:
-    CONV_CHECK("fwd", d=d, x=x, w=w, bias=bias, residual=residual, relu=relu, round_out=rnd, out=y)
+    CONV_CHECK("fwd", d=d, x=x, w=w, bias=bias, residual=residual, relu=relu, round_out=rnd, out=y, arith=_arith(x.tf32))
   return y
 
 
@@ -375,7 +409,7 @@ def conv2d_dgrad(d, dy, w, bias=None, round_out=False, relu_mask=None, mask_for=
   if mref is not None:
     dx.premasked_for = id(mask_for)
   if CONV_CHECK is not None:
-    CONV_CHECK("dgrad", d=d, dy=dy, w=w, bias=bias, round_out=rnd, mask=mref, mask_leak=mleak, out=dx)
+    CONV_CHECK("dgrad", d=d, dy=dy, w=w, bias=bias, round_out=rnd, mask=mref, mask_leak=mleak, out=dx, arith=_arith(dy.tf32))
   cin = d.cin
 
   def vjp(g, needs):   # linear in dy and in w
@@ -403,7 +437,7 @@ def conv2d_wgrad(d, x, dy, leaf=None):
   _call("conv2d_wgrad_ex", ctypes.byref(d), x.ptr, dy.ptr, flags, dw.ptr)
   _trace("wgrad", _desc_key(d), x.tf32, dy.tf32, b_is_weight=False)
   if CONV_CHECK is not None:
-    CONV_CHECK("wgrad", d=d, x=x, dy=dy, out=dw)
+    CONV_CHECK("wgrad", d=d, x=x, dy=dy, out=dw, arith=_arith(x.tf32, dy.tf32, b_is_weight=False))
 
   def vjp(g, needs):
     raise NotImplementedError("third-order differentiation through conv2d_wgrad is not needed on this path")
@@ -457,7 +491,7 @@ def bmm(a, b, ta=False, tb=False):
         b.ptr, b.shape[2], b.shape[1] * b.shape[2], 0.0, c.ptr, n, m * n, bsz)
   _trace("bmm", (bsz, int(ta), int(tb), m, n, k))
   if CONV_CHECK is not None:
-    CONV_CHECK("bmm", a=a, b=b, ta=ta, tb=tb, out=c)
+    CONV_CHECK("bmm", a=a, b=b, ta=ta, tb=tb, out=c, arith=_arith())
 
   def vjp(g, needs):
     ga = gb = None

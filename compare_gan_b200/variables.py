@@ -61,7 +61,10 @@ class VariableStore(object):
     return v
 
   def trainable_under(self, prefix):
-    return OrderedDict((k, v) for k, v in self.trainable.items() if k.startswith(prefix + "/"))
+    """Trainable variables of a network.  The reference selects them by substring (`self._name in var.name`,
+    architectures/abstract_arch.py:43-45), which is how SSGAN's `discriminator_rotation/...` head trains with the
+    discriminator: here the top-level scope must START with the network's name."""
+    return OrderedDict((k, v) for k, v in self.trainable.items() if k.split("/")[0].startswith(prefix))
 
   # ---- flat packing -----------------------------------------------------------------------
   def pack(self, prefix):

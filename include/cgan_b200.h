@@ -42,10 +42,12 @@ const char* cgan_last_error(cgan_ctx* ctx);
 int64_t cgan_launch_count(cgan_ctx* ctx);
 /* Tuning knobs and introspection (tests compare kernel variants bit for bit and ask which path a contraction took).
  *   CGAN_OPT_TC_MT      (set/get) max pixel tiles (conv) / work units (filter gradient) per tcgen05 CTA: 1 or 2.
- *   CGAN_OPT_TC_HALO    (set/get) 1: 3x3 stride-1 tcgen05 convolutions fetch one (rows+2)-row activation box per kernel
- *                       column instead of one box per tap (default); 0: one box per tap.
+ *   CGAN_OPT_TC_HALO    (set/get) 3x3 stride-1 tcgen05 convolutions fetch one (rows+2)-row activation box per kernel column
+ *                       instead of one box per tap: 0 never, 1 where it measured faster (operand rounded in the kernel,
+ *                       >= 256 output channels; default), 2 wherever the geometry allows.
+ *   CGAN_OPT_TC_PAIR    (set/get) 1: tcgen05 convolutions run as CTA pairs (cta_group::2, M = 256) sharing each weight tile.
  *   CGAN_OPT_LAST_PATH  (get) CGAN_PATH_* taken by the most recent conv2d_fwd / dgrad / wgrad / gemm_batched call. */
-enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3 };
+enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3, CGAN_OPT_TC_PAIR = 4 };
 enum { CGAN_PATH_SIMT_FP32 = 0, CGAN_PATH_TCGEN05_TF32 = 1, CGAN_PATH_THIN_FP32 = 2 };
 int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value);
 int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value);
@@ -220,6 +222,13 @@ int cgan_gan_loss(cgan_ctx*, int kind, const float* logits_real, const float* lo
 /* gans/penalty_lib.py:78-81: slopes = sqrt(1e-4 + sum_hwc g^2); penalty = mean((slopes-1)^2);
  * dg (nullable) = d(weight*penalty)/dg. */
 int cgan_gp_penalty(cgan_ctx*, float* penalty_out, float* dg, const float* g, int n, int64_t per, float weight);
+
+/* ---- self-supervision (gans/ssgan.py, gans/utils.py:38-49) ------------------------------------------------------ */
+/* y = x rotated by k * 90 degrees (k = 1, 2, 3), square NHWC images: rotate_images' transposes / flips in one pass. */
+int cgan_rot90(cgan_ctx*, float* y, const float* x, int n, int hw, int c, int k);
+/* rotation loss: `rows` = num_rotations * m logit rows [rows, num_rotations], row r labelled r / m;
+ * *loss_out = -mean log(softmax(logits)[label] + 1e-10) (ssgan.py:205-213); dlogits (nullable) = its gradient. */
+int cgan_rotation_loss(cgan_ctx*, float* loss_out, float* dlogits, const float* logits, int rows, int num_rotations);
 
 /* ---- optimizer (tf.train.AdamOptimizer + tf.train.ExponentialMovingAverage, gans/modular_gan.py:498-508) ---- */
 /* One fused multi-tensor step over a flat parameter buffer.  *step_dev (int32, device) is incremented first; then

@@ -168,7 +168,7 @@ class GanOracle(object):
       gen = gen_sample(i, False).detach()
       d_loss, _ = self.create_loss(torch.as_tensor(images[i]).to(self.dtype), gen, ys[i], sys_[i],
                                    None if alphas is None else torch.as_tensor(alphas[i]).to(self.dtype))
-      params = self.store.trainable_under("discriminator")
+      params = getattr(self, "_d_params", None) or self.store.trainable_under("discriminator")
       grads = torch.autograd.grad(d_loss, list(params.values()), allow_unused=True)
       self.last_d_grads = OrderedDict((n, torch.zeros_like(p) if g is None else g.detach().clone())
                                       for (n, p), g in zip(params.items(), grads))
@@ -192,3 +192,77 @@ class GanOracle(object):
           self.ema[n].sub_((self.ema[n] - p) * (1.0 - decay))
     self.global_step += 1
     return d_losses, float(g_loss.detach())
+
+
+# --------------------------------------------------------------------------- SSGAN (gans/ssgan.py)
+
+def rotate_images(images, rot90_scalars=(0, 1, 2, 3)):
+  """gans/utils.py:38-49 on NHWC tensors: transpose_image swaps H and W, flip_up_down reverses H, flip_left_right W."""
+  tr = lambda x: x.permute(0, 2, 1, 3)
+  ud = lambda x: torch.flip(x, dims=[1])
+  lr = lambda x: torch.flip(x, dims=[2])
+  rotated = [images, ud(tr(images)), lr(ud(images)), tr(ud(images))]
+  return torch.cat([rotated[i] for i in rot90_scalars], 0)
+
+
+class SsganOracle(GanOracle):
+  """gans/ssgan.py:40-226 restated: rotation head on the discriminator features, rotation losses for D (real) and G (fake)."""
+
+  def __init__(self, cfg, rotated_batch_size, self_supervision="rotation_gan", weight_rotation_loss_d=1.0,
+               weight_rotation_loss_g=0.2, **kw):
+    super(SsganOracle, self).__init__(cfg, **kw)
+    self.rotated_batch_size, self.self_supervision = rotated_batch_size, self_supervision
+    self.w_d, self.w_g = weight_rotation_loss_d, weight_rotation_loss_g
+
+  def _head(self, x, y):
+    d, logits, final = nets.discriminator(self.store, self.cfg, x, y, True)
+    with self.store.scope("discriminator_rotation"):
+      rot = nets.linear(self.store, self.cfg, final.reshape(x.shape[0], -1), 4, "score_classify", use_sn=self.cfg.d_sn)
+    return d, logits, rot
+
+  def build(self, batch):
+    super(SsganOracle, self).build(batch)
+    h, w, c = self.cfg.image_shape
+    with torch.no_grad():
+      self._head(torch.zeros(2 * batch, h, w, c, dtype=self.dtype), None if not self.conditional else self.one_hot(np.zeros(2 * batch, np.int64)))
+    return self
+
+  def _ensure_opts(self):
+    if self.d_opt is None:
+      d_params = OrderedDict((k, v) for k, v in self.store.trainable.items() if k.split("/")[0].startswith("discriminator"))
+      self.d_opt = TFAdam(d_params, self.d_lr, self.beta1, self.beta2)
+      self.g_opt = TFAdam(self.store.trainable_under("generator"), self.g_lr, self.beta1, self.beta2)
+      self._d_params = d_params
+
+  def create_loss(self, images, generated, y, sampled_y, alpha=None, for_d=True):
+    bs = images.shape[0]
+    n = self.rotated_batch_size // 4
+    rotation = "rotation" in (self.self_supervision or "")
+    all_y = None
+    if rotation:
+      ir = rotate_images(images[bs - n:], (1, 2, 3))
+      gr = rotate_images(generated[bs - n:], (1, 2, 3))
+      all_images = torch.cat([images, ir, generated, gr], 0)
+      if self.conditional:
+        yr = y[bs - n:].repeat(3, 1)
+        all_y = torch.cat([y, yr, sampled_y, yr], 0)
+    else:
+      all_images = torch.cat([images, generated], 0)
+      if self.conditional:
+        all_y = torch.cat([y, sampled_y], 0)
+    d_all, d_logits, c_logits = self._head(all_images, all_y)
+    half = d_all.shape[0] // 2
+    d_loss, _, _, g_loss = get_losses(self.loss, d_all[:bs], d_all[half:half + bs], d_logits[:bs], d_logits[half:half + bs])
+    if for_d:
+      d_loss = d_loss + self.lamba * get_penalty_loss(self.penalty, self.store, self.cfg, images, generated, y, True, alpha)
+    if rotation:
+      rb = self.rotated_batch_size
+      labels = torch.arange(4).repeat_interleave(n)
+      onehot = torch.nn.functional.one_hot(labels, 4).to(self.dtype)
+      c_real = -(onehot * torch.log(torch.softmax(c_logits[half - rb:half], -1) + 1e-10)).sum(1).mean()
+      c_fake = -(onehot * torch.log(torch.softmax(c_logits[2 * half - rb:], -1) + 1e-10)).sum(1).mean()
+      if self.self_supervision == "rotation_only":
+        d_loss, g_loss = d_loss * 0.0, g_loss * 0.0
+      d_loss = d_loss + c_real * self.w_d
+      g_loss = g_loss + c_fake * self.w_g
+    return (d_loss if for_d else None), g_loss

@@ -73,10 +73,10 @@ class EmulatedLib(object):
     return self.launches
 
   def get_option(self, key):
-    return {1: 2, 2: self.last_path, 3: 1}[key]
+    return {1: 2, 2: self.last_path, 3: 1, 4: 0}[key]
 
   def set_option(self, key, value):
-    assert (key == 1 and value in (1, 2)) or (key == 3 and value in (0, 1))
+    assert (key == 1 and value in (1, 2)) or (key == 3 and value in (0, 1, 2)) or (key == 4 and value in (0, 1))
 
   def call(self, name, *args):
     self.launches += 1
@@ -400,6 +400,22 @@ class EmulatedLib(object):
     else:                                  # y = (tanh+1)/2  =>  dy/dx = (1 - tanh^2)/2 = 2 y (1 - y)
       out = g * 2 * r * (1 - r)
     f32(dx, n)[:] = rna_tf32(out) if rnd else out
+
+  def cgan_rot90(self, y, x, n, hw, c, k):
+    v = f32(x, n * hw * hw * c).reshape(n, hw, hw, c)
+    tr = lambda a: a.transpose(0, 2, 1, 3)
+    out = {1: lambda: tr(v)[:, ::-1], 2: lambda: v[:, ::-1, ::-1], 3: lambda: tr(v[:, ::-1])}[k]()
+    f32(y, n * hw * hw * c)[:] = np.ascontiguousarray(out).ravel()
+
+  def cgan_rotation_loss(self, loss_out, dlogits, logits, rows, nrot):
+    z = torch.from_numpy(f32(logits, rows * nrot).reshape(rows, nrot).copy()).double().requires_grad_(True)
+    labels = torch.arange(nrot).repeat_interleave(rows // nrot)
+    p = torch.softmax(z, -1)[torch.arange(rows), labels]
+    loss = -(torch.log(p + 1e-10)).mean()
+    loss.backward()
+    f32(loss_out, 1)[0] = float(loss.detach())
+    if dlogits is not None:
+      f32(dlogits, rows * nrot)[:] = z.grad.numpy().astype(np.float32).ravel()
 
   def cgan_add(self, y, a, b, n):
     f32(y, n)[:] = f32(a, n) + f32(b, n)

@@ -450,8 +450,8 @@ def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
     if k == 1 and up:
       assert launched == 3, "1x1 up-sampling conv: weight prep + one tcgen05 phase + bias fill, got %d" % launched
     elif k * k <= 32:
-      # (one weight preparation serves the four sub-pixel phases of a convolution over a zero-inserted input)
-      assert launched == (2 if not up else 5), "expected the tcgen05 path (weight prep + conv per phase), got %d launches" % launched
+      # (the four sub-pixel phases of a convolution over a zero-inserted input share one weight preparation and ONE launch)
+      assert launched == 2, "expected the tcgen05 path (weight prep + one launch), got %d launches" % launched
     assert_close(y.cpu(), ref.detach().numpy(), 1e-3, "tc conv fwd")
     gx, gw = tape_grads(K, y, gy, [xd, wd])
     assert_close(gx.cpu(), xt.grad.numpy(), 1e-3, "tc conv dgrad")
