@@ -18,6 +18,8 @@ struct cgan_ctx {
   int tc_mt_max;       // tcgen05 kernels: max tiles per CTA sharing one operand tile (CGAN_OPT_TC_MT / env CGAN_TC_MT, default 2)
   int tc_halo;         // 3x3 stride-1 tcgen05 convolutions use the halo variant (CGAN_OPT_TC_HALO / env CGAN_TC_HALO, default 1)
   int tc_pair;         // tcgen05 convolutions run as CTA pairs sharing each weight tile (CGAN_OPT_TC_PAIR / env CGAN_TC_PAIR)
+  int tc_epi;          // coalescing (shared-memory transposed) epilogue of the tcgen05 convolutions (CGAN_OPT_TC_EPI / env CGAN_TC_EPI)
+  int tc_pair_mt;      // experiment knob: pixel tiles per CTA of the pair kernel (env CGAN_TC_PAIR_MT; 0 = automatic)
   int last_path;       // CGAN_PATH_* of the most recent contraction (cgan_ctx_get_option(CGAN_OPT_LAST_PATH))
   unsigned* counters;  // CGAN_NUM_COUNTERS zero-initialised tickets for single-launch two-stage reductions (norm.cu)
   void* p2p;           // peer-memory all-reduce state (p2p.cu), null until cgan_p2p_local_handle

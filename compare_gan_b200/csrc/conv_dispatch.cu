@@ -16,6 +16,9 @@ bool cgan_fwd_thin_ok(const cgan_conv_desc* d);
 int cgan_fwd_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int relu,
                   int ldy, int round_out);
 bool cgan_fwd_thin3_ok(const cgan_conv_desc* d);
+bool cgan_pw_thin_ok(const cgan_conv_desc* d);
+int cgan_fwd_pw_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                     const float* residual, int relu, int ldy, int round_out);
 int cgan_wgrad_tc_batched(cgan_ctx* ctx, const float* a, const float* b, float* c, int batch, int h, int w, int k1, int k2);
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d);
 int cgan_wgrad_tc(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw, int x_tf32, int dy_tf32);
@@ -172,6 +175,12 @@ int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, c
   // exact-fp32 paths: residual / mask / rounding are applied by one extra pointwise pass
   bool post = ep && (ep->residual || ep->mask || (ep->flags & CGAN_CONV_ROUND_OUT));
   int rc;
+  if (cgan_pw_thin_ok(d) && ptr_ok && al16p(w) && ldy % 4 == 0 && !(ep && ep->mask)) {
+    // pointwise conv over <= 4 channels: one streaming kernel with residual add, ReLU and rounding fused
+    ctx->last_path = CGAN_PATH_THIN_FP32;
+    return cgan_fwd_pw_thin(ctx, d, x, w, bias, y, ep ? ep->residual : nullptr, relu, ldy,
+                            (ep && (ep->flags & CGAN_CONV_ROUND_OUT)) ? 1 : 0);
+  }
   if (cgan_fwd_thin_ok(d)) {
     ctx->last_path = CGAN_PATH_THIN_FP32;
     const bool fused = post && !ep->residual && !ep->mask && cgan_fwd_thin3_ok(d);   // ReLU + rounding in the 3x3 kernel itself

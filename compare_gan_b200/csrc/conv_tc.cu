@@ -41,6 +41,7 @@ struct TcParams {
   int rows_used;                    // bw*bh*bni <= 128 pixel rows actually filled by the TMA box
   int img_n, img_h, img_w;          // extent of the pixel grid (tiles at the border hang over; those rows are not stored)
   int relu;                         // fused ReLU in the epilogue
+  int epi_stage;                    // 1: the epilogue transposes through shared memory for coalesced stores (tc_epilogue)
   int round_a;                      // 1: round the activation tiles to nearest TF32 in shared memory (operand not pre-rounded)
   int round_out;                    // 1: store TF32-rounded outputs (the consumer is another tensor-core contraction)
   float mask_leak;                  // with `mask`: out = ref > 0 ? v : mask_leak * v  ((leaky-)ReLU backward fused into a dgrad)
@@ -97,20 +98,54 @@ __device__ __forceinline__ void tc_tile_origin(const TcParams& p, int t, int& ow
 
 // Epilogue of warps 2..9: tcgen05.ld the accumulators of this CTA's tiles, apply bias / residual / ReLU / mask / TF32
 // rounding, store.  TMEM lane quarter is fixed by (warp id % 4); row of the tile = TMEM lane.
+//
+// tcgen05.ld hands every thread 32 consecutive columns of ITS row; storing them from there costs one 16-byte piece in
+// each of 32 different 128-byte lines per instruction — 32 LSU wavefronts, and the epilogue (a fifth of the kernel at
+// one CTA per SM, ncu r2: 129 k wavefronts per SM) is bound by exactly that.  Each warp therefore transposes its
+// 32 x 32 chunk through a private 32 x 36-float staging area in the (by now idle) operand ring, after which a quarter
+// warp owns one row's 128 contiguous bytes: 4 wavefronts per store instruction, and the fused residual / mask reads
+// coalesce the same way.  `stg` = shared address of this warp's staging area (0: none, per-thread rows).
+constexpr int TC_EPI_ROW_BYTES = 36 * 4;                     // 32 columns + 16 B pad: 16-byte aligned, conflict-free v4 access
+constexpr int TC_EPI_WARP_BYTES = 32 * TC_EPI_ROW_BYTES;     // 4608 B per warp, 36 KB per CTA
+
+__device__ __forceinline__ float4 tc_epilogue_math(const TcParams& p, float4 v, const float4 bv, long long off) {
+  v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+  if (p.residual) {
+    const float4 rv = *reinterpret_cast<const float4*>(p.residual + off);
+    v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+  }
+  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (p.mask) {
+    const float4 mv = *reinterpret_cast<const float4*>(p.mask + off);
+    v.x = mv.x > 0.f ? v.x : p.mask_leak * v.x; v.y = mv.y > 0.f ? v.y : p.mask_leak * v.y;
+    v.z = mv.z > 0.f ? v.z : p.mask_leak * v.z; v.w = mv.w > 0.f ? v.w : p.mask_leak * v.w;
+  }
+  if (p.round_out) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
+  return v;
+}
+
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_base, int tile0, int nt_here, int nb0, int warp,
-                                            int lane, long long out_base) {
+                                            int lane, long long out_base, uint32_t stg) {
   const int quarter = warp & 3;
   const int m = quarter * 32 + lane;
   const int wi = m % p.bw;
   const int hi = (m / p.bw) % p.bh;
   const int ni = m / (p.bw * p.bh);
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;       // transposed role: row (i*4 + sub) of the chunk, columns c4..c4+3
   for (int tl = 0; tl < nt_here; ++tl) {
     int ow0, oh0, n0;
     tc_tile_origin(p, tile0 + tl, ow0, oh0, n0);
     // rows beyond the box (stale smem) and pixels outside the grid are computed but never stored
     const bool row_ok = m < p.rows_used && n0 + ni < p.img_n && oh0 + hi < p.img_h && ow0 + wi < p.img_w;
-    float* orow = p.out + out_base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
-                  (long long)(ow0 + wi) * p.s_w + nb0;
+    // element offset of this row's first column in `out` (residual / mask share the output's geometry)
+    const long long roff = out_base + (long long)(n0 + ni) * p.s_n + (long long)(oh0 + hi) * p.s_h +
+                           (long long)(ow0 + wi) * p.s_w + nb0;
+    const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+    long long roffs[8];
+    if (stg) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) roffs[i] = __shfl_sync(0xffffffffu, roff, i * 4 + sub);
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * p.bn);
     // two warps share a lane quarter: the first takes the lower half of the 32-column chunks, the second the rest
     const int nchunks = p.bn / 32, csplit = (nchunks + 1) / 2;
@@ -118,32 +153,37 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
     for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + (uint32_t)c0, r);
-      if (!row_ok) continue;                 // (the tcgen05.ld above is warp-collective; only the stores are predicated)
-      const long long roff = orow - p.out;   // residual / mask share the output's geometry
-      if (nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0) {
+      const bool whole = nb0 + c0 + 32 <= p.cout && (p.cout & 3) == 0;      // warp-uniform
+      if (whole && stg) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v;
-          v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
-          v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-          if (p.bias) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        for (int j = 0; j < 8; ++j)
+          sts128(stg + lane * TC_EPI_ROW_BYTES + j * 16,
+                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3])));
+        __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + c4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = lds128(stg + (i * 4 + sub) * TC_EPI_ROW_BYTES + c4 * 4);
+          if ((okmask >> (i * 4 + sub)) & 1u) {
+            const long long off = roffs[i] + c0 + c4;
+            *reinterpret_cast<float4*>(p.out + off) = tc_epilogue_math(p, v, bv, off);
           }
-          if (p.residual) {
-            const float4 rv = *reinterpret_cast<const float4*>(p.residual + roff + c0 + j);
-            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-          }
-          if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (p.mask) {
-            const float4 mv = *reinterpret_cast<const float4*>(p.mask + roff + c0 + j);
-            v.x = mv.x > 0.f ? v.x : p.mask_leak * v.x; v.y = mv.y > 0.f ? v.y : p.mask_leak * v.y;
-            v.z = mv.z > 0.f ? v.z : p.mask_leak * v.z; v.w = mv.w > 0.f ? v.w : p.mask_leak * v.w;
-          }
-          if (p.round_out) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
-          *reinterpret_cast<float4*>(orow + c0 + j) = v;
         }
-      } else {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
+        __syncwarp();
+      } else if (whole) {
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                         __uint_as_float(r[j + 3]));
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + nb0 + c0 + j);
+            *reinterpret_cast<float4*>(p.out + roff + c0 + j) = tc_epilogue_math(p, v, bv, roff + c0 + j);
+          }
+        }
+      } else if (row_ok) {      // thin / padded tile (e.g. the 256->3 image conv): only the first `cout` columns exist
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (nb0 + c0 + j < p.cout) {
@@ -153,7 +193,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint32_t tmem_bas
             if (p.relu) v = fmaxf(v, 0.f);
             if (p.mask) v = p.mask[roff + c0 + j] > 0.f ? v : p.mask_leak * v;
             if (p.round_out) v = rna_tf32(v);
-            orow[c0 + j] = v;
+            p.out[roff + c0 + j] = v;
           }
         }
       }
@@ -285,7 +325,8 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.ph_base[blockIdx.z]);
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.ph_base[blockIdx.z],
+                p.epi_stage ? smem_u32(smem) + (warp - 2) * TC_EPI_WARP_BYTES : 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -306,7 +347,7 @@ conv_tc_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUte
 // MMA warp issues for both and commits `empty` / `tmem_full` with a multicast arrive to both CTAs, each CTA's epilogue
 // warps drain their own TMEM half.  Operands that still need rounding are rounded by each CTA's warps 2..9 in its own
 // shared memory; they arrive on the leader's `ready` barrier (count 2 x 8 warps).
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2)
 conv_tc_pair_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__ CUtensorMap tm_b, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -437,7 +478,8 @@ conv_tc_pair_kernel(const __grid_constant__ AMaps tm_as, const __grid_constant__
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue(p, tmem_base, tile0, p.mt, nb0, warp, lane, p.ph_base[blockIdx.z]);
+    tc_epilogue(p, tmem_base, tile0, p.mt, nb0, warp, lane, p.ph_base[blockIdx.z],
+                p.epi_stage ? smem_u32(smem) + (warp - 2) * TC_EPI_WARP_BYTES : 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -587,7 +629,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.base);
+    tc_epilogue(p, tmem_base, tile0, nt_here, nb0, warp, lane, p.base,
+                p.epi_stage ? smem_u32(smem) + (warp - 2) * TC_EPI_WARP_BYTES : 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -714,6 +757,7 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
   p.rows_used = p.bw * p.bh * p.bni;
   p.img_n = n; p.img_h = gh; p.img_w = gw;
   p.relu = relu;
+  p.epi_stage = ctx->tc_epi;          // every ring below holds >= 40 KB >= 8 warps x TC_EPI_WARP_BYTES
   p.round_a = (ex && ex->a_prerounded) ? 0 : 1;
   if (ex) {
     p.round_out = ex->round_out; p.residual = ex->residual; p.mask = ex->mask; p.mask_leak = ex->mask_leak;
@@ -870,12 +914,16 @@ int cgan_conv_tc(cgan_ctx* ctx, const float* in, int nviews, const long long* vi
     for (int m = 4; m >= 2; --m)
       if (m * q.bn <= 512 && tiles_total * ncol_tiles * q.nphases >= 2ll * m * ctx->num_sms) { q.mt = m; break; }
     if (ctx->tc_mt_max < 2) q.mt = 1;
+    if (ctx->tc_pair_mt > 0 && ctx->tc_pair_mt * q.bn <= 512) q.mt = ctx->tc_pair_mt;       // experiment knob (CGAN_TC_PAIR_MT)
     const long long groups = (tiles_total + q.mt - 1) / q.mt;
     if (q.bn % 32 == 0 && q.bn >= 64 && groups * ncol_tiles * q.nphases >= ctx->num_sms) {
       const size_t stage_bytes = (size_t)q.mt * TC_A_BYTES + (size_t)(q.bn / 2) * TC_BK * 4;
-      q.stages = (int)((227 * 1024 - 1024 - 512) / stage_bytes);
+      // two CTA pairs per SM pair when the accumulators take at most half of the TMEM: one pair's epilogue then overlaps
+      // the other's main loop
+      const bool two_per_sm = q.mt * q.bn <= 256;
+      q.stages = (int)(((two_per_sm ? 113 : 227) * 1024 - 1024 - 512) / stage_bytes);
       if (q.stages > 6) q.stages = 6;
-      if (q.stages >= 3) {
+      if (q.stages >= 2) {
         q.tiles_total = (int)tiles_total;
         q.tmem_cols = 32;
         while (q.tmem_cols < q.mt * q.bn) q.tmem_cols *= 2;

@@ -331,9 +331,103 @@ __global__ void thin_reduce_kernel(float* __restrict__ out, const float* __restr
 
 }  // namespace
 
+// ---- 1x1 kernels over <= 4 input channels (the shortcut of BigGAN's first discriminator block, resnet_biggan.py:
+// a 3 -> ch pointwise conv at full image resolution) ----------------------------------------------------------------------
+// Both are streams over the [pixels, cout] tensor: the forward writes it once (thread = 4 output channels of one pixel,
+// filter rows in registers; residual add, ReLU and TF32 rounding fused), the filter gradient reads it once (thread =
+// output channel, PWT_U pixels in flight, one partial [cin, cout] per CTA).
+__device__ __forceinline__ float thin_rna(float v) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+template <int CIN>
+__global__ void fwd_pw_thin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ y, const float* __restrict__ residual, long long npix, int cout,
+                                   int ldy, int relu, int round_out) {
+  const int q = cout >> 2;                                   // float4 columns per pixel
+  const long long total = npix * q;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long pix = e / q;
+    const int c = (int)(e - pix * q) * 4;
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float xv = __ldg(x + pix * CIN + ci);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)ci * cout + c));
+      acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+    }
+    const long long o = pix * ldy + c;
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + o);
+      acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (round_out) { acc.x = thin_rna(acc.x); acc.y = thin_rna(acc.y); acc.z = thin_rna(acc.z); acc.w = thin_rna(acc.w); }
+    *reinterpret_cast<float4*>(y + o) = acc;
+  }
+}
+
+constexpr int PWT_U = 8;
+template <int CIN>
+__global__ void __launch_bounds__(128)
+wgrad_pw_thin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, long long npix,
+                     int cout, long long pix_per_block) {
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool co_ok = co < cout;
+  float acc[CIN];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+  const long long p0 = (long long)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  if (co_ok) {
+    long long pix = p0;
+    for (; pix + PWT_U <= p1; pix += PWT_U) {
+      float g[PWT_U];
+#pragma unroll
+      for (int u = 0; u < PWT_U; ++u) g[u] = __ldg(dy + (pix + u) * cout + co);
+#pragma unroll
+      for (int u = 0; u < PWT_U; ++u)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) acc[ci] = fmaf(__ldg(x + (pix + u) * CIN + ci), g[u], acc[ci]);
+    }
+    for (; pix < p1; ++pix) {
+      const float g = __ldg(dy + pix * cout + co);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) acc[ci] = fmaf(__ldg(x + pix * CIN + ci), g, acc[ci]);
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) partial[((size_t)blockIdx.x * CIN + ci) * cout + co] = acc[ci];
+  }
+}
+
+bool cgan_pw_thin_ok(const cgan_conv_desc* d) {       // 1x1, stride 1, <= 4 input channels: the pointwise stream kernels
+  return d->kh == 1 && d->kw == 1 && d->stride == 1 && !d->upsample && d->cin >= 1 && d->cin <= 4 && d->cout >= 16 &&
+         d->cout % 4 == 0 && d->oh == d->h && d->ow == d->w;
+}
+
+int cgan_fwd_pw_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                     const float* residual, int relu, int ldy, int round_out) {
+  const long long npix = (long long)d->n * d->h * d->w;
+  if (npix == 0) return CGAN_OK;
+  const long long total = npix * (d->cout / 4);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16ll * ctx->num_sms;
+  if (blocks > cap) blocks = cap;
+  switch (d->cin) {
+    case 1: fwd_pw_thin_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, w, bias, y, residual, npix, d->cout, ldy, relu, round_out); break;
+    case 2: fwd_pw_thin_kernel<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, w, bias, y, residual, npix, d->cout, ldy, relu, round_out); break;
+    case 3: fwd_pw_thin_kernel<3><<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, w, bias, y, residual, npix, d->cout, ldy, relu, round_out); break;
+    default: fwd_pw_thin_kernel<4><<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, w, bias, y, residual, npix, d->cout, ldy, relu, round_out); break;
+  }
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
 bool cgan_wgrad_thin_ok(const cgan_conv_desc* d) {
   if ((long long)d->n * d->oh * d->ow >= (1ll << 31)) return false;      // 32-bit pixel arithmetic in the kernels
   int m = d->kh * d->kw * d->cin;
+  if (cgan_pw_thin_ok(d)) return true;
   if (d->cin <= 4 && (m == 9 || m == 18 || m == 27 || m == 36) && d->kh == 3 && d->kw == 3) return true;
   if (d->cout <= 4 && d->cout == 3 && d->kh == 3 && d->kw == 3) return true;
   return false;
@@ -346,6 +440,29 @@ int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, cons
   p.vw = d->upsample ? 2 * d->w : d->w;
   p.npix = (long long)d->n * d->oh * d->ow;
   if (p.npix >= (1ll << 31)) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: more than 2^31 output pixels%s", "cgan_wgrad_thin");
+  if (cgan_pw_thin_ok(d)) {
+    const int co_blocks = (d->cout + 127) / 128;
+    long long want = 8ll * ctx->num_sms / co_blocks;
+    long long ppb = (p.npix + want - 1) / want;
+    ppb = (ppb + PWT_U - 1) / PWT_U * PWT_U;
+    const int blocks = (int)((p.npix + ppb - 1) / ppb);
+    const long long wn = (long long)d->cin * d->cout;
+    void* ws = nullptr;
+    int rc = cgan_ws(ctx, (size_t)blocks * wn * sizeof(float), &ws);
+    if (rc) return rc;
+    float* partial = reinterpret_cast<float*>(ws);
+    dim3 grid(blocks, co_blocks);
+    switch (d->cin) {
+      case 1: wgrad_pw_thin_kernel<1><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, p.npix, d->cout, ppb); break;
+      case 2: wgrad_pw_thin_kernel<2><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, p.npix, d->cout, ppb); break;
+      case 3: wgrad_pw_thin_kernel<3><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, p.npix, d->cout, ppb); break;
+      default: wgrad_pw_thin_kernel<4><<<grid, 128, 0, ctx->stream>>>(x, dy, partial, p.npix, d->cout, ppb); break;
+    }
+    CGAN_LAUNCHED(ctx);
+    thin_reduce_kernel<<<cdiv(wn, 256), 256, 0, ctx->stream>>>(dw, partial, wn, blocks);
+    CGAN_LAUNCHED(ctx);
+    return CGAN_OK;
+  }
   if (d->cin <= 4 && d->kh == 3 && d->kw == 3) {
     Thin3Params q;
     const int co_blocks = (d->cout + 127) / 128;

@@ -46,8 +46,11 @@ int64_t cgan_launch_count(cgan_ctx* ctx);
  *                       instead of one box per tap: 0 never, 1 where it measured faster (operand rounded in the kernel,
  *                       >= 256 output channels; default), 2 wherever the geometry allows.
  *   CGAN_OPT_TC_PAIR    (set/get) 1: tcgen05 convolutions run as CTA pairs (cta_group::2, M = 256) sharing each weight tile.
+ *   CGAN_OPT_TC_EPI     (set/get) 1 (default): the tcgen05 convolution epilogue transposes each 32 x 32 accumulator chunk through
+ *                       shared memory so that stores (and the fused residual / mask reads) cover whole 128-byte lines;
+ *                       0: every thread stores its own row (the round-1 epilogue; results are bit-identical).
  *   CGAN_OPT_LAST_PATH  (get) CGAN_PATH_* taken by the most recent conv2d_fwd / dgrad / wgrad / gemm_batched call. */
-enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3, CGAN_OPT_TC_PAIR = 4 };
+enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3, CGAN_OPT_TC_PAIR = 4, CGAN_OPT_TC_EPI = 5 };
 enum { CGAN_PATH_SIMT_FP32 = 0, CGAN_PATH_TCGEN05_TF32 = 1, CGAN_PATH_THIN_FP32 = 2 };
 int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value);
 int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value);

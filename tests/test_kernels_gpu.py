@@ -38,6 +38,8 @@ CONV_CASES = [
     (3, 4, 8, 8, 3, 1, True),
     (2, 8, 16, 24, 4, 2, False),
     (2, 8, 16, 16, 1, 1, False),
+    (3, 10, 3, 96, 1, 1, False),       # pointwise conv over image channels (BigGAN D B1 shortcut): the streaming 1x1 kernels
+    (2, 7, 4, 20, 1, 1, False),
     (2, 4, 8, 8, 1, 1, True),
     (2, 9, 5, 7, 5, 2, False),
     (2, 8, 32, 3, 3, 1, False),
@@ -70,6 +72,46 @@ def test_conv2d_fwd_dgrad_wgrad(K, n, h, cin, cout, k, stride, up):
   assert_close(gx.cpu(), xt.grad.numpy(), TOL, "conv dgrad")
   assert_close(gw.cpu(), wt.grad.numpy(), TOL, "conv wgrad")
   assert_close(gb.cpu(), bt.grad.numpy(), TOL, "conv bias grad")
+
+
+@pytest.mark.parametrize("mode,n,h,cin,cout,k,up", [
+    (0, 3, 10, 3, 96, 1, False),        # pointwise stream kernel (residual fused in the kernel)
+    (0, 2, 12, 3, 32, 3, False),        # 3x3 image-side kernel + post pass
+    (0, 2, 8, 16, 24, 3, False),        # exact fp32 SIMT + post pass
+    (1, 4, 16, 64, 64, 3, False),       # tcgen05 epilogue
+    (1, 4, 8, 64, 96, 3, True),         # tcgen05, sub-pixel phases
+    (1, 4, 8, 64, 64, 1, True),         # 1x1 over the zero-inserted input (phase 0 + bias phases + post pass)
+])
+def test_conv2d_fused_epilogue(K, mode, n, h, cin, cout, k, up):
+  """conv2d(..., relu, residual) == relu(conv2d(...) + residual) on every forward path, and the gradients flow to the
+  residual, the input and the filter as in the unfused composition."""
+  from compare_gan_b200 import tape
+  rng = np.random.RandomState(cin * cout + k)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) * 0.1).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  oh = 2 * h if up else h
+  r = rng.randn(n, oh, oh, cout).astype(np.float32)
+  gy = rng.randn(n, oh, oh, cout).astype(np.float32)
+  K.set_math_mode(mode)
+  try:
+    outs = []
+    for fused in (True, False):
+      xd, wd, bd, rd = dev(K, x, True), dev(K, w, True), dev(K, b, True), dev(K, r, True)
+      if fused:
+        y = K.conv2d(xd, wd, bd, upsample=up, relu=True, residual=rd)
+      else:
+        y = K.relu(K.add(K.conv2d(xd, wd, bd, upsample=up), rd))
+      grads = tape_grads(K, y, gy, [xd, wd, bd, rd])
+      outs.append([y.cpu()] + [g.cpu() for g in grads])
+  finally:
+    K.set_math_mode(0)
+  for a, c, what in zip(outs[0], outs[1], ("output", "dx", "dw", "dbias", "dresidual")):
+    # math_mode 1: the fused path hands the ReLU gradient to the contractions TF32-rounded (3e-4 operand noise)
+    assert_close(a, c, 1e-5 if mode == 0 else 1e-3, "fused vs composed " + what)
+  xt = torch.from_numpy(x)
+  ref = torch.relu(T.conv2d_same(T.unpool(xt) if up else xt, torch.from_numpy(w), 1) + torch.from_numpy(b) + torch.from_numpy(r))
+  assert_close(outs[0][0], ref.numpy(), TOL if mode == 0 else 2e-3, "fused conv epilogue vs oracle")
 
 
 @pytest.mark.parametrize("k,stride,h", [(4, 2, 4), (3, 1, 6), (5, 2, 5)])

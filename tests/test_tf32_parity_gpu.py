@@ -62,16 +62,20 @@ its deterministic split-K grouping follows the CTA count), and match the fp32
   lib = K.lib()
   try:
     res = {}
-    for halo, mt, pair in ((2, 2, 0), (2, 1, 0), (0, 2, 0), (0, 1, 0), (0, 2, 1)):
+    for halo, mt, pair, epi in ((2, 2, 0, 1), (2, 1, 0, 1), (0, 2, 0, 1), (0, 1, 0, 1), (0, 2, 1, 1), (0, 2, 0, 0)):
         lib.set_option(_lib.OPT_TC_MT, mt)
         lib.set_option(_lib.OPT_TC_HALO, halo)
         lib.set_option(_lib.OPT_TC_PAIR, pair)
+        lib.set_option(_lib.OPT_TC_EPI, epi)
         xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
         y = K.conv2d(xd, wd, bd, stride=1, upsample=up)
         assert lib.get_option(_lib.OPT_LAST_PATH) == 1, "expected the tcgen05 path"
         gx, gw = tape.backward([(y, dev(K, gy))], [xd, wd], K.add_grad)
-        res[(halo, mt) if not pair else "pair"] = (y.cpu(), gx.cpu(), gw.cpu())
+        res["pair" if pair else (halo, mt) if epi else "rowwise"] = (y.cpu(), gx.cpu(), gw.cpu())
         del xd, wd, bd, y, gx, gw
+    # the coalescing epilogue (32 x 32 chunks transposed through shared memory) only changes which thread stores a value
+    for a, c, what in zip(res["rowwise"][:2], res[0, 2][:2], ("forward", "input gradient")):
+      np.testing.assert_array_equal(a, c, err_msg="%s: transposing epilogue differs from per-thread rows (%s)" % (name, what))
     # CTA pairs (cta_group::2, M = 256, each CTA holding half of the weight tile) vs single CTAs: same products, same order
     for a, c, what in zip(res["pair"][:2], res[0, 2][:2], ("forward", "input gradient")):
       assert_close(a, c, 1e-6, "%s: CTA pairs vs single CTAs (%s)" % (name, what))
@@ -90,6 +94,7 @@ its deterministic split-K grouping follows the CTA count), and match the fp32
     lib.set_option(_lib.OPT_TC_MT, 2)
     lib.set_option(_lib.OPT_TC_HALO, 1)
     lib.set_option(_lib.OPT_TC_PAIR, PAIR_DEFAULT)
+    lib.set_option(_lib.OPT_TC_EPI, 1)
     K.set_math_mode(0)
   sel = np.r_[0:4, n - 4:n]
   xt = torch.from_numpy(x[sel]).requires_grad_(True)
