@@ -113,6 +113,10 @@ class Lib(object):
     self.call("ctx_get_option", int(key), ctypes.byref(v))
     return int(v.value)
 
+  def attention_supported(self, batch, lq, lk, dk, dv):
+    """cgan_attention_supported: 1 / 0, not an error code."""
+    return bool(self.fn["cgan_attention_supported"](self.ctx, int(batch), int(lq), int(lk), int(dk), int(dv)))
+
   def close(self):
     if self.ctx:
       self.fn["cgan_ctx_destroy"](self.ctx)

@@ -259,17 +259,18 @@ def non_local_block(x, name, use_sn):
     n, h, w, num_channels = x.shape
     num_channels_attn = num_channels // 8
     num_channels_g = num_channels // 2
-    theta = conv1x1(x, num_channels_attn, name="conv2d_theta", use_sn=use_sn, use_bias=False)
+    # the fused attention kernel reads theta / phi / g as TF32 operands: their producers store them rounded
+    fused = K.attention_shape_ok(n, h * w, h * w // 4, num_channels_attn, num_channels_g)
+    theta = conv1x1(x, num_channels_attn, name="conv2d_theta", use_sn=use_sn, use_bias=False, _tf32=fused)
     theta = K.reshape(theta, n, h * w, num_channels_attn)
-    phi = conv1x1(x, num_channels_attn, name="conv2d_phi", use_sn=use_sn, use_bias=False)
+    phi = conv1x1(x, num_channels_attn, name="conv2d_phi", use_sn=use_sn, use_bias=False, _tf32=fused)
     phi = K.maxpool2(phi)
     phi = K.reshape(phi, n, h * w // 4, num_channels_attn)
-    attn = K.bmm(theta, phi, False, True)
-    attn = K.softmax(attn)
-    g = conv1x1(x, num_channels_g, name="conv2d_g", use_sn=use_sn, use_bias=False)
+    g = conv1x1(x, num_channels_g, name="conv2d_g", use_sn=use_sn, use_bias=False, _tf32=fused)
     g = K.maxpool2(g)
     g = K.reshape(g, n, h * w // 4, num_channels_g)
-    attn_g = K.bmm(attn, g)
+    # attn = softmax(theta phi^T); attn_g = attn g (arch_ops.py:744-753): one fused kernel where the shape allows
+    attn_g = K.attention(theta, phi, g)
     attn_g = K.reshape(attn_g, n, h, w, num_channels_g)
     sigma = V.get_variable("sigma", (), zeros_init)
     attn_g = conv1x1(attn_g, num_channels, name="conv2d_attn_g", use_sn=use_sn, use_bias=False)

@@ -1,0 +1,717 @@
+// Fused self-attention of the non-local block (arch_ops.py:734-753) on tcgen05 — math_mode 1.
+//
+//   O[i] = softmax(Q[i] K[i]^T) V[i]          Q = theta [Lq, dk], K = phi [Lk, dk], V = g [Lk, dv] per image i
+//
+// The reference materialises the [Lq, Lk] score matrix (tf.matmul -> tf.nn.softmax -> tf.matmul); at BigGAN-128 that is
+// 4096 x 1024 floats per image, 4.3 GB per batch of 256, crossing HBM three times per direction.  Here the scores never
+// leave the SM: S tiles are produced by tcgen05.mma into TMEM, read by the softmax warps with tcgen05.ld, exponentiated,
+// written as TF32 into a 128B-swizzled K-major shared-memory tile and consumed from there by the second tcgen05.mma.
+//
+// Forward (attn_fwd_kernel): one CTA per 128 queries of one image, key tiles of 64.
+//   pass 1: S_j = Q K_j^T (M=128, N=64, K=8 per MMA, dk <= 32 zero-padded by TMA) -> row maxima m.
+//   pass 2: S_j again (K has 4x fewer channels than V: recomputing costs 1/4 of the P V MMAs and avoids rescaling O in
+//           TMEM), p = exp(s - m), l += p, P -> smem, O += P V_j (V is MN-major as it lies in HBM: the filter-gradient
+//           kernel's SWIZZLE_128B_BASE32B operand form).  Epilogue: O / l, lse = m + log l (kept for the backward).
+// Backward: P is recomputed from Q, K and lse (no [Lq, Lk] tensor is ever stored); with D = rowsum(dO * O),
+//   dS = P * (dO V^T - D),  dQ = dS K,  dK = dS^T Q,  dV = P^T dO.
+//   attn_bwd_dq_kernel: one CTA per 128 queries, loops over key tiles (accumulates dQ in TMEM);
+//   attn_bwd_dkv_kernel: one CTA per 128 keys, loops over query tiles of 64 (accumulates dK, dV in TMEM) — S^T and dP^T
+//   are produced directly (M = keys), so no transposition pass exists and the summation order is fixed (deterministic).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = softmax / epilogue
+// (one thread per accumulator row = TMEM lane).
+//
+// Operands are consumed as TF32: callers pass tensors already rounded to the nearest TF32 value (cgan_round_tf32 or a
+// producer's ROUND_OUT epilogue); P and dS are rounded to nearest by the softmax warps.  Accumulation is fp32 in TMEM.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TQ = 128;          // rows per CTA (UMMA M)
+constexpr int AT_TK = 64;           // columns per score tile (UMMA N of the score MMAs)
+constexpr float AT_LOG2E = 1.4426950408889634f;
+
+struct AtParams {
+  int lq, lk, dk, dv;
+  int kq;               // MMA k-steps of the score contraction: ceil(dk / 8)
+  int kv;               // MMA k-steps of a contraction over dv: ceil(dv / 8)
+  int vg;               // 32-channel groups of V / dO: ceil(dv / 32)
+  int nv;               // UMMA N of the contractions producing dv columns (dv, a multiple of 16)
+  float* out;           // fwd: O          dq: dQ        dkv: dK
+  float* out2;          // fwd: lse        dq: -         dkv: dV
+  const float* lse;     // bwd
+  const float* dsum;    // bwd: D = rowsum(dO * O)
+};
+
+// K-major, 128B-swizzled operand (rows x 32 fp32 = 128 B per row, 8-row groups 1024 B apart) — as conv_tc.cu
+__device__ __forceinline__ uint64_t desc_k(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major 32-bit operand, SWIZZLE_128B_BASE32B: 32-channel groups 4096 B apart (LBO), 4-row groups 512 B apart (SBO) — as
+// wgrad_tc.cu
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, M = 128, N = n; b_mn: B operand MN-major
+__device__ __forceinline__ uint32_t idesc(int n, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(AT_TQ >> 4) << 24);
+}
+
+// mbarrier wait that traps instead of hanging the device if a protocol error ever leaves a barrier incomplete
+__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one 128-byte row (32 floats) of a K-major 128B-swizzled [rows x 32] chunk: 16-byte unit u of row r lives at unit u ^ (r & 7)
+__device__ __forceinline__ void store_row32(uint32_t chunk_base, int row, const float (&v)[32]) {
+  const uint32_t ra = chunk_base + (uint32_t)row * 128u;
+  const int x = row & 7;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) sts128(ra + (uint32_t)((u ^ x) << 4), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// rows of `dst` (dv floats each) from an accumulator at TMEM column `col`, scaled
+__device__ __forceinline__ void store_acc_row(float* dst, uint32_t taddr, int ncols, float scale) {
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)c0, r);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (c0 + j < ncols)
+        *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale,
+                                                                __uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------ forward
+// shared memory: Q 16 KB | K ring 2 x 8 KB | V vg x 2 x 4 KB | P 32 KB | barriers.  TMEM: S0 @0, S1 @64, O @128 (256 columns).
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const AtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int v_bytes = p.vg * 2 * 4096;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = sV + v_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* s_empty = bars + 7;       // 2
+  uint64_t* v_full = bars + 9;
+  uint64_t* v_empty = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* p_empty = bars + 12;
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_TQ, img = blockIdx.y;
+  const int nkt = p.lk / AT_TK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
+      }
+      mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 256);
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 16384);
+      tma_load_4d(sQ, &tm_q, q_full, 0, q0, 0, img);
+      for (int it = 0; it < 2 * nkt; ++it) {
+        const int s = it & 1, j = it < nkt ? it : it - nkt;
+        bwait(&k_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[s], 8192);
+        tma_load_4d(sK + s * 8192, &tm_k, &k_full[s], 0, j * AT_TK, 0, img);
+        if (it >= nkt) {
+          bwait(v_empty, (j & 1) ^ 1);
+          mbar_expect_tx(v_full, (uint32_t)v_bytes);
+          for (int kb = 0; kb < 2; ++kb)
+            for (int g = 0; g < p.vg; ++g)
+              tma_load_4d(sV + (kb * p.vg + g) * 4096, &tm_v, v_full, g * 32, j * AT_TK + kb * 32, 0, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t id_s = idesc(AT_TK, 0), id_pv = idesc(p.nv, 1);
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+    bwait(q_full, 0);
+    auto issue_s = [&](int it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      bwait(&k_full[s], ph);
+      bwait(&s_empty[s], ph ^ 1);
+      fence_after();
+      if (lane == 0) {
+        for (int k = 0; k < p.kq; ++k)
+          umma_tf32(tmem + (uint32_t)(s * AT_TK), desc_k(aQ + k * 32), desc_k(aK + s * 8192 + k * 32), id_s, k ? 1u : 0u);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    for (int it = 0; it < nkt; ++it) issue_s(it);          // pass 1: scores for the row maxima
+    issue_s(nkt);
+    for (int j = 0; j < nkt; ++j) {
+      if (j + 1 < nkt) issue_s(nkt + j + 1);
+      bwait(p_full, j & 1);
+      bwait(v_full, j & 1);
+      fence_after();
+      if (lane == 0) {
+        for (int kk = 0; kk < AT_TK / 8; ++kk)
+          umma_tf32(tmem + 128, desc_k(aP + (kk >> 2) * 16384 + (kk & 3) * 32),
+                    desc_mn(aV + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_pv, (j | kk) ? 1u : 0u);
+        umma_commit(p_empty);
+        umma_commit(v_empty);
+        if (j == nkt - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t aP = smem_u32(sP);
+    float m = -INFINITY;
+    for (int it = 0; it < nkt; ++it) {
+      const int s = it & 1;
+      bwait(&s_full[s], (it >> 1) & 1);
+      fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld32(tl + (uint32_t)(s * AT_TK + h * 32), r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+    const float m2 = m * AT_LOG2E;
+    float l = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      const int it = nkt + j, s = it & 1;
+      bwait(&s_full[s], (it >> 1) & 1);
+      fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tl + (uint32_t)(s * AT_TK), r0);
+      tmem_ld32(tl + (uint32_t)(s * AT_TK + 32), r1);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      float pv[32];
+      bwait(p_empty, (j & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r0[i]), AT_LOG2E, -m2))); l += pv[i]; }
+      store_row32(aP, row, pv);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r1[i]), AT_LOG2E, -m2))); l += pv[i]; }
+      store_row32(aP + 16384, row, pv);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    bwait(o_full, 0);
+    fence_after();
+    const long long grow = (long long)img * p.lq + q0 + row;
+    store_acc_row(p.out + grow * p.dv, tl + 128, p.dv, 1.0f / l);
+    p.out2[grow] = m + logf(l);
+    fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------- backward: dQ
+// shared memory: Q 16 KB | dO vg x 16 KB | K (K-major, 64 keys) 8 KB | V (K-major, 64 keys) vg x 8 KB | K (MN-major) 8 KB |
+// dS 32 KB | barriers.  TMEM (512 columns): buffer b @ b*128: S @+0, dP @+64; dQ @256.
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
+                   const __grid_constant__ CUtensorMap tm_km, const AtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sKk = sdO + p.vg * 16384;
+  uint8_t* sVk = sKk + 8192;
+  uint8_t* sKm = sVk + p.vg * 8192;
+  uint8_t* sdS = sKm + 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* km_full = bars + 1;
+  uint64_t* km_empty = bars + 2;
+  uint64_t* mn_full = bars + 3;
+  uint64_t* mn_empty = bars + 4;
+  uint64_t* sd_full = bars + 5;       // 2
+  uint64_t* sd_empty = bars + 7;      // 2
+  uint64_t* ds_full = bars + 9;
+  uint64_t* ds_empty = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_TQ, img = blockIdx.y;
+  const int nkt = p.lk / AT_TK;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1); mbar_init(km_full, 1); mbar_init(km_empty, 1); mbar_init(mn_full, 1); mbar_init(mn_empty, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], 4); }
+      mbar_init(ds_full, 4); mbar_init(ds_empty, 1); mbar_init(dq_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, (uint32_t)(16384 + p.vg * 16384));
+      tma_load_4d(sQ, &tm_q, q_full, 0, q0, 0, img);
+      for (int g = 0; g < p.vg; ++g) tma_load_4d(sdO + g * 16384, &tm_do, q_full, g * 32, q0, 0, img);
+      for (int j = 0; j < nkt; ++j) {
+        const uint32_t ph = j & 1;
+        bwait(km_empty, ph ^ 1);
+        mbar_expect_tx(km_full, (uint32_t)(8192 + p.vg * 8192));
+        tma_load_4d(sKk, &tm_k, km_full, 0, j * AT_TK, 0, img);
+        for (int g = 0; g < p.vg; ++g) tma_load_4d(sVk + g * 8192, &tm_vk, km_full, g * 32, j * AT_TK, 0, img);
+        bwait(mn_empty, ph ^ 1);
+        mbar_expect_tx(mn_full, 8192);
+        for (int kb = 0; kb < 2; ++kb) tma_load_4d(sKm + kb * 4096, &tm_km, mn_full, 0, j * AT_TK + kb * 32, 0, img);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t id_s = idesc(AT_TK, 0), id_dq = idesc(32, 1);
+    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKm = smem_u32(sKm),
+                   adS = smem_u32(sdS);
+    bwait(q_full, 0);
+    auto issue_sd = [&](int j) {
+      const int b = j & 1;
+      bwait(km_full, j & 1);
+      bwait(&sd_empty[b], ((j >> 1) & 1) ^ 1);
+      fence_after();
+      if (lane == 0) {
+        for (int k = 0; k < p.kq; ++k)
+          umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aQ + k * 32), desc_k(aKk + k * 32), id_s, k ? 1u : 0u);
+        for (int kk = 0; kk < p.kv; ++kk)
+          umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(adO + (kk >> 2) * 16384 + (kk & 3) * 32),
+                    desc_k(aVk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
+        umma_commit(km_empty);
+        umma_commit(&sd_full[b]);
+      }
+      __syncwarp();
+    };
+    issue_sd(0);
+    for (int j = 0; j < nkt; ++j) {
+      if (j + 1 < nkt) issue_sd(j + 1);
+      bwait(ds_full, j & 1);
+      bwait(mn_full, j & 1);
+      fence_after();
+      if (lane == 0) {
+        for (int kk = 0; kk < AT_TK / 8; ++kk)
+          umma_tf32(tmem + 256, desc_k(adS + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aKm + (kk >> 2) * 4096 + (kk & 3) * 1024),
+                    id_dq, (j | kk) ? 1u : 0u);
+        umma_commit(ds_empty);
+        umma_commit(mn_empty);
+        if (j == nkt - 1) umma_commit(dq_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t adS = smem_u32(sdS);
+    const long long grow = (long long)img * p.lq + q0 + row;
+    const float lse2 = p.lse[grow] * AT_LOG2E, dsum = p.dsum[grow];
+    for (int j = 0; j < nkt; ++j) {
+      const int b = j & 1;
+      bwait(&sd_full[b], (j >> 1) & 1);
+      fence_after();
+      float ds[2][32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tl + (uint32_t)(b * 128 + h * 32), rs);
+        tmem_ld32(tl + (uint32_t)(b * 128 + 64 + h * 32), rd);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          ds[h][i] = rna_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sd_empty[b]);
+      bwait(ds_empty, (j & 1) ^ 1);
+      store_row32(adS, row, ds[0]);
+      store_row32(adS + 16384, row, ds[1]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    bwait(dq_full, 0);
+    fence_after();
+    store_acc_row(p.out + grow * p.dk, tl + 256, p.dk, 1.0f);
+    fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- backward: dK, dV
+// One CTA per 128 keys; query tiles of 64.  S^T = K Q^T and dP^T = V dO^T (M = keys, N = queries) so that P^T and dS^T come out
+// in the A-operand orientation of dV += P^T dO and dK += dS^T Q.
+// shared memory: K 16 KB | V vg x 16 KB | Q (K-major, 64 q) 8 KB | dO (K-major, 64 q) vg x 8 KB | Q (MN-major) 8 KB |
+// dO (MN-major) vg x 8 KB | P^T 32 KB | dS^T 32 KB | lse, D of the query tile 2 x 2 x 64 floats | barriers.
+// TMEM (512 columns): buffer b @ b*128: S^T @+0, dP^T @+64; dK @256; dV @320.
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
+                    const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_qm, const __grid_constant__ CUtensorMap tm_dom, const AtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + 16384;
+  uint8_t* sQk = sV + p.vg * 16384;
+  uint8_t* sdOk = sQk + 8192;
+  uint8_t* sQm = sdOk + p.vg * 8192;
+  uint8_t* sdOm = sQm + 8192;
+  uint8_t* sPt = sdOm + p.vg * 8192;
+  uint8_t* sdSt = sPt + 32768;
+  float* sL = reinterpret_cast<float*>(sdSt + 32768);        // [2][64] lse * log2(e)
+  float* sD = sL + 128;                                      // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
+  uint64_t* kv_full = bars;
+  uint64_t* qk_full = bars + 1;
+  uint64_t* qk_empty = bars + 2;
+  uint64_t* qm_full = bars + 3;
+  uint64_t* qm_empty = bars + 4;
+  uint64_t* sd_full = bars + 5;       // 2
+  uint64_t* sd_empty = bars + 7;      // 2
+  uint64_t* pt_full = bars + 9;
+  uint64_t* pt_empty = bars + 10;
+  uint64_t* acc_full = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * AT_TQ, img = blockIdx.y;
+  const int nqt = p.lq / AT_TK;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1); mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(qm_full, 1); mbar_init(qm_empty, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], 4); }
+      mbar_init(pt_full, 4); mbar_init(pt_empty, 1); mbar_init(acc_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, (uint32_t)(16384 + p.vg * 16384));
+      tma_load_4d(sK, &tm_k, kv_full, 0, k0, 0, img);
+      for (int g = 0; g < p.vg; ++g) tma_load_4d(sV + g * 16384, &tm_vk, kv_full, g * 32, k0, 0, img);
+      for (int i = 0; i < nqt; ++i) {
+        const uint32_t ph = i & 1;
+        bwait(qk_empty, ph ^ 1);
+        mbar_expect_tx(qk_full, (uint32_t)(8192 + p.vg * 8192));
+        tma_load_4d(sQk, &tm_q, qk_full, 0, i * AT_TK, 0, img);
+        for (int g = 0; g < p.vg; ++g) tma_load_4d(sdOk + g * 8192, &tm_do, qk_full, g * 32, i * AT_TK, 0, img);
+        bwait(qm_empty, ph ^ 1);
+        mbar_expect_tx(qm_full, (uint32_t)(8192 + p.vg * 8192));
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_4d(sQm + kb * 4096, &tm_qm, qm_full, 0, i * AT_TK + kb * 32, 0, img);
+          for (int g = 0; g < p.vg; ++g)
+            tma_load_4d(sdOm + (kb * p.vg + g) * 4096, &tm_dom, qm_full, g * 32, i * AT_TK + kb * 32, 0, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t id_s = idesc(AT_TK, 0), id_dk = idesc(32, 1), id_dv = idesc(p.nv, 1);
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQk = smem_u32(sQk), adOk = smem_u32(sdOk), aQm = smem_u32(sQm),
+                   adOm = smem_u32(sdOm), aPt = smem_u32(sPt), adSt = smem_u32(sdSt);
+    bwait(kv_full, 0);
+    auto issue_sd = [&](int i) {
+      const int b = i & 1;
+      bwait(qk_full, i & 1);
+      bwait(&sd_empty[b], ((i >> 1) & 1) ^ 1);
+      fence_after();
+      if (lane == 0) {
+        for (int k = 0; k < p.kq; ++k)
+          umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aK + k * 32), desc_k(aQk + k * 32), id_s, k ? 1u : 0u);
+        for (int kk = 0; kk < p.kv; ++kk)
+          umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(aV + (kk >> 2) * 16384 + (kk & 3) * 32),
+                    desc_k(adOk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
+        umma_commit(qk_empty);
+        umma_commit(&sd_full[b]);
+      }
+      __syncwarp();
+    };
+    issue_sd(0);
+    for (int i = 0; i < nqt; ++i) {
+      if (i + 1 < nqt) issue_sd(i + 1);
+      bwait(pt_full, i & 1);
+      bwait(qm_full, i & 1);
+      fence_after();
+      if (lane == 0) {
+        for (int kk = 0; kk < AT_TK / 8; ++kk)
+          umma_tf32(tmem + 320, desc_k(aPt + (kk >> 2) * 16384 + (kk & 3) * 32),
+                    desc_mn(adOm + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_dv, (i | kk) ? 1u : 0u);
+        for (int kk = 0; kk < AT_TK / 8; ++kk)
+          umma_tf32(tmem + 256, desc_k(adSt + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aQm + (kk >> 2) * 4096 + (kk & 3) * 1024),
+                    id_dk, (i | kk) ? 1u : 0u);
+        umma_commit(pt_empty);
+        umma_commit(qm_empty);
+        if (i == nqt - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const int st = threadIdx.x - 64;             // 0..127 among the softmax threads
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t aPt = smem_u32(sPt), adSt = smem_u32(sdSt);
+    for (int i = 0; i < nqt; ++i) {
+      const int b = i & 1;
+      // this tile's per-query lse and D (columns here): staged once, read as broadcasts.  Buffer b was last read two tiles
+      // ago, and every softmax thread has passed the barrier of the tile in between.
+      if (st < AT_TK) {
+        const long long gq = (long long)img * p.lq + i * AT_TK + st;
+        sL[b * AT_TK + st] = p.lse[gq] * AT_LOG2E;
+        sD[b * AT_TK + st] = p.dsum[gq];
+      }
+      softmax_bar();
+      bwait(&sd_full[b], (i >> 1) & 1);
+      fence_after();
+      float pt[2][32], ds[2][32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tl + (uint32_t)(b * 128 + h * 32), rs);
+        tmem_ld32(tl + (uint32_t)(b * 128 + 64 + h * 32), rd);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float pe = ex2(fmaf(__uint_as_float(rs[c]), AT_LOG2E, -sL[b * AT_TK + h * 32 + c]));
+          pt[h][c] = rna_tf32(pe);
+          ds[h][c] = rna_tf32(pe * (__uint_as_float(rd[c]) - sD[b * AT_TK + h * 32 + c]));
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sd_empty[b]);
+      bwait(pt_empty, (i & 1) ^ 1);
+      store_row32(aPt, row, pt[0]);
+      store_row32(aPt + 16384, row, pt[1]);
+      store_row32(adSt, row, ds[0]);
+      store_row32(adSt + 16384, row, ds[1]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+    }
+    bwait(acc_full, 0);
+    fence_after();
+    const long long grow = (long long)img * p.lk + k0 + row;
+    store_acc_row(p.out + grow * p.dk, tl + 256, p.dk, 1.0f);
+    store_acc_row(p.out2 + grow * p.dv, tl + 320, p.dv, 1.0f);
+    fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void round_tf32_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = rna_tf32(x[i]);
+}
+
+// [batch, rows, ch] fp32 tensor seen as {ch, rows, 1, batch}; box = 32 channels x box_rows rows
+bool make_rows_map(CUtensorMap* tm, const float* base, int ch, int rows, int batch, int box_rows, bool mn_major) {
+  return make_act_map(tm, base, ch, rows, 1, batch, ch, (long long)rows * ch, (long long)rows * ch, box_rows, 1, 1,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+bool shape_ok(int batch, int lq, int lk, int dk, int dv) {
+  return batch >= 1 && batch <= 65535 && lq >= 128 && lq % 128 == 0 && lk >= 128 && lk % 128 == 0 && dk >= 4 && dk <= 32 &&
+         dk % 4 == 0 && dv >= 16 && dv <= 128 && dv % 16 == 0;
+}
+
+void fill_params(AtParams* p, int lq, int lk, int dk, int dv) {
+  memset(p, 0, sizeof(*p));
+  p->lq = lq; p->lk = lk; p->dk = dk; p->dv = dv;
+  p->kq = (dk + 7) / 8; p->kv = (dv + 7) / 8; p->vg = (dv + 31) / 32; p->nv = dv;
+}
+
+template <typename F>
+int set_smem(cgan_ctx* ctx, F* kernel, size_t bytes, const char* who) {
+  if (bytes > 227 * 1024) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: shared memory%s", who);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
+  return CGAN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgan_round_tf32(cgan_ctx* ctx, float* y, const float* x, int64_t n) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, y && x && n >= 0, "bad argument");
+  if (n == 0) return CGAN_OK;
+  long long blocks = (n + 255) / 256, cap = (long long)ctx->num_sms * 16;
+  round_tf32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(y, x, n);
+  CGAN_LAUNCHED(ctx);
+  return CGAN_OK;
+}
+
+int cgan_attention_supported(cgan_ctx* ctx, int batch, int lq, int lk, int dk, int dv) {
+  return (ctx && ctx->math_mode == 1 && shape_ok(batch, lq, lk, dk, dv) && get_encode()) ? 1 : 0;
+}
+
+int cgan_attention_fwd(cgan_ctx* ctx, const float* q, const float* k, const float* v, float* out, float* lse, int batch, int lq,
+                       int lk, int dk, int dv) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, q && k && v && out && lse, "null pointer");
+  if (!cgan_attention_supported(ctx, batch, lq, lk, dk, dv))
+    return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: needs math_mode 1, lq, lk multiples of 128, dk <= 32 (x4), dv <= 128 (x16)%s",
+                     "cgan_attention_fwd");
+  AtParams p;
+  fill_params(&p, lq, lk, dk, dv);
+  p.out = out; p.out2 = lse;
+  CUtensorMap tq, tk, tv;
+  if (!make_rows_map(&tq, q, dk, lq, batch, 128, false) || !make_rows_map(&tk, k, dk, lk, batch, 64, false) ||
+      !make_rows_map(&tv, v, dv, lk, batch, 32, true))
+    return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_fwd");
+  const size_t smem = 32768 + (size_t)p.vg * 8192 + 32768 + 256 + 1024;
+  int rc = set_smem(ctx, attn_fwd_kernel, smem, "cgan_attention_fwd");
+  if (rc) return rc;
+  attn_fwd_kernel<<<dim3(lq / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tq, tk, tv, p);
+  CGAN_LAUNCHED(ctx);
+  ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+  return CGAN_OK;
+}
+
+int cgan_attention_bwd(cgan_ctx* ctx, const float* q, const float* k, const float* v, const float* out, const float* lse,
+                       const float* dout, float* dq, float* dk_out, float* dv_out, int batch, int lq, int lk, int dk, int dv) {
+  if (!ctx) return CGAN_ERR_ARG;
+  CGAN_REQUIRE(ctx, q && k && v && out && lse && dout && dq && dk_out && dv_out, "null pointer");
+  if (!cgan_attention_supported(ctx, batch, lq, lk, dk, dv))
+    return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: unsupported shape or math mode%s", "cgan_attention_bwd");
+  void* ws = nullptr;
+  int rc = cgan_ws(ctx, (size_t)batch * lq * sizeof(float), &ws);
+  if (rc) return rc;
+  float* dsum = reinterpret_cast<float*>(ws);
+  rc = cgan_rowdot(ctx, dsum, dout, out, (int64_t)batch * lq, dv);          // D = rowsum(dO * O)
+  if (rc) return rc;
+  AtParams p;
+  fill_params(&p, lq, lk, dk, dv);
+  p.lse = lse; p.dsum = dsum;
+  CUtensorMap tq128, tdo128, tk64, tvk64, tkm, tk128, tvk128, tq64, tdo64, tqm, tdom;
+  if (!make_rows_map(&tq128, q, dk, lq, batch, 128, false) || !make_rows_map(&tdo128, dout, dv, lq, batch, 128, false) ||
+      !make_rows_map(&tk64, k, dk, lk, batch, 64, false) || !make_rows_map(&tvk64, v, dv, lk, batch, 64, false) ||
+      !make_rows_map(&tkm, k, dk, lk, batch, 32, true) || !make_rows_map(&tk128, k, dk, lk, batch, 128, false) ||
+      !make_rows_map(&tvk128, v, dv, lk, batch, 128, false) || !make_rows_map(&tq64, q, dk, lq, batch, 64, false) ||
+      !make_rows_map(&tdo64, dout, dv, lq, batch, 64, false) || !make_rows_map(&tqm, q, dk, lq, batch, 32, true) ||
+      !make_rows_map(&tdom, dout, dv, lq, batch, 32, true))
+    return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_bwd");
+  {
+    p.out = dq; p.out2 = nullptr;
+    const size_t smem = 16384 + (size_t)p.vg * 16384 + 8192 + (size_t)p.vg * 8192 + 8192 + 32768 + 256 + 1024;
+    rc = set_smem(ctx, attn_bwd_dq_kernel, smem, "cgan_attention_bwd");
+    if (rc) return rc;
+    attn_bwd_dq_kernel<<<dim3(lq / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tq128, tdo128, tk64, tvk64, tkm, p);
+    CGAN_LAUNCHED(ctx);
+  }
+  {
+    p.out = dk_out; p.out2 = dv_out;
+    const size_t smem = 16384 + (size_t)p.vg * 16384 + 2 * (8192 + (size_t)p.vg * 8192) + 65536 + 1024 + 256 + 1024;
+    rc = set_smem(ctx, attn_bwd_dkv_kernel, smem, "cgan_attention_bwd");
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<<<dim3(lk / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tk128, tvk128, tq64, tdo64, tqm, tdom, p);
+    CGAN_LAUNCHED(ctx);
+  }
+  ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+  return CGAN_OK;
+}
+
+}  // extern "C"

@@ -81,7 +81,7 @@ def _desc_key(d):
   return (d.n, d.h * up, d.w * up, d.cin, d.cout, d.kh, d.kw, d.stride)
 
 
-_TC_NODES = ("conv2d", "conv2d_dgrad")
+_TC_NODES = ("conv2d", "conv2d_dgrad", "attention")
 _PASS_NODES = ("avgpool2", "reshape")
 
 
@@ -503,6 +503,59 @@ def bmm(a, b, ta=False, tb=False):
   return attach("bmm", c, [a, b], vjp)
 
 
+def round_tf32(x):
+  """x rounded to the nearest TF32 value (identity for the gradient, like the rounding a tensor-core contraction applies to
+  its operands); a no-op when the producer already stored x rounded."""
+  if x.tf32 or not tf32_on():
+    return x
+  y = empty(*x.shape)
+  _call("round_tf32", y.ptr, x.ptr, y.numel)
+  y.tf32 = True
+  return attach("round_tf32", y, [x], lambda g, needs: [g])
+
+
+def attention_shape_ok(bsz, lq, lk, dk, dv):
+  """Do the fused tcgen05 attention kernels take this shape in the current math mode?"""
+  return bool(tf32_on() and lib().attention_supported(bsz, lq, lk, dk, dv))
+
+
+def attention_fused_ok(theta, phi, g):
+  bsz, lq, dk = theta.shape
+  return attention_shape_ok(bsz, lq, phi.shape[1], dk, g.shape[2])
+
+
+def attention(theta, phi, g):
+  """softmax(theta phi^T) g per image — tf.matmul(theta, phi, transpose_b=True) -> tf.nn.softmax -> tf.matmul(attn, g)
+  (arch_ops.py:744-753).  In math_mode 1, for shapes the fused tcgen05 kernels take (csrc/attn_tc.cu: BigGAN's 4096 x 1024
+  scores at 24 / 12 key channels), ONE kernel per direction keeps the scores in TMEM / shared memory; otherwise the three
+  ops are composed as the reference writes them."""
+  if not attention_fused_ok(theta, phi, g):
+    return bmm(softmax(bmm(theta, phi, False, True)), g)
+  bsz, lq, dk = theta.shape
+  lk, dv = g.shape[1], g.shape[2]
+  q, k, v = round_tf32(theta), round_tf32(phi), round_tf32(g)
+  out = empty(bsz, lq, dv)
+  lse = empty(bsz, lq)
+  _call("attention_fwd", q.ptr, k.ptr, v.ptr, out.ptr, lse.ptr, bsz, lq, lk, dk, dv)
+  _trace("attention", (bsz, lq, lk, dk, dv), True, True, b_is_weight=False)
+  if CONV_CHECK is not None:
+    CONV_CHECK("attention", q=q, k=k, v=v, out=out, lse=lse)
+  ov = DT(out.t)
+
+  def vjp(gout, needs):
+    _no_second_order("attention")
+    go = gout
+    if not go.tf32:
+      go = empty(*gout.shape)
+      _call("round_tf32", go.ptr, gout.ptr, go.numel)
+    dq, dkk, dvv = empty(bsz, lq, dk), empty(bsz, lk, dk), empty(bsz, lk, dv)
+    _call("attention_bwd", q.ptr, k.ptr, v.ptr, ov.ptr, lse.ptr, go.ptr, dq.ptr, dkk.ptr, dvv.ptr, bsz, lq, lk, dk, dv)
+    if CONV_CHECK is not None:
+      CONV_CHECK("attention_bwd", q=q, k=k, v=v, out=ov, lse=lse, dout=go, dq=dq, dk=dkk, dv=dvv)
+    return [dq, dkk, dvv]
+  return attach("attention", out, [q, k, v], vjp)
+
+
 def colsum(x2, groups=1, leaf=None):
   """Per-channel sum over rows (bias / beta gradients).  `leaf`: the variable this is the gradient of, see _grad_out."""
   rows, c = x2.shape
@@ -621,6 +674,7 @@ def maxpool2(x):
   n, h, w, c = x.shape
   y = empty(n, h // 2, w // 2, c)
   _call("maxpool2_fwd", y.ptr, x.ptr, n, h, w, c)
+  y.tf32 = x.tf32           # a maximum of TF32 values is one of them
 
   def vjp(g, needs):
     _no_second_order("maxpool2")

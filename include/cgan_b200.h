@@ -129,6 +129,25 @@ int cgan_gemm_batched(cgan_ctx*, int trans_a, int trans_b, int m, int n, int k, 
                       int64_t stride_a, const float* b, int ldb, int64_t stride_b, float beta, float* c, int ldc,
                       int64_t stride_c, int batch);
 
+/* ---- fused self-attention (non_local_block, arch_ops.py:734-753) --------------------------------------------------
+ * out[i] = softmax(q[i] k[i]^T) v[i] per image i: q = theta [batch, lq, dk], k = phi [batch, lk, dk], v = g [batch, lk, dv],
+ * out [batch, lq, dv] — tf.matmul(theta, phi, transpose_b=True) -> tf.nn.softmax -> tf.matmul(attn, g) in ONE tcgen05
+ * kernel: the [lq, lk] scores live in TMEM / shared memory only (csrc/attn_tc.cu).  lse [batch, lq] receives the
+ * log-sum-exp of every score row; the backward recomputes the probabilities from it.  Operands are consumed as TF32:
+ * pass tensors that already hold TF32-representable values (cgan_round_tf32, or a producer's ROUND_OUT epilogue).
+ * cgan_attention_supported returns 1 when the fused kernels accept the shape in the current math mode (math_mode 1,
+ * lq and lk multiples of 128, dk <= 32 and a multiple of 4, dv <= 128 and a multiple of 16), else 0 — callers then
+ * compose cgan_gemm_batched / cgan_softmax_* as the reference does. */
+int cgan_attention_supported(cgan_ctx*, int batch, int lq, int lk, int dk, int dv);
+int cgan_attention_fwd(cgan_ctx*, const float* q, const float* k, const float* v, float* out, float* lse, int batch, int lq,
+                       int lk, int dk, int dv);
+/* gradients of the above w.r.t. q, k, v given dout [batch, lq, dv] (TF's MatMul / Softmax gradients of arch_ops.py:744-753):
+ * two kernels, one accumulating dq per query tile, one accumulating dk and dv per key tile; fixed summation order. */
+int cgan_attention_bwd(cgan_ctx*, const float* q, const float* k, const float* v, const float* out, const float* lse,
+                       const float* dout, float* dq, float* dk_out, float* dv_out, int batch, int lq, int lk, int dk, int dv);
+/* y = x rounded to the nearest TF32 value (10 mantissa bits), what a tensor-core contraction in math_mode 1 does to its operands */
+int cgan_round_tf32(cgan_ctx*, float* y, const float* x, int64_t n);
+
 /* ---- rows x channels reductions / bias -------------------------------------------------- */
 /* y[r,c] = x[r,c] + bias[c]   (linear bias, arch_ops.py:549-555) */
 int cgan_bias_add(cgan_ctx*, float* y, const float* x, const float* bias, int64_t rows, int c);

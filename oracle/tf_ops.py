@@ -45,6 +45,10 @@ def _tf32_used(kind, key):
   if TF32_PLAN is None:
     return False, False
   rec = TF32_PLAN.get((kind,) + tuple(int(v) for v in key))
+  if rec is None and kind == "bmm" and any(k[0] == "attention" and k[1] == int(key[0]) for k in TF32_PLAN):
+    # the engine ran this block's products inside its fused attention kernels (kernels.attention): every operand of the
+    # five products (theta, phi, g, the probabilities, dS, d out) enters them rounded to TF32
+    return True, True
   if rec is None:
     raise KeyError("TF32 plan has no entry for %s %s (the engine never ran this contraction)" % (kind, key))
   return bool(rec[1]), bool(rec[2])

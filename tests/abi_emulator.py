@@ -461,6 +461,44 @@ class EmulatedLib(object):
     p = f32(y, rows * cols).reshape(rows, cols).astype(np.float64)
     f32(dx, rows * cols).reshape(rows, cols)[:] = p * (g - (g * p).sum(1, keepdims=True))
 
+  # ---- fused attention (csrc/attn_tc.cu): same contract, same shape rule, TF32 probabilities ----
+  def attention_supported(self, batch, lq, lk, dk, dv):
+    return (self.math_mode == 1 and 1 <= batch <= 65535 and lq >= 128 and lq % 128 == 0 and lk >= 128 and lk % 128 == 0 and
+            4 <= dk <= 32 and dk % 4 == 0 and 16 <= dv <= 128 and dv % 16 == 0)
+
+  def cgan_round_tf32(self, y, x, n):
+    f32(y, n)[:] = rna_tf32(f32(x, n))
+
+  def cgan_attention_fwd(self, q, k, v, out, lse, batch, lq, lk, dk, dv):
+    assert self.attention_supported(batch, lq, lk, dk, dv)
+    self.last_path = 1
+    Q = f32(q, batch * lq * dk).reshape(batch, lq, dk)
+    Kk = f32(k, batch * lk * dk).reshape(batch, lk, dk)
+    Vv = f32(v, batch * lk * dv).reshape(batch, lk, dv)
+    s = np.einsum("bqd,bkd->bqk", Q, Kk).astype(np.float32)
+    m = s.max(2, keepdims=True)
+    pe = rna_tf32(np.exp(s - m).astype(np.float32))
+    l = pe.sum(2, keepdims=True, dtype=np.float32)
+    f32(out, batch * lq * dv).reshape(batch, lq, dv)[:] = np.einsum("bqk,bkd->bqd", pe, Vv) / l
+    f32(lse, batch * lq).reshape(batch, lq)[:] = (m + np.log(l))[:, :, 0]
+
+  def cgan_attention_bwd(self, q, k, v, out, lse, dout, dq, dk_out, dv_out, batch, lq, lk, dk, dv):
+    assert self.attention_supported(batch, lq, lk, dk, dv)
+    self.last_path = 1
+    Q = f32(q, batch * lq * dk).reshape(batch, lq, dk)
+    Kk = f32(k, batch * lk * dk).reshape(batch, lk, dk)
+    Vv = f32(v, batch * lk * dv).reshape(batch, lk, dv)
+    O = f32(out, batch * lq * dv).reshape(batch, lq, dv)
+    dO = f32(dout, batch * lq * dv).reshape(batch, lq, dv)
+    L = f32(lse, batch * lq).reshape(batch, lq, 1)
+    p = np.exp(np.einsum("bqd,bkd->bqk", Q, Kk).astype(np.float32) - L).astype(np.float32)
+    dsum = (dO * O).sum(2, keepdims=True, dtype=np.float32)
+    ds = rna_tf32(p * (np.einsum("bqd,bkd->bqk", dO, Vv).astype(np.float32) - dsum))
+    p = rna_tf32(p)
+    f32(dq, batch * lq * dk).reshape(batch, lq, dk)[:] = np.einsum("bqk,bkd->bqd", ds, Kk)
+    f32(dk_out, batch * lk * dk).reshape(batch, lk, dk)[:] = np.einsum("bqk,bqd->bkd", ds, Q)
+    f32(dv_out, batch * lk * dv).reshape(batch, lk, dv)[:] = np.einsum("bqk,bqd->bkd", p, dO)
+
   def cgan_rowdot(self, out, a, b, rows, cols):
     f32(out, rows)[:] = (f32(a, rows * cols).reshape(rows, cols).astype(np.float64) *
                          f32(b, rows * cols).reshape(rows, cols)).sum(1)

@@ -132,6 +132,7 @@ SHAPE_RULES = {
     "unpool": lambda x: (x.shape[0], 2 * x.shape[1], 2 * x.shape[2], x.shape[3]),
     "matmul": _matmul, "bmm": _bmm, "conv2d": _conv2d, "deconv2d": _deconv2d,
     "one_hot": lambda labels, classes: (labels.shape[0], classes),
+    "attention": lambda theta, phi, g: (theta.shape[0], theta.shape[1], g.shape[2]),
 }
 
 
@@ -156,6 +157,9 @@ def traced_kernels():
     return f
 
   keep = {"BNState", "same_pad", "conv_desc"}
+  saved["attention_shape_ok"] = K.attention_shape_ok
+  K.attention_shape_ok = lambda *a: False          # a host-side predicate (math_mode 0 in the traces), not a kernel call
+  keep.add("attention_shape_ok")
   for name in dir(K):
     obj = getattr(K, name)
     if name.startswith("_") or not callable(obj) or isinstance(obj, type) or name in keep:

@@ -634,3 +634,70 @@ def test_conv_into_channel_slice(K, mode, n, h, cin, cout, k, stride, pad):
   assert_close(out[..., 24:24 + cout], ref, 1e-3 if mode else TOL, "sliced conv")
   np.testing.assert_array_equal(out[..., 24:24 + cout], whole)       # same kernel, same K order: bit-identical
   assert (out[..., :24] == 7.0).all() and (out[..., 24 + cout:] == 7.0).all()
+
+
+def _rna_tf32(a):
+  a = np.ascontiguousarray(a, np.float32)
+  return ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("bsz,lq,lk,dk,dv", [(3, 256, 128, 24, 96), (2, 1024, 256, 12, 48), (2, 4096, 1024, 24, 96),
+                                              (2, 4096, 1024, 12, 48), (1, 128, 128, 32, 128), (2, 256, 128, 4, 16)])
+def test_tc_fused_attention(K, bsz, lq, lk, dk, dv):
+  """math_mode 1: softmax(theta phi^T) g of the non-local block (arch_ops.py:744-753) and its three gradients in the fused
+  tcgen05 kernels (csrc/attn_tc.cu) — scores only in TMEM / shared memory.  Checked (a) against the float64 evaluation on the
+  SAME TF32-rounded operands (what remains is the TF32 rounding of the probabilities and fp32 accumulation: <= 5e-4), (b) against
+  the reference's own composition tf.matmul -> tf.nn.softmax -> tf.matmul in fp32 on the unrounded operands at north_star's
+  1e-3, and (c) against the engine's composed path (three launches per direction) in exact-fp32 mode."""
+  rng = np.random.RandomState(lq + lk + dk)
+  theta = (0.5 * rng.randn(bsz, lq, dk)).astype(np.float32)
+  phi = (0.5 * rng.randn(bsz, lk, dk)).astype(np.float32)
+  g = rng.randn(bsz, lk, dv).astype(np.float32)
+  gy = rng.randn(bsz, lq, dv).astype(np.float32)
+
+  def torch_ref(arrs, dtype):
+    tt, pt, gt = [torch.from_numpy(a).to(dtype).requires_grad_(True) for a in arrs[:3]]
+    out = torch.bmm(torch.softmax(torch.bmm(tt, pt.transpose(1, 2)), -1), gt)
+    out.backward(torch.from_numpy(arrs[3]).to(dtype))
+    return [t.detach().numpy() for t in (out, tt.grad, pt.grad, gt.grad)]
+  ref32 = torch_ref((theta, phi, g, gy), torch.float32)
+  ref64 = torch_ref((_rna_tf32(theta), _rna_tf32(phi), _rna_tf32(g), _rna_tf32(gy)), torch.float64)
+
+  K.set_math_mode(1)
+  try:
+    assert K.attention_shape_ok(bsz, lq, lk, dk, dv)
+    td, pd, gd = dev(K, theta, True), dev(K, phi, True), dev(K, g, True)
+    n0 = K.lib().launch_count()
+    y = K.attention(td, pd, gd)
+    assert K.lib().launch_count() - n0 == 4, "3 operand roundings + ONE fused forward kernel"
+    n0 = K.lib().launch_count()
+    grads = tape_grads(K, y, gy, [td, pd, gd])
+    assert K.lib().launch_count() - n0 <= 5, "rounding of dO + rowdot + the dQ kernel + the dK/dV kernel"
+    got = [y.cpu()] + [t.cpu() for t in grads]
+  finally:
+    K.set_math_mode(0)
+  for name, a, r64, r32 in zip(("out", "d theta", "d phi", "d g"), got, ref64, ref32):
+    assert_close(a, r64, 5e-4, "fused attention %s vs float64 on the TF32-rounded operands" % name)
+    assert_close(a, r32, 1e-3, "fused attention %s vs fp32 reference composition" % name)
+  # the composed path (exact fp32) of the same op
+  td, pd, gd = dev(K, theta, True), dev(K, phi, True), dev(K, g, True)
+  y0 = K.attention(td, pd, gd)
+  grads0 = tape_grads(K, y0, gy, [td, pd, gd])
+  for name, a, b in zip(("out", "d theta", "d phi", "d g"), got, [y0.cpu()] + [t.cpu() for t in grads0]):
+    assert_close(a, b, 1e-3, "fused vs composed attention %s" % name)
+
+
+def test_attention_falls_back_for_shapes_the_fused_kernel_does_not_take(K):
+  """Toy widths (2 key channels at ch = 8) and math_mode 0 compose bmm -> softmax -> bmm like the reference."""
+  rng = np.random.RandomState(5)
+  theta, phi, g = rng.randn(2, 64, 2).astype(np.float32), rng.randn(2, 16, 2).astype(np.float32), rng.randn(2, 16, 8).astype(np.float32)
+  ref = torch.bmm(torch.softmax(torch.bmm(torch.from_numpy(theta), torch.from_numpy(phi).transpose(1, 2)), -1), torch.from_numpy(g))
+  for mode in (0, 1):
+    K.set_math_mode(mode)
+    try:
+      assert not K.attention_shape_ok(2, 64, 16, 2, 8)
+      y = K.attention(dev(K, theta), dev(K, phi), dev(K, g))
+    finally:
+      K.set_math_mode(0)
+    assert_close(y.cpu(), ref.numpy(), 1e-3 if mode else TOL, "composed attention")
+  assert not K.attention_shape_ok(2, 4096, 1024, 24, 96), "math_mode 0 never takes the TF32 kernel"

@@ -158,7 +158,7 @@ ARCHS = {
                    pair=dict(loss="hinge", g_bn="conditional_batch_norm", g_sn=True, d_sn=True, sn_singular="auto",
                              conditional=True, initializer="orthogonal", use_moving_averages=False, g_lr=1e-4, beta1=0.0,
                              beta2=0.999, ch=16, project_y=True,
-                             extra_bindings=["resnet_biggan.Generator.blocks_with_attention = 'B2'",
+                             extra_bindings=["resnet_biggan.Generator.blocks_with_attention = 'B3'",
                                              "resnet_biggan.Discriminator.blocks_with_attention = 'B1'"])),
 }
 
@@ -179,6 +179,27 @@ class _InSitu(object):
   def __call__(self, kind, **kw):
     K = self.K
     t = lambda dt: torch.from_numpy(dt.cpu().copy())
+    if kind in ("attention", "attention_bwd"):
+      # the fused kernels' arithmetic on the engine's own (TF32-rounded) operands: fp32 scores, probabilities and dS rounded
+      # to TF32 before their second contraction, everything else fp32
+      q, k, v = t(kw["q"]), t(kw["k"]), t(kw["v"])
+      s = torch.bmm(q, k.transpose(1, 2))
+      if kind == "attention":
+        m = s.max(-1, keepdim=True).values
+        pe = T.rna_tf32(torch.exp(s - m))
+        l = pe.sum(-1, keepdim=True)
+        pairs = [("out", kw["out"], torch.bmm(pe, v) / l), ("lse", kw["lse"], (m + torch.log(l))[..., 0])]
+      else:
+        o, lse, do = t(kw["out"]), t(kw["lse"]), t(kw["dout"])
+        pr = torch.exp(s - lse[..., None])
+        ds = T.rna_tf32(pr * (torch.bmm(do, v.transpose(1, 2)) - (do * o).sum(-1, keepdim=True)))
+        pairs = [("dq", kw["dq"], torch.bmm(ds, k)), ("dk", kw["dk"], torch.bmm(ds.transpose(1, 2), q)),
+                 ("dv", kw["dv"], torch.bmm(T.rna_tf32(pr).transpose(1, 2), do))]
+      for what, got, ref in pairs:
+        scale = float(np.linalg.norm(ref.numpy().ravel()))
+        err = float(np.linalg.norm((got.cpu() - ref.numpy()).ravel())) / max(scale, 1e-30)
+        self.results.append((err, "%s %s%s" % (kind, what, tuple(q.shape) + tuple(v.shape[1:])), "tcgen05_tf32", scale))
+      return
     if kind == "bmm":
       a, b, ta, tb = t(kw["a"]), t(kw["b"]), kw["ta"], kw["tb"]
       m = a.shape[2] if ta else a.shape[1]
