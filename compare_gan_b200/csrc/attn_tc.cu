@@ -17,8 +17,9 @@
 //   attn_bwd_dq_kernel: one CTA per 128 queries, loops over key tiles (accumulates dQ in TMEM);
 //   attn_bwd_dkv_kernel: one CTA per 128 keys, loops over query tiles of 64 (accumulates dK, dV in TMEM) — S^T and dP^T
 //   are produced directly (M = keys), so no transposition pass exists and the summation order is fixed (deterministic).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = softmax / epilogue
-// (one thread per accumulator row = TMEM lane).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = softmax / epilogue:
+// TMEM lane quarter = warp % 4, two warps per quarter, each owning one 32-column half of every 64-column score tile (one
+// warp per SM sub-partition could not hide the tcgen05.ld / MUFU latencies of its own dependent chain).
 //
 // Operands are consumed as TF32: callers pass tensors already rounded to the nearest TF32 value (cgan_round_tf32 or a
 // producer's ROUND_OUT epilogue); P and dS are rounded to nearest by the softmax warps.  Accumulation is fp32 in TMEM.
@@ -28,7 +29,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;
+constexpr int AT_SWARPS = 8;         // softmax warps
 constexpr int AT_TQ = 128;          // rows per CTA (UMMA M)
 constexpr int AT_TK = 64;           // columns per score tile (UMMA N of the score MMAs)
 constexpr float AT_LOG2E = 1.4426950408889634f;
@@ -111,11 +113,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// rows of `dst` (dv floats each) from an accumulator at TMEM column `col`, scaled
-__device__ __forceinline__ void store_acc_row(float* dst, uint32_t taddr, int ncols, float scale) {
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
+// one row of `dst` from the accumulator columns [0, ncols) at `taddr`, scaled; this thread takes the 32-column chunks
+// c_begin, c_begin + c_step, ...
+__device__ __forceinline__ void store_acc_row(float* dst, uint32_t taddr, int ncols, float scale, int c_begin, int c_step) {
+  for (int c0 = c_begin * 32; c0 < ncols; c0 += c_step * 32) {
     uint32_t r[32];
     tmem_ld32(taddr + (uint32_t)c0, r);
 #pragma unroll
@@ -150,6 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* p_empty = bars + 12;
   uint64_t* o_full = bars + 13;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  float* sX = reinterpret_cast<float*>(bars + 32);       // [2][128]: row maxima / row sums of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_TQ, img = blockIdx.y;
@@ -164,9 +168,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
+        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], AT_SWARPS);
       }
-      mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+      mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(p_full, AT_SWARPS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -231,54 +235,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3, row = quarter * 32 + lane;
-    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t aP = smem_u32(sP);
+    const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
+    const uint32_t aP = smem_u32(sP) + (uint32_t)(half * 16384);
     float m = -INFINITY;
     for (int it = 0; it < nkt; ++it) {
       const int s = it & 1;
       bwait(&s_full[s], (it >> 1) & 1);
       fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r[32];
-        tmem_ld32(tl + (uint32_t)(s * AT_TK + h * 32), r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-      }
+      uint32_t r[32];
+      tmem_ld32(tl + (uint32_t)(s * AT_TK), r);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[s]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
     }
+    sX[half * 128 + row] = m;
+    softmax_bar();
+    m = fmaxf(sX[row], sX[128 + row]);
+    softmax_bar();                       // sX is reused for the row sums
     const float m2 = m * AT_LOG2E;
     float l = 0.f;
     for (int j = 0; j < nkt; ++j) {
       const int it = nkt + j, s = it & 1;
       bwait(&s_full[s], (it >> 1) & 1);
       fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(tl + (uint32_t)(s * AT_TK), r0);
-      tmem_ld32(tl + (uint32_t)(s * AT_TK + 32), r1);
+      uint32_t r[32];
+      tmem_ld32(tl + (uint32_t)(s * AT_TK), r);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[s]);
       float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r[i]), AT_LOG2E, -m2))); l += pv[i]; }
       bwait(p_empty, (j & 1) ^ 1);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r0[i]), AT_LOG2E, -m2))); l += pv[i]; }
       store_row32(aP, row, pv);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r1[i]), AT_LOG2E, -m2))); l += pv[i]; }
-      store_row32(aP + 16384, row, pv);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
+    sX[half * 128 + row] = l;
+    softmax_bar();
+    l = sX[row] + sX[128 + row];
     bwait(o_full, 0);
     fence_after();
     const long long grow = (long long)img * p.lq + q0 + row;
-    store_acc_row(p.out + grow * p.dv, tl + 128, p.dv, 1.0f / l);
-    p.out2[grow] = m + logf(l);
+    store_acc_row(p.out + grow * p.dv, tmem + ((uint32_t)(quarter * 32) << 16) + 128, p.dv, 1.0f / l, half, 2);
+    if (half == 0) p.out2[grow] = m + logf(l);
     fence_before();
   }
   __syncthreads();
@@ -323,8 +327,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1); mbar_init(km_full, 1); mbar_init(km_empty, 1); mbar_init(mn_full, 1); mbar_init(mn_empty, 1);
-      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], 4); }
-      mbar_init(ds_full, 4); mbar_init(ds_empty, 1); mbar_init(dq_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
+      mbar_init(ds_full, AT_SWARPS); mbar_init(ds_empty, 1); mbar_init(dq_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -389,38 +393,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3, row = quarter * 32 + lane;
-    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t adS = smem_u32(sdS);
+    const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
+    const uint32_t adS = smem_u32(sdS) + (uint32_t)(half * 16384);
     const long long grow = (long long)img * p.lq + q0 + row;
     const float lse2 = p.lse[grow] * AT_LOG2E, dsum = p.dsum[grow];
     for (int j = 0; j < nkt; ++j) {
       const int b = j & 1;
       bwait(&sd_full[b], (j >> 1) & 1);
       fence_after();
-      float ds[2][32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tl + (uint32_t)(b * 128 + h * 32), rs);
-        tmem_ld32(tl + (uint32_t)(b * 128 + 64 + h * 32), rd);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          ds[h][i] = rna_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
-      }
+      uint32_t rs[32], rd[32];
+      tmem_ld32(tl + (uint32_t)(b * 128), rs);
+      tmem_ld32(tl + (uint32_t)(b * 128 + 64), rd);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sd_empty[b]);
+      float ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        ds[i] = rna_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
       bwait(ds_empty, (j & 1) ^ 1);
-      store_row32(adS, row, ds[0]);
-      store_row32(adS + 16384, row, ds[1]);
+      store_row32(adS, row, ds);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
     }
     bwait(dq_full, 0);
     fence_after();
-    store_acc_row(p.out + grow * p.dk, tl + 256, p.dk, 1.0f);
+    if (half == 0) store_acc_row(p.out + grow * p.dk, tmem + ((uint32_t)(quarter * 32) << 16) + 256, p.dk, 1.0f, 0, 1);
     fence_before();
   }
   __syncthreads();
@@ -472,8 +472,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(kv_full, 1); mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(qm_full, 1); mbar_init(qm_empty, 1);
-      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], 4); }
-      mbar_init(pt_full, 4); mbar_init(pt_empty, 1); mbar_init(acc_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
+      mbar_init(pt_full, AT_SWARPS); mbar_init(pt_empty, 1); mbar_init(acc_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -545,43 +545,44 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3, row = quarter * 32 + lane;
-    const int st = threadIdx.x - 64;             // 0..127 among the softmax threads
-    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t aPt = smem_u32(sPt), adSt = smem_u32(sdSt);
+    const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
+    const int st = threadIdx.x - 64;             // 0..255 among the softmax threads
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
+    const uint32_t aPt = smem_u32(sPt) + (uint32_t)(half * 16384), adSt = smem_u32(sdSt) + (uint32_t)(half * 16384);
+    // per-query lse and D of a tile (columns here) are staged in shared memory and read as broadcasts; the global loads for
+    // tile i + 1 are issued at the top of tile i so that their latency is off the per-tile critical path
+    const long long gq0 = (long long)img * p.lq + (st < AT_TK ? st : 0);
+    float nl = 0.f, nd = 0.f;
+    if (st < AT_TK) { nl = p.lse[gq0]; nd = p.dsum[gq0]; }
     for (int i = 0; i < nqt; ++i) {
       const int b = i & 1;
-      // this tile's per-query lse and D (columns here): staged once, read as broadcasts.  Buffer b was last read two tiles
-      // ago, and every softmax thread has passed the barrier of the tile in between.
+      // buffer b was last read two tiles ago, and every softmax thread has passed the barrier of the tile in between
       if (st < AT_TK) {
-        const long long gq = (long long)img * p.lq + i * AT_TK + st;
-        sL[b * AT_TK + st] = p.lse[gq] * AT_LOG2E;
-        sD[b * AT_TK + st] = p.dsum[gq];
+        sL[b * AT_TK + st] = nl * AT_LOG2E;
+        sD[b * AT_TK + st] = nd;
+        if (i + 1 < nqt) { nl = p.lse[gq0 + (i + 1) * AT_TK]; nd = p.dsum[gq0 + (i + 1) * AT_TK]; }
       }
       softmax_bar();
       bwait(&sd_full[b], (i >> 1) & 1);
       fence_after();
-      float pt[2][32], ds[2][32];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tl + (uint32_t)(b * 128 + h * 32), rs);
-        tmem_ld32(tl + (uint32_t)(b * 128 + 64 + h * 32), rd);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float pe = ex2(fmaf(__uint_as_float(rs[c]), AT_LOG2E, -sL[b * AT_TK + h * 32 + c]));
-          pt[h][c] = rna_tf32(pe);
-          ds[h][c] = rna_tf32(pe * (__uint_as_float(rd[c]) - sD[b * AT_TK + h * 32 + c]));
-        }
-      }
+      uint32_t rs[32], rd[32];
+      tmem_ld32(tl + (uint32_t)(b * 128), rs);
+      tmem_ld32(tl + (uint32_t)(b * 128 + 64), rd);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sd_empty[b]);
+      float pt[32], ds[32];
+      const float* lrow = sL + b * AT_TK + half * 32;
+      const float* drow = sD + b * AT_TK + half * 32;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float pe = ex2(fmaf(__uint_as_float(rs[c]), AT_LOG2E, -lrow[c]));
+        pt[c] = rna_tf32(pe);
+        ds[c] = rna_tf32(pe * (__uint_as_float(rd[c]) - drow[c]));
+      }
       bwait(pt_empty, (i & 1) ^ 1);
-      store_row32(aPt, row, pt[0]);
-      store_row32(aPt + 16384, row, pt[1]);
-      store_row32(adSt, row, ds[0]);
-      store_row32(adSt + 16384, row, ds[1]);
+      store_row32(aPt, row, pt);
+      store_row32(adSt, row, ds);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pt_full);
@@ -589,8 +590,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     bwait(acc_full, 0);
     fence_after();
     const long long grow = (long long)img * p.lk + k0 + row;
-    store_acc_row(p.out + grow * p.dk, tl + 256, p.dk, 1.0f);
-    store_acc_row(p.out2 + grow * p.dv, tl + 320, p.dv, 1.0f);
+    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    if (half == 1) store_acc_row(p.out + grow * p.dk, tq + 256, p.dk, 1.0f, 0, 1);
+    store_acc_row(p.out2 + grow * p.dv, tq + 320, p.dv, 1.0f, half, 2);
     fence_before();
   }
   __syncthreads();
@@ -662,7 +664,7 @@ int cgan_attention_fwd(cgan_ctx* ctx, const float* q, const float* k, const floa
   if (!make_rows_map(&tq, q, dk, lq, batch, 128, false) || !make_rows_map(&tk, k, dk, lk, batch, 64, false) ||
       !make_rows_map(&tv, v, dv, lk, batch, 32, true))
     return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_fwd");
-  const size_t smem = 32768 + (size_t)p.vg * 8192 + 32768 + 256 + 1024;
+  const size_t smem = 32768 + (size_t)p.vg * 8192 + 32768 + 256 + 1024 + 1024;
   int rc = set_smem(ctx, attn_fwd_kernel, smem, "cgan_attention_fwd");
   if (rc) return rc;
   attn_fwd_kernel<<<dim3(lq / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tq, tk, tv, p);

@@ -7,7 +7,7 @@ name = rows[0][1]
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(hdr) and r[col["# Samples"]].isdigit()]
 tot = sum(int(r[col["# Samples"]]) for r in data)
 by = {k: sum(int(r[col[k]]) for r in data) for k in reasons}
 print("== %s: %d samples over %d SASS instructions ==" % (name[:70], tot, len(data)))
