@@ -7,6 +7,9 @@
 // leave the SM: S tiles are produced by tcgen05.mma into TMEM, read by the softmax warps with tcgen05.ld, exponentiated,
 // written as TF32 into a 128B-swizzled K-major shared-memory tile and consumed from there by the second tcgen05.mma.
 //
+// Operand tiles stream through multi-stage shared-memory rings filled by ONE polling TMA thread (the first version refilled
+// a single buffer after its last reader retired: every tile then paid a full TMA round trip, ~5000 clk per tile in all three
+// kernels whatever their arithmetic — profiles/r2_attention_*.txt).
 // Forward (attn_fwd_kernel): one CTA per 128 queries of one image, key tiles of 64.
 //   pass 1: S_j = Q K_j^T (M=128, N=64, K=8 per MMA, dk <= 32 zero-padded by TMA) -> row maxima m.
 //   pass 2: S_j again (K has 4x fewer channels than V: recomputing costs 1/4 of the P V MMAs and avoids rescaling O in
@@ -23,6 +26,8 @@
 //
 // Operands are consumed as TF32: callers pass tensors already rounded to the nearest TF32 value (cgan_round_tf32 or a
 // producer's ROUND_OUT epilogue); P and dS are rounded to nearest by the softmax warps.  Accumulation is fp32 in TMEM.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -35,8 +40,13 @@ constexpr int AT_TQ = 128;          // rows per CTA (UMMA M)
 constexpr int AT_TK = 64;           // columns per score tile (UMMA N of the score MMAs)
 constexpr float AT_LOG2E = 1.4426950408889634f;
 
+constexpr int AT_MAX_STAGES = 4;
+constexpr size_t AT_SMEM_MAX = 227 * 1024;
+
 struct AtParams {
   int lq, lk, dk, dv;
+  int np;               // fwd: P buffers (1: two CTAs per SM, 2: one CTA per SM with deeper rings)
+  int ns_a, ns_b;       // ring depths: fwd K / V tiles; dq: key-tile ring (both operand groups); dkv: K-major / MN-major query groups
   int kq;               // MMA k-steps of the score contraction: ceil(dk / 8)
   int kv;               // MMA k-steps of a contraction over dv: ceil(dv / 8)
   int vg;               // 32-channel groups of V / dO: ceil(dv / 32)
@@ -89,6 +99,29 @@ __device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// non-blocking probe (the TMA producer polls several rings: it must never block on one while another could be refilled)
+__device__ __forceinline__ bool btest(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// the idle branch of a polling producer: back off briefly, trap after ~2 s without progress
+__device__ __forceinline__ void poll_idle(long long& t_last) {
+  __nanosleep(64);
+  if (clock64() - t_last > 4000000000ll) __trap();
+}
+
+// round to the nearest TF32 value, ties away from zero — bit-identical to cvt.rna.tf32.f32 for finite values below the
+// largest TF32 binade (probabilities and their products here), but two full-rate integer ops instead of one instruction on
+// the quarter-rate conversion pipe, which the exponentials already saturate (ncu r2: softmax warps XU-bound)
+__device__ __forceinline__ float rnd_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -130,7 +163,8 @@ __device__ __forceinline__ void store_acc_row(float* dst, uint32_t taddr, int nc
 }
 
 // ------------------------------------------------------------------------------------------------------------ forward
-// shared memory: Q 16 KB | K ring 2 x 8 KB | V vg x 2 x 4 KB | P 32 KB | barriers.  TMEM: S0 @0, S1 @64, O @128 (256 columns).
+// shared memory: Q 16 KB | P 2 x 32 KB | K ring ns_a x 8 KB | V ring ns_b x (vg x 8 KB) | barriers | row max / sum exchange.
+// TMEM: S0 @0, S1 @64, O @128 (256 columns).
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AtParams p) {
@@ -138,21 +172,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int v_bytes = p.vg * 2 * 4096;
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sV = smem + 32768;
-  uint8_t* sP = sV + v_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 2
-  uint64_t* k_empty = bars + 3;       // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* s_empty = bars + 7;       // 2
-  uint64_t* v_full = bars + 9;
-  uint64_t* v_empty = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* p_empty = bars + 12;
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint8_t* sP = smem + 16384;
+  uint8_t* sK = sP + p.np * 32768;
+  uint8_t* sV = sK + p.ns_a * 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.ns_b * v_bytes);
+  uint64_t* q_full = bars;                          // 1
+  uint64_t* k_full = bars + 1;                      // AT_MAX_STAGES
+  uint64_t* k_empty = k_full + AT_MAX_STAGES;
+  uint64_t* v_full = k_empty + AT_MAX_STAGES;
+  uint64_t* v_empty = v_full + AT_MAX_STAGES;
+  uint64_t* s_full = v_empty + AT_MAX_STAGES;       // 2
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;                   // 2
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;                   // 26 barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
   float* sX = reinterpret_cast<float*>(bars + 32);       // [2][128]: row maxima / row sums of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,10 +201,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], AT_SWARPS);
+      for (int s = 0; s < AT_MAX_STAGES; ++s) {
+        mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       }
-      mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(p_full, AT_SWARPS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], AT_SWARPS); mbar_init(&p_full[s], AT_SWARPS); mbar_init(&p_empty[s], 1);
+      }
+      mbar_init(o_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -185,18 +222,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(q_full, 16384);
       tma_load_4d(sQ, &tm_q, q_full, 0, q0, 0, img);
-      for (int it = 0; it < 2 * nkt; ++it) {
-        const int s = it & 1, j = it < nkt ? it : it - nkt;
-        bwait(&k_empty[s], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&k_full[s], 8192);
-        tma_load_4d(sK + s * 8192, &tm_k, &k_full[s], 0, j * AT_TK, 0, img);
-        if (it >= nkt) {
-          bwait(v_empty, (j & 1) ^ 1);
-          mbar_expect_tx(v_full, (uint32_t)v_bytes);
-          for (int kb = 0; kb < 2; ++kb)
-            for (int g = 0; g < p.vg; ++g)
-              tma_load_4d(sV + (kb * p.vg + g) * 4096, &tm_v, v_full, g * 32, j * AT_TK + kb * 32, 0, img);
+      // K tiles are consumed twice (pass 1: row maxima, pass 2), V tiles once; both rings are refilled as soon as a stage
+      // drains, so V runs ns_b tiles ahead of pass 2 (its first tiles load during pass 1)
+      int kt = 0, vt = 0;
+      long long t_last = clock64();
+      while (kt < 2 * nkt || vt < nkt) {
+        bool progress = false;
+        if (kt < 2 * nkt) {
+          const int s = kt % p.ns_a;
+          if (btest(&k_empty[s], ((kt / p.ns_a) & 1) ^ 1)) {
+            mbar_expect_tx(&k_full[s], 8192);
+            tma_load_4d(sK + s * 8192, &tm_k, &k_full[s], 0, (kt % nkt) * AT_TK, 0, img);
+            ++kt; progress = true;
+          }
         }
+        if (vt < nkt) {
+          const int s = vt % p.ns_b;
+          if (btest(&v_empty[s], ((vt / p.ns_b) & 1) ^ 1)) {
+            mbar_expect_tx(&v_full[s], (uint32_t)v_bytes);
+            for (int kb = 0; kb < 2; ++kb)
+              for (int g = 0; g < p.vg; ++g)
+                tma_load_4d(sV + s * v_bytes + (kb * p.vg + g) * 4096, &tm_v, &v_full[s], g * 32, vt * AT_TK + kb * 32, 0, img);
+            ++vt; progress = true;
+          }
+        }
+        if (progress) t_last = clock64(); else poll_idle(t_last);
       }
     }
   } else if (warp == 1) {
@@ -204,16 +254,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
     bwait(q_full, 0);
     auto issue_s = [&](int it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      bwait(&k_full[s], ph);
-      bwait(&s_empty[s], ph ^ 1);
+      const int ks = it % p.ns_a, sb = it & 1;
+      bwait(&k_full[ks], (it / p.ns_a) & 1);
+      bwait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
       fence_after();
       if (lane == 0) {
         for (int k = 0; k < p.kq; ++k)
-          umma_tf32(tmem + (uint32_t)(s * AT_TK), desc_k(aQ + k * 32), desc_k(aK + s * 8192 + k * 32), id_s, k ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(&s_full[s]);
+          umma_tf32(tmem + (uint32_t)(sb * AT_TK), desc_k(aQ + k * 32), desc_k(aK + ks * 8192 + k * 32), id_s, k ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
@@ -221,15 +270,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     issue_s(nkt);
     for (int j = 0; j < nkt; ++j) {
       if (j + 1 < nkt) issue_s(nkt + j + 1);
-      bwait(p_full, j & 1);
-      bwait(v_full, j & 1);
+      const int vs = j % p.ns_b, pb = j % p.np;
+      bwait(&p_full[pb], (j / p.np) & 1);
+      bwait(&v_full[vs], (j / p.ns_b) & 1);
       fence_after();
       if (lane == 0) {
         for (int kk = 0; kk < AT_TK / 8; ++kk)
-          umma_tf32(tmem + 128, desc_k(aP + (kk >> 2) * 16384 + (kk & 3) * 32),
-                    desc_mn(aV + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_pv, (j | kk) ? 1u : 0u);
-        umma_commit(p_empty);
-        umma_commit(v_empty);
+          umma_tf32(tmem + 128, desc_k(aP + pb * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32),
+                    desc_mn(aV + vs * v_bytes + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_pv, (j | kk) ? 1u : 0u);
+        umma_commit(&p_empty[pb]);
+        umma_commit(&v_empty[vs]);
         if (j == nkt - 1) umma_commit(o_full);
       }
       __syncwarp();
@@ -258,7 +308,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float m2 = m * AT_LOG2E;
     float l = 0.f;
     for (int j = 0; j < nkt; ++j) {
-      const int it = nkt + j, s = it & 1;
+      const int it = nkt + j, s = it & 1, pb = j % p.np;
       bwait(&s_full[s], (it >> 1) & 1);
       fence_after();
       uint32_t r[32];
@@ -268,12 +318,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (lane == 0) mbar_arrive(&s_empty[s]);
       float pv[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { pv[i] = rna_tf32(ex2(fmaf(__uint_as_float(r[i]), AT_LOG2E, -m2))); l += pv[i]; }
-      bwait(p_empty, (j & 1) ^ 1);
-      store_row32(aP, row, pv);
+      for (int i = 0; i < 32; ++i) { pv[i] = rnd_tf32(ex2(fmaf(__uint_as_float(r[i]), AT_LOG2E, -m2))); l += pv[i]; }
+      bwait(&p_empty[pb], ((j / p.np) & 1) ^ 1);
+      store_row32(aP + (uint32_t)(pb * 32768), row, pv);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[pb]);
     }
     sX[half * 128 + row] = l;
     softmax_bar();
@@ -293,32 +343,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // -------------------------------------------------------------------------------------------------------- backward: dQ
-// shared memory: Q 16 KB | dO vg x 16 KB | K (K-major, 64 keys) 8 KB | V (K-major, 64 keys) vg x 8 KB | K (MN-major) 8 KB |
-// dS 32 KB | barriers.  TMEM (512 columns): buffer b @ b*128: S @+0, dP @+64; dQ @256.
+// shared memory: Q 16 KB | dO vg x 16 KB | dS 32 KB | key-tile ring ns_a x [K (K-major) 8 KB | V (K-major) vg x 8 KB |
+// K (MN-major) 8 KB] | barriers.  TMEM (512 columns): buffer b @ b*128: S @+0, dP @+64; dQ @256.
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
                    const __grid_constant__ CUtensorMap tm_km, const AtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 16384 + p.vg * 8192;     // [K K-major 8 KB | V K-major vg x 8 KB | K MN-major 8 KB]
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + 16384;
-  uint8_t* sKk = sdO + p.vg * 16384;
-  uint8_t* sVk = sKk + 8192;
-  uint8_t* sKm = sVk + p.vg * 8192;
-  uint8_t* sdS = sKm + 8192;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint8_t* sdS = sdO + p.vg * 16384;
+  uint8_t* ring = sdS + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ns_a * stage_bytes);
   uint64_t* q_full = bars;
-  uint64_t* km_full = bars + 1;
-  uint64_t* km_empty = bars + 2;
-  uint64_t* mn_full = bars + 3;
-  uint64_t* mn_empty = bars + 4;
-  uint64_t* sd_full = bars + 5;       // 2
-  uint64_t* sd_empty = bars + 7;      // 2
-  uint64_t* ds_full = bars + 9;
-  uint64_t* ds_empty = bars + 10;
-  uint64_t* dq_full = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* km_full = bars + 1;                     // AT_MAX_STAGES each
+  uint64_t* km_empty = km_full + AT_MAX_STAGES;
+  uint64_t* mn_full = km_empty + AT_MAX_STAGES;
+  uint64_t* mn_empty = mn_full + AT_MAX_STAGES;
+  uint64_t* sd_full = mn_empty + AT_MAX_STAGES;     // 2
+  uint64_t* sd_empty = sd_full + 2;
+  uint64_t* ds_full = sd_empty + 2;
+  uint64_t* ds_empty = ds_full + 1;
+  uint64_t* dq_full = ds_empty + 1;                 // 24 barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dq_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_TQ, img = blockIdx.y;
@@ -326,7 +375,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(q_full, 1); mbar_init(km_full, 1); mbar_init(km_empty, 1); mbar_init(mn_full, 1); mbar_init(mn_empty, 1);
+      mbar_init(q_full, 1);
+      for (int s = 0; s < AT_MAX_STAGES; ++s) {
+        mbar_init(&km_full[s], 1); mbar_init(&km_empty[s], 1); mbar_init(&mn_full[s], 1); mbar_init(&mn_empty[s], 1);
+      }
       for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
       mbar_init(ds_full, AT_SWARPS); mbar_init(ds_empty, 1); mbar_init(dq_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -344,25 +396,42 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_expect_tx(q_full, (uint32_t)(16384 + p.vg * 16384));
       tma_load_4d(sQ, &tm_q, q_full, 0, q0, 0, img);
       for (int g = 0; g < p.vg; ++g) tma_load_4d(sdO + g * 16384, &tm_do, q_full, g * 32, q0, 0, img);
-      for (int j = 0; j < nkt; ++j) {
-        const uint32_t ph = j & 1;
-        bwait(km_empty, ph ^ 1);
-        mbar_expect_tx(km_full, (uint32_t)(8192 + p.vg * 8192));
-        tma_load_4d(sKk, &tm_k, km_full, 0, j * AT_TK, 0, img);
-        for (int g = 0; g < p.vg; ++g) tma_load_4d(sVk + g * 8192, &tm_vk, km_full, g * 32, j * AT_TK, 0, img);
-        bwait(mn_empty, ph ^ 1);
-        mbar_expect_tx(mn_full, 8192);
-        for (int kb = 0; kb < 2; ++kb) tma_load_4d(sKm + kb * 4096, &tm_km, mn_full, 0, j * AT_TK + kb * 32, 0, img);
+      // two operand groups per key tile with different lifetimes: the K-major K / V tiles are free once S and dP are
+      // computed, the MN-major K tile once dQ has consumed dS
+      int kt = 0, mt = 0;
+      long long t_last = clock64();
+      while (kt < nkt || mt < nkt) {
+        bool progress = false;
+        if (kt < nkt) {
+          const int s = kt % p.ns_a;
+          if (btest(&km_empty[s], ((kt / p.ns_a) & 1) ^ 1)) {
+            uint8_t* st = ring + s * stage_bytes;
+            mbar_expect_tx(&km_full[s], (uint32_t)(8192 + p.vg * 8192));
+            tma_load_4d(st, &tm_k, &km_full[s], 0, kt * AT_TK, 0, img);
+            for (int g = 0; g < p.vg; ++g) tma_load_4d(st + 8192 + g * 8192, &tm_vk, &km_full[s], g * 32, kt * AT_TK, 0, img);
+            ++kt; progress = true;
+          }
+        }
+        if (mt < nkt) {
+          const int s = mt % p.ns_a;
+          if (btest(&mn_empty[s], ((mt / p.ns_a) & 1) ^ 1)) {
+            uint8_t* st = ring + s * stage_bytes + 8192 + p.vg * 8192;
+            mbar_expect_tx(&mn_full[s], 8192);
+            for (int kb = 0; kb < 2; ++kb) tma_load_4d(st + kb * 4096, &tm_km, &mn_full[s], 0, mt * AT_TK + kb * 32, 0, img);
+            ++mt; progress = true;
+          }
+        }
+        if (progress) t_last = clock64(); else poll_idle(t_last);
       }
     }
   } else if (warp == 1) {
     const uint32_t id_s = idesc(AT_TK, 0), id_dq = idesc(32, 1);
-    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKm = smem_u32(sKm),
-                   adS = smem_u32(sdS);
+    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aR = smem_u32(ring), adS = smem_u32(sdS);
     bwait(q_full, 0);
     auto issue_sd = [&](int j) {
-      const int b = j & 1;
-      bwait(km_full, j & 1);
+      const int b = j & 1, s = j % p.ns_a;
+      const uint32_t aKk = aR + s * stage_bytes, aVk = aKk + 8192;
+      bwait(&km_full[s], (j / p.ns_a) & 1);
       bwait(&sd_empty[b], ((j >> 1) & 1) ^ 1);
       fence_after();
       if (lane == 0) {
@@ -371,7 +440,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int kk = 0; kk < p.kv; ++kk)
           umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(adO + (kk >> 2) * 16384 + (kk & 3) * 32),
                     desc_k(aVk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
-        umma_commit(km_empty);
+        umma_commit(&km_empty[s]);
         umma_commit(&sd_full[b]);
       }
       __syncwarp();
@@ -379,15 +448,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     issue_sd(0);
     for (int j = 0; j < nkt; ++j) {
       if (j + 1 < nkt) issue_sd(j + 1);
+      const int s = j % p.ns_a;
+      const uint32_t aKm = aR + s * stage_bytes + 8192 + p.vg * 8192;
       bwait(ds_full, j & 1);
-      bwait(mn_full, j & 1);
+      bwait(&mn_full[s], (j / p.ns_a) & 1);
       fence_after();
       if (lane == 0) {
         for (int kk = 0; kk < AT_TK / 8; ++kk)
           umma_tf32(tmem + 256, desc_k(adS + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aKm + (kk >> 2) * 4096 + (kk & 3) * 1024),
                     id_dq, (j | kk) ? 1u : 0u);
         umma_commit(ds_empty);
-        umma_commit(mn_empty);
+        umma_commit(&mn_empty[s]);
         if (j == nkt - 1) umma_commit(dq_full);
       }
       __syncwarp();
@@ -411,7 +482,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       float ds[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        ds[i] = rna_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
+        ds[i] = rnd_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
       bwait(ds_empty, (j & 1) ^ 1);
       store_row32(adS, row, ds);
       fence_async_smem();
@@ -433,37 +504,39 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // ---------------------------------------------------------------------------------------------------- backward: dK, dV
 // One CTA per 128 keys; query tiles of 64.  S^T = K Q^T and dP^T = V dO^T (M = keys, N = queries) so that P^T and dS^T come out
 // in the A-operand orientation of dV += P^T dO and dK += dS^T Q.
-// shared memory: K 16 KB | V vg x 16 KB | Q (K-major, 64 q) 8 KB | dO (K-major, 64 q) vg x 8 KB | Q (MN-major) 8 KB |
-// dO (MN-major) vg x 8 KB | P^T 32 KB | dS^T 32 KB | lse, D of the query tile 2 x 2 x 64 floats | barriers.
+// shared memory: K 16 KB | V vg x 16 KB | P^T 32 KB | dS^T 32 KB | ring ns_a x [Q (K-major, 64 q) 8 KB | dO (K-major) vg x 8 KB] |
+// ring ns_b x [Q (MN-major) 8 KB | dO (MN-major) vg x 8 KB] | lse, D of the query tile 2 x 2 x 64 floats | barriers.  The whole
+// 227 KB are in use at dv = 96, so the buffer is NOT re-aligned in the kernel: the 1024-byte alignment the swizzled layouts
+// need is asserted (extern __shared__ __align__(1024)).
 // TMEM (512 columns): buffer b @ b*128: S^T @+0, dP^T @+64; dK @256; dV @320.
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
                     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_qm, const __grid_constant__ CUtensorMap tm_dom, const AtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();
+  const int stage_bytes = 8192 + p.vg * 8192;
   uint8_t* sK = smem;
   uint8_t* sV = sK + 16384;
-  uint8_t* sQk = sV + p.vg * 16384;
-  uint8_t* sdOk = sQk + 8192;
-  uint8_t* sQm = sdOk + p.vg * 8192;
-  uint8_t* sdOm = sQm + 8192;
-  uint8_t* sPt = sdOm + p.vg * 8192;
+  uint8_t* sPt = sV + p.vg * 16384;
   uint8_t* sdSt = sPt + 32768;
-  float* sL = reinterpret_cast<float*>(sdSt + 32768);        // [2][64] lse * log2(e)
+  uint8_t* ringk = sdSt + 32768;                             // K-major Q / dO tiles
+  uint8_t* ringm = ringk + p.ns_a * stage_bytes;             // MN-major Q / dO tiles
+  float* sL = reinterpret_cast<float*>(ringm + p.ns_b * stage_bytes);        // [2][64] lse * log2(e)
   float* sD = sL + 128;                                      // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
   uint64_t* kv_full = bars;
-  uint64_t* qk_full = bars + 1;
-  uint64_t* qk_empty = bars + 2;
-  uint64_t* qm_full = bars + 3;
-  uint64_t* qm_empty = bars + 4;
-  uint64_t* sd_full = bars + 5;       // 2
-  uint64_t* sd_empty = bars + 7;      // 2
-  uint64_t* pt_full = bars + 9;
-  uint64_t* pt_empty = bars + 10;
-  uint64_t* acc_full = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qk_full = bars + 1;                     // AT_MAX_STAGES each
+  uint64_t* qk_empty = qk_full + AT_MAX_STAGES;
+  uint64_t* qm_full = qk_empty + AT_MAX_STAGES;
+  uint64_t* qm_empty = qm_full + AT_MAX_STAGES;
+  uint64_t* sd_full = qm_empty + AT_MAX_STAGES;     // 2
+  uint64_t* sd_empty = sd_full + 2;
+  uint64_t* pt_full = sd_empty + 2;
+  uint64_t* pt_empty = pt_full + 1;
+  uint64_t* acc_full = pt_empty + 1;                // 24 barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * AT_TQ, img = blockIdx.y;
@@ -471,7 +544,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
 
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(kv_full, 1); mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(qm_full, 1); mbar_init(qm_empty, 1);
+      mbar_init(kv_full, 1);
+      for (int s = 0; s < AT_MAX_STAGES; ++s) {
+        mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1); mbar_init(&qm_full[s], 1); mbar_init(&qm_empty[s], 1);
+      }
       for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
       mbar_init(pt_full, AT_SWARPS); mbar_init(pt_empty, 1); mbar_init(acc_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -489,29 +565,45 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       mbar_expect_tx(kv_full, (uint32_t)(16384 + p.vg * 16384));
       tma_load_4d(sK, &tm_k, kv_full, 0, k0, 0, img);
       for (int g = 0; g < p.vg; ++g) tma_load_4d(sV + g * 16384, &tm_vk, kv_full, g * 32, k0, 0, img);
-      for (int i = 0; i < nqt; ++i) {
-        const uint32_t ph = i & 1;
-        bwait(qk_empty, ph ^ 1);
-        mbar_expect_tx(qk_full, (uint32_t)(8192 + p.vg * 8192));
-        tma_load_4d(sQk, &tm_q, qk_full, 0, i * AT_TK, 0, img);
-        for (int g = 0; g < p.vg; ++g) tma_load_4d(sdOk + g * 8192, &tm_do, qk_full, g * 32, i * AT_TK, 0, img);
-        bwait(qm_empty, ph ^ 1);
-        mbar_expect_tx(qm_full, (uint32_t)(8192 + p.vg * 8192));
-        for (int kb = 0; kb < 2; ++kb) {
-          tma_load_4d(sQm + kb * 4096, &tm_qm, qm_full, 0, i * AT_TK + kb * 32, 0, img);
-          for (int g = 0; g < p.vg; ++g)
-            tma_load_4d(sdOm + (kb * p.vg + g) * 4096, &tm_dom, qm_full, g * 32, i * AT_TK + kb * 32, 0, img);
+      int kt = 0, mt = 0;
+      long long t_last = clock64();
+      while (kt < nqt || mt < nqt) {
+        bool progress = false;
+        if (kt < nqt) {
+          const int s = kt % p.ns_a;
+          if (btest(&qk_empty[s], ((kt / p.ns_a) & 1) ^ 1)) {
+            uint8_t* st = ringk + s * stage_bytes;
+            mbar_expect_tx(&qk_full[s], (uint32_t)stage_bytes);
+            tma_load_4d(st, &tm_q, &qk_full[s], 0, kt * AT_TK, 0, img);
+            for (int g = 0; g < p.vg; ++g) tma_load_4d(st + 8192 + g * 8192, &tm_do, &qk_full[s], g * 32, kt * AT_TK, 0, img);
+            ++kt; progress = true;
+          }
         }
+        if (mt < nqt) {
+          const int s = mt % p.ns_b;
+          if (btest(&qm_empty[s], ((mt / p.ns_b) & 1) ^ 1)) {
+            uint8_t* st = ringm + s * stage_bytes;
+            mbar_expect_tx(&qm_full[s], (uint32_t)stage_bytes);
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_load_4d(st + kb * 4096, &tm_qm, &qm_full[s], 0, mt * AT_TK + kb * 32, 0, img);
+              for (int g = 0; g < p.vg; ++g)
+                tma_load_4d(st + 8192 + (kb * p.vg + g) * 4096, &tm_dom, &qm_full[s], g * 32, mt * AT_TK + kb * 32, 0, img);
+            }
+            ++mt; progress = true;
+          }
+        }
+        if (progress) t_last = clock64(); else poll_idle(t_last);
       }
     }
   } else if (warp == 1) {
     const uint32_t id_s = idesc(AT_TK, 0), id_dk = idesc(32, 1), id_dv = idesc(p.nv, 1);
-    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQk = smem_u32(sQk), adOk = smem_u32(sdOk), aQm = smem_u32(sQm),
-                   adOm = smem_u32(sdOm), aPt = smem_u32(sPt), adSt = smem_u32(sdSt);
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aRk = smem_u32(ringk), aRm = smem_u32(ringm), aPt = smem_u32(sPt),
+                   adSt = smem_u32(sdSt);
     bwait(kv_full, 0);
     auto issue_sd = [&](int i) {
-      const int b = i & 1;
-      bwait(qk_full, i & 1);
+      const int b = i & 1, s = i % p.ns_a;
+      const uint32_t aQk = aRk + s * stage_bytes, adOk = aQk + 8192;
+      bwait(&qk_full[s], (i / p.ns_a) & 1);
       bwait(&sd_empty[b], ((i >> 1) & 1) ^ 1);
       fence_after();
       if (lane == 0) {
@@ -520,7 +612,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
         for (int kk = 0; kk < p.kv; ++kk)
           umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(aV + (kk >> 2) * 16384 + (kk & 3) * 32),
                     desc_k(adOk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
-        umma_commit(qk_empty);
+        umma_commit(&qk_empty[s]);
         umma_commit(&sd_full[b]);
       }
       __syncwarp();
@@ -528,8 +620,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     issue_sd(0);
     for (int i = 0; i < nqt; ++i) {
       if (i + 1 < nqt) issue_sd(i + 1);
+      const int s = i % p.ns_b;
+      const uint32_t aQm = aRm + s * stage_bytes, adOm = aQm + 8192;
       bwait(pt_full, i & 1);
-      bwait(qm_full, i & 1);
+      bwait(&qm_full[s], (i / p.ns_b) & 1);
       fence_after();
       if (lane == 0) {
         for (int kk = 0; kk < AT_TK / 8; ++kk)
@@ -539,7 +633,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
           umma_tf32(tmem + 256, desc_k(adSt + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aQm + (kk >> 2) * 4096 + (kk & 3) * 1024),
                     id_dk, (i | kk) ? 1u : 0u);
         umma_commit(pt_empty);
-        umma_commit(qm_empty);
+        umma_commit(&qm_empty[s]);
         if (i == nqt - 1) umma_commit(acc_full);
       }
       __syncwarp();
@@ -577,8 +671,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const float pe = ex2(fmaf(__uint_as_float(rs[c]), AT_LOG2E, -lrow[c]));
-        pt[c] = rna_tf32(pe);
-        ds[c] = rna_tf32(pe * (__uint_as_float(rd[c]) - drow[c]));
+        pt[c] = rnd_tf32(pe);
+        ds[c] = rnd_tf32(pe * (__uint_as_float(rd[c]) - drow[c]));
       }
       bwait(pt_empty, (i & 1) ^ 1);
       store_row32(aPt, row, pt);
@@ -615,7 +709,7 @@ bool make_rows_map(CUtensorMap* tm, const float* base, int ch, int rows, int bat
 
 bool shape_ok(int batch, int lq, int lk, int dk, int dv) {
   return batch >= 1 && batch <= 65535 && lq >= 128 && lq % 128 == 0 && lk >= 128 && lk % 128 == 0 && dk >= 4 && dk <= 32 &&
-         dk % 4 == 0 && dv >= 16 && dv <= 128 && dv % 16 == 0;
+         dk % 4 == 0 && dv >= 16 && dv <= 128 && dv % 16 == 0;      // (dv = 128: one stage per ring in the dK/dV kernel still fits)
 }
 
 void fill_params(AtParams* p, int lq, int lk, int dk, int dv) {
@@ -664,7 +758,23 @@ int cgan_attention_fwd(cgan_ctx* ctx, const float* q, const float* k, const floa
   if (!make_rows_map(&tq, q, dk, lq, batch, 128, false) || !make_rows_map(&tk, k, dk, lk, batch, 64, false) ||
       !make_rows_map(&tv, v, dv, lk, batch, 32, true))
     return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_fwd");
-  const size_t smem = 32768 + (size_t)p.vg * 8192 + 32768 + 256 + 1024 + 1024;
+  // Two CTAs per SM (default: one P buffer, rings as deep as half an SM's shared memory allows) or one CTA per SM with two P
+  // buffers and deeper rings (env CGAN_ATTN_CTAS=1).  Measured (profiles/r2_attention_*.txt): the softmax warps are bound
+  // by TMEM reads and the exponentials, which two resident CTAs overlap better than deeper prefetch in one.
+  static const int ctas = []() { const char* e = getenv("CGAN_ATTN_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
+  const size_t v_stage = (size_t)p.vg * 8192;
+  size_t budget = ctas == 2 ? (AT_SMEM_MAX - 2048) / 2 : AT_SMEM_MAX;
+  p.np = ctas == 2 ? 1 : 2;
+  size_t fixed = 16384 + (size_t)p.np * 32768 + 1280 + 1024;
+  if (ctas == 2 && fixed + 2 * 8192 + v_stage > budget) {       // dv = 128: one CTA per SM
+    budget = AT_SMEM_MAX; p.np = 2; fixed = 16384 + 65536 + 1280 + 1024;
+  }
+  p.ns_a = budget == AT_SMEM_MAX ? AT_MAX_STAGES : 2;
+  p.ns_b = (int)((budget - fixed - (size_t)p.ns_a * 8192) / v_stage);
+  if (p.ns_b > AT_MAX_STAGES) p.ns_b = AT_MAX_STAGES;
+  if (p.ns_b > lk / AT_TK) p.ns_b = lk / AT_TK;
+  if (p.ns_b < 1) return cgan_fail(ctx, CGAN_ERR_UNSUPPORTED, "%s: shared memory%s", "cgan_attention_fwd");
+  const size_t smem = fixed + (size_t)p.ns_a * 8192 + (size_t)p.ns_b * v_stage;
   int rc = set_smem(ctx, attn_fwd_kernel, smem, "cgan_attention_fwd");
   if (rc) return rc;
   attn_fwd_kernel<<<dim3(lq / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tq, tk, tv, p);
@@ -698,7 +808,12 @@ int cgan_attention_bwd(cgan_ctx* ctx, const float* q, const float* k, const floa
     return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_bwd");
   {
     p.out = dq; p.out2 = nullptr;
-    const size_t smem = 16384 + (size_t)p.vg * 16384 + 8192 + (size_t)p.vg * 8192 + 8192 + 32768 + 256 + 1024;
+    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 32768 + 256 + 1024, stage = 16384 + (size_t)p.vg * 8192;
+    p.ns_a = (int)((AT_SMEM_MAX - fixed) / stage);
+    if (p.ns_a > AT_MAX_STAGES) p.ns_a = AT_MAX_STAGES;
+    if (p.ns_a > lk / AT_TK) p.ns_a = lk / AT_TK;
+    p.ns_b = p.ns_a;
+    const size_t smem = fixed + (size_t)p.ns_a * stage;
     rc = set_smem(ctx, attn_bwd_dq_kernel, smem, "cgan_attention_bwd");
     if (rc) return rc;
     attn_bwd_dq_kernel<<<dim3(lq / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tq128, tdo128, tk64, tvk64, tkm, p);
@@ -706,7 +821,15 @@ int cgan_attention_bwd(cgan_ctx* ctx, const float* q, const float* k, const floa
   }
   {
     p.out = dk_out; p.out2 = dv_out;
-    const size_t smem = 16384 + (size_t)p.vg * 16384 + 2 * (8192 + (size_t)p.vg * 8192) + 65536 + 1024 + 256 + 1024;
+    // no alignment slack here (the kernel asserts the 1024-byte alignment of its buffer): at dv = 96 that is the third stage
+    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 65536 + 1024 + 256, stage = 8192 + (size_t)p.vg * 8192;
+    int total = (int)((AT_SMEM_MAX - fixed) / stage);
+    if (total > 2 * AT_MAX_STAGES) total = 2 * AT_MAX_STAGES;
+    p.ns_a = (total + 1) / 2;           // K-major group: needed first (S^T, dP^T)
+    p.ns_b = total / 2;                 // MN-major group (dV, dK)
+    if (p.ns_a > lq / AT_TK) p.ns_a = lq / AT_TK;
+    if (p.ns_b > lq / AT_TK) p.ns_b = lq / AT_TK;
+    const size_t smem = fixed + (size_t)(p.ns_a + p.ns_b) * stage;
     rc = set_smem(ctx, attn_bwd_dkv_kernel, smem, "cgan_attention_bwd");
     if (rc) return rc;
     attn_bwd_dkv_kernel<<<dim3(lk / AT_TQ, batch), AT_THREADS, smem, ctx->stream>>>(tk128, tvk128, tq64, tdo64, tqm, tdom, p);

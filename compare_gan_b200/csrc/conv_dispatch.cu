@@ -26,6 +26,19 @@ int cgan_conv2d_wgrad_simt(cgan_ctx* ctx, const cgan_conv_desc* d, const float* 
 bool cgan_wgrad_thin_ok(const cgan_conv_desc* d);
 int cgan_wgrad_thin(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, float* dw);
 
+// image-side convolutions (<= 4 input or output channels) through a 32-wide patch tensor on the tensor cores (thin_tc.cu)
+bool cgan_thin_tc_cin_ok(cgan_ctx* ctx, const cgan_conv_desc* d);
+bool cgan_thin_tc_wgrad_cin_ok(cgan_ctx* ctx, const cgan_conv_desc* d);
+bool cgan_thin_tc_dgrad_cin_ok(cgan_ctx* ctx, const cgan_conv_desc* d);
+bool cgan_thin_tc_cout_ok(cgan_ctx* ctx, const cgan_conv_desc* d);
+bool cgan_thin_tc_wgrad_cout_ok(cgan_ctx* ctx, const cgan_conv_desc* d);
+int cgan_thin_tc_fwd_cin(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const cgan_conv_epilogue* ep, float* y);
+int cgan_thin_tc_wgrad_cin(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* dy, int dy_tf32, float* dw);
+int cgan_thin_tc_dgrad_cin(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, const cgan_conv_epilogue* ep, float* dx);
+int cgan_thin_tc_fwd_cout(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* w, const cgan_conv_epilogue* ep, float* y);
+int cgan_thin_tc_dgrad_cout(cgan_ctx*, const cgan_conv_desc*, const float* dy, const float* w, const cgan_conv_epilogue* ep, float* dx);
+int cgan_thin_tc_wgrad_cout(cgan_ctx*, const cgan_conv_desc*, const float* x, const float* dy, int x_tf32, float* dw);
+
 namespace {
 
 inline TcExtra tc_extra(const cgan_conv_epilogue* ep, bool tf32_in) {
@@ -82,6 +95,16 @@ int cgan_conv2d_fwd_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, c
   const bool ptr_ok = al16p(x) && al16p(y) && (!bias || al16p(bias)) && (!ep || ((!ep->residual || al16p(ep->residual)) &&
                                                                                   (!ep->mask || al16p(ep->mask))));
   TcExtra ex = tc_extra(ep, x_tf32);
+  if (ctx->tc_thin && ptr_ok && ld_ok && al16p(w) && !(d->kh == 1 && d->kw == 1)) {
+    if (cgan_thin_tc_cin_ok(ctx, d)) {
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_fwd_cin(ctx, d, x, w, ep, y);
+    }
+    if (ldy == d->cout && cgan_thin_tc_cout_ok(ctx, d)) {
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_fwd_cout(ctx, d, x, w, ep, y);
+    }
+  }
   // a 1x1 kernel over a zero-inserted input (BigGAN's up-sampling shortcut): phase (0,0) is a plain 1x1 conv written to the
   // even pixels, the other three phases are bias only
   if (ctx->math_mode == 1 && d->stride == 1 && d->upsample && d->kh == 1 && d->kw == 1 && d->oh == 2 * d->h &&
@@ -211,6 +234,16 @@ int cgan_conv2d_dgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* dy
                       (!ep || ((!ep->residual || al16p(ep->residual)) && (!ep->mask || al16p(ep->mask))));
   TcExtra ex = tc_extra(ep, dy_tf32);
   const bool geom = d->oh == (d->upsample ? 2 * d->h : d->h) && d->ow == (d->upsample ? 2 * d->w : d->w);
+  if (ctx->tc_thin && ptr_ok && al16p(w) && !(d->kh == 1 && d->kw == 1)) {
+    if (cgan_thin_tc_cout_ok(ctx, d)) {          // dy has <= 4 channels (the generator's image conv)
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_dgrad_cout(ctx, d, dy, w, ep, dx);
+    }
+    if (cgan_thin_tc_dgrad_cin_ok(ctx, d)) {     // dx has <= 4 channels (gradient w.r.t. the discriminator's input image)
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_dgrad_cin(ctx, d, dy, w, ep, dx);
+    }
+  }
   if (ctx->math_mode == 1 && d->stride == 1 && d->kh * d->kw <= 32 && geom &&
       cgan_tc_shape_ok(d->n, d->h, d->w, d->cout, d->cin) && ptr_ok) {
     // dx[n,ih,iw,ci] = sum_{kh,kw,co} dy[n, oh, ow, co] * w[kh,kw,ci,co]: HWIO is already [tap][row=ci][k=co], i.e.
@@ -297,6 +330,16 @@ int cgan_conv2d_wgrad(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, co
 int cgan_conv2d_wgrad_ex(cgan_ctx* ctx, const cgan_conv_desc* d, const float* x, const float* dy, int flags, float* dw) {
   if (!ctx) return CGAN_ERR_ARG;
   CGAN_REQUIRE(ctx, d && x && dy && dw, "null pointer");
+  if (ctx->tc_thin && d->n > 0 && d->kh * d->kw > 1 && al16p(x) && al16p(dy) && al16p(dw)) {
+    if (cgan_thin_tc_wgrad_cin_ok(ctx, d)) {
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_wgrad_cin(ctx, d, x, dy, (flags & CGAN_CONV_IN2_TF32) ? 1 : 0, dw);
+    }
+    if (cgan_thin_tc_wgrad_cout_ok(ctx, d)) {
+      ctx->last_path = CGAN_PATH_TCGEN05_TF32;
+      return cgan_thin_tc_wgrad_cout(ctx, d, x, dy, (flags & CGAN_CONV_IN_TF32) ? 1 : 0, dw);
+    }
+  }
   if (d->n > 0 && d->cin > 0 && d->cout > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0 && cgan_wgrad_thin_ok(d)) {
     ctx->last_path = CGAN_PATH_THIN_FP32;
     return cgan_wgrad_thin(ctx, d, x, dy, dw);      // exact fp32 streaming kernels for 3-channel image-side layers

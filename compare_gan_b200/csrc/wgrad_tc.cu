@@ -250,6 +250,12 @@ int pick_bn(int ncols) {
 
 }  // namespace
 
+// can the pixel loop of a stride-1 n x h x w grid be cut into 32-pixel TMA boxes?
+bool cgan_wgrad_tc_geometry_ok(int n, int h, int w) {
+  int bw, bh, bni;
+  return box32(n, h, w, &bw, &bh, &bni);
+}
+
 bool cgan_wgrad_tc_ok(const cgan_conv_desc* d) {
   if ((d->stride != 1 && d->stride != 2) || d->kh * d->kw > WG_MAX_TAPS) return false;
   if (d->stride == 2) {
