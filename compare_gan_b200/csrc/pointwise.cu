@@ -33,6 +33,8 @@ int cgan_ctx_create(cgan_ctx** out, int device) {
   if (const char* e = getenv("CGAN_TC_EPI")) c->tc_epi = atoi(e) ? 1 : 0;
   c->tc_halo = 1;
   if (const char* e = getenv("CGAN_TC_HALO")) c->tc_halo = atoi(e) ? 1 : 0;
+  c->tc_thin = 1;
+  if (const char* e = getenv("CGAN_TC_THIN")) c->tc_thin = atoi(e) ? 1 : 0;
   c->stream = 0;
   if (cudaMalloc(reinterpret_cast<void**>(&c->counters), CGAN_NUM_COUNTERS * sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(c->counters, 0, CGAN_NUM_COUNTERS * sizeof(unsigned)) != cudaSuccess) {
@@ -89,6 +91,10 @@ int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value) {
       CGAN_REQUIRE(ctx, value >= 0 && value <= 2, "CGAN_OPT_TC_HALO must be 0, 1 or 2");
       ctx->tc_halo = (int)value;
       return CGAN_OK;
+    case CGAN_OPT_TC_THIN:
+      CGAN_REQUIRE(ctx, value == 0 || value == 1, "CGAN_OPT_TC_THIN must be 0 or 1");
+      ctx->tc_thin = (int)value;
+      return CGAN_OK;
     default:
       return cgan_fail(ctx, CGAN_ERR_ARG, "%s: unknown or read-only option%s", "cgan_ctx_set_option");
   }
@@ -103,6 +109,7 @@ int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value) {
     case CGAN_OPT_TC_HALO: *host_value = ctx->tc_halo; return CGAN_OK;
     case CGAN_OPT_TC_PAIR: *host_value = ctx->tc_pair; return CGAN_OK;
     case CGAN_OPT_TC_EPI: *host_value = ctx->tc_epi; return CGAN_OK;
+    case CGAN_OPT_TC_THIN: *host_value = ctx->tc_thin; return CGAN_OK;
     default:
       return cgan_fail(ctx, CGAN_ERR_ARG, "%s: unknown option%s", "cgan_ctx_get_option");
   }
@@ -764,6 +771,25 @@ int cgan_conv_post_epilogue(cgan_ctx* ctx, float* y, int64_t rows, int c, int ld
   conv_post_kernel<<<ew_grid(ctx, rows * c), 256, 0, ctx->stream>>>(y, rows, c, ld, residual, mask, mask_leak, relu, round_out);
   CGAN_LAUNCHED(ctx);
   return CGAN_OK;
+}
+
+namespace {
+__global__ void random_uniform_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+  EW_LOOP(i, n) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (offset + (unsigned long long)i + 1ull);     // SplitMix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = (float)(z >> 40) * (1.0f / 16777216.0f);
+  }
+}
+}  // namespace
+
+int cgan_random_uniform(cgan_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && n >= 0, "bad argument");
+  if (n == 0) return CGAN_OK;
+  random_uniform_kernel<<<ew_grid(ctx, n), 256, 0, ctx->stream>>>(out, n, seed, offset);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 
 int cgan_rot90(cgan_ctx* ctx, float* y, const float* x, int n, int hw, int c, int k) {

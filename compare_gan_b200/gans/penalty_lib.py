@@ -1,10 +1,11 @@
 """Gradient penalties (reference gans/penalty_lib.py:28-108)."""
-import torch
-
 from .. import gin_lite as gin
 from .. import kernels as K
 from .. import tape
 from .. import utils
+
+
+_ALPHA_RNG = {"seed": 0x5EEDA1FA, "offset": 0}     # stream of the un-fed interpolation coefficients (per process)
 
 
 @gin.configurable
@@ -18,7 +19,11 @@ def wgangp_penalty(discriminator, x, x_fake, y, is_training, alpha=None):
   """WGAN gradient penalty (reference penalty_lib.py:59-82).  `alpha` [B,1,1,1] may be fed (parity tests,
   bench); otherwise it is drawn U[0,1) on the device."""
   if alpha is None:
-    alpha = tape.DT(torch.rand(x.shape[0], 1, 1, 1, device=x.t.device, dtype=torch.float32))
+    # tf.random.uniform (penalty_lib.py:72-73) through the library's counter-based generator (cgan_random_uniform): no
+    # torch op on the product path; successive draws advance the offset
+    alpha = K.empty(x.shape[0], 1, 1, 1)
+    K._call("random_uniform", alpha.ptr, alpha.numel, _ALPHA_RNG["seed"], _ALPHA_RNG["offset"])
+    _ALPHA_RNG["offset"] += alpha.numel
   interpolates = K.interpolate(x, x_fake, alpha)
   interpolates.req = True                      # differentiate the logits wrt this leaf
   with tape.record(True):

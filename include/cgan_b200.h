@@ -49,8 +49,13 @@ int64_t cgan_launch_count(cgan_ctx* ctx);
  *   CGAN_OPT_TC_EPI     (set/get) 1 (default): the tcgen05 convolution epilogue transposes each 32 x 32 accumulator chunk through
  *                       shared memory so that stores (and the fused residual / mask reads) cover whole 128-byte lines;
  *                       0: every thread stores its own row (the round-1 epilogue; results are bit-identical).
+ *   CGAN_OPT_TC_THIN    (set/get) 1 (default): in math_mode 1 the image-side convolutions (<= 4 input or <= 4 output channels,
+ *                       kh*kw*channels <= 32: every discriminator's first and every generator's last convolution, Inception's
+ *                       stem) run as ONE 32-wide GEMM on the tcgen05 kernels over a [pixels, 32] patch tensor (csrc/thin_tc.cu),
+ *                       TF32 operands like every other tensor-core contraction; 0: the exact-fp32 streaming kernels (thin.cu).
  *   CGAN_OPT_LAST_PATH  (get) CGAN_PATH_* taken by the most recent conv2d_fwd / dgrad / wgrad / gemm_batched call. */
-enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3, CGAN_OPT_TC_PAIR = 4, CGAN_OPT_TC_EPI = 5 };
+enum { CGAN_OPT_TC_MT = 1, CGAN_OPT_LAST_PATH = 2, CGAN_OPT_TC_HALO = 3, CGAN_OPT_TC_PAIR = 4, CGAN_OPT_TC_EPI = 5,
+       CGAN_OPT_TC_THIN = 6 };
 enum { CGAN_PATH_SIMT_FP32 = 0, CGAN_PATH_TCGEN05_TF32 = 1, CGAN_PATH_THIN_FP32 = 2 };
 int cgan_ctx_set_option(cgan_ctx* ctx, int key, int64_t value);
 int cgan_ctx_get_option(cgan_ctx* ctx, int key, int64_t* host_value);
@@ -67,6 +72,10 @@ int cgan_axpby(cgan_ctx*, float* y, float a, const float* x, float b, const floa
 int cgan_scale_by_dev(cgan_ctx*, float* y, const float* x, const float* scalar_dev, float mul, int inverse, int64_t n);
 /* out[0] = sum_i a[i]*b[i]  (deterministic two-stage) — d sigma of non_local_block, SN backward */
 int cgan_dot(cgan_ctx*, float* out_dev, const float* a, const float* b, int64_t n);
+/* out[i] = uniform [0, 1) from the counter-based generator SplitMix64(seed, offset + i) (24 mantissa bits): the
+ * tf.random.uniform draws of the gradient penalties (gans/penalty_lib.py:72-73) when the caller does not feed them.
+ * Stateless: the same (seed, offset) always yields the same numbers, on any launch configuration. */
+int cgan_random_uniform(cgan_ctx*, float* out, int64_t n, uint64_t seed, uint64_t offset);
 /* y[n,:] = x[n,:] + alpha[n]*(xf[n,:]-x[n,:]) — WGAN-GP interpolates (gans/penalty_lib.py:74-75) */
 int cgan_interpolate(cgan_ctx*, float* y, const float* x, const float* xf, const float* alpha, int n, int64_t per);
 /* one-hot rows: out[n, labels[n]] = 1 (gans/modular_gan.py:359-363) */

@@ -73,10 +73,10 @@ class EmulatedLib(object):
     return self.launches
 
   def get_option(self, key):
-    return {1: 2, 2: self.last_path, 3: 1, 4: 0, 5: 1}[key]
+    return {1: 2, 2: self.last_path, 3: 1, 4: 0, 5: 1, 6: 1}[key]
 
   def set_option(self, key, value):
-    assert (key == 1 and value in (1, 2)) or (key == 3 and value in (0, 1, 2)) or (key in (4, 5) and value in (0, 1))
+    assert (key == 1 and value in (1, 2)) or (key == 3 and value in (0, 1, 2)) or (key in (4, 5, 6) and value in (0, 1))
 
   def call(self, name, *args):
     self.launches += 1
@@ -95,9 +95,13 @@ class EmulatedLib(object):
 
   def _tc(self, d=None):
     """math_mode 1 is emulated as the tensor-core ARITHMETIC (operands rounded to the nearest TF32 value, fp32
-    accumulation) for every contraction with more than 4 input channels; the image-side layers stay exact like the thin
-    kernels.  Sets the path CGAN_OPT_LAST_PATH reports."""
-    tc = self.math_mode == 1 and (d is None or (d.cin > 4 and d.cout > 4))
+    accumulation) for every contraction with more than 4 input and output channels, and for the image-side layers whose
+    taps fit one 32-wide patch row (the library runs those as 32-wide GEMMs, csrc/thin_tc.cu); other thin layers stay exact.  Sets the path CGAN_OPT_LAST_PATH reports."""
+    thin = d is not None and min(d.cin, d.cout) <= 4
+    if thin:      # image-side layers: a 32-wide GEMM over patch tensors (csrc/thin_tc.cu) when kh*kw*channels fits one row
+      thin_tc = (not d.upsample and d.kh * d.kw > 1 and d.kh * d.kw * min(d.cin, d.cout) <= 32 and
+                 max(d.cin, d.cout) >= 32 and max(d.cin, d.cout) % 4 == 0 and (d.cin <= 4 or d.stride == 1))
+    tc = self.math_mode == 1 and (d is None or not thin or thin_tc)
     self.last_path = 1 if tc else 0
     return tc
 
@@ -125,6 +129,15 @@ class EmulatedLib(object):
 
   def cgan_dot(self, out_dev, a, b, n):
     f32(out_dev, 1)[0] = np.float32(np.dot(f32(a, n).astype(np.float64), f32(b, n).astype(np.float64)))
+
+  def cgan_random_uniform(self, out, n, seed, offset):
+    m = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+      z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (np.uint64(offset) + np.arange(1, n + 1, dtype=np.uint64))
+      z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+      z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+      z = z ^ (z >> np.uint64(31))
+    f32(out, n)[:] = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
 
   def cgan_interpolate(self, y, x, xf, alpha, n, per):
     xa, xb = f32(x, n * per).reshape(n, per), f32(xf, n * per).reshape(n, per)

@@ -491,6 +491,9 @@ def test_conv2d_tcgen05_tf32(K, n, h, cin, cout, k, up):
     launched = K.lib().launch_count() - n0
     if k == 1 and up:
       assert launched == 3, "1x1 up-sampling conv: weight prep + one tcgen05 phase + bias fill, got %d" % launched
+    elif min(cin, cout) <= 4 and not up:
+      # image-side layer (csrc/thin_tc.cu): filter re-layout + weight prep + ONE 32-wide tcgen05 GEMM + the shift-add pass
+      assert launched == 4, "expected the patch-tensor tcgen05 path (4 launches), got %d" % launched
     elif k * k <= 32:
       # (the four sub-pixel phases of a convolution over a zero-inserted input share one weight preparation and ONE launch)
       assert launched == 2, "expected the tcgen05 path (weight prep + one launch), got %d launches" % launched
@@ -701,3 +704,75 @@ def test_attention_falls_back_for_shapes_the_fused_kernel_does_not_take(K):
       K.set_math_mode(0)
     assert_close(y.cpu(), ref.numpy(), 1e-3 if mode else TOL, "composed attention")
   assert not K.attention_shape_ok(2, 4096, 1024, 24, 96), "math_mode 0 never takes the TF32 kernel"
+
+
+THIN_TC_CASES = [
+    # n, h, cin, cout, k, stride, padding          image-side layers of the BASELINE architectures
+    (8, 32, 3, 128, 3, 1, "SAME"),     # resnet_cifar / sndcgan D: first conv
+    (4, 64, 3, 96, 3, 1, "SAME"),      # BigGAN D block 1 conv1 (ch = 96)
+    (4, 32, 256, 3, 3, 1, "SAME"),     # resnet_cifar G: image conv
+    (2, 64, 96, 3, 3, 1, "SAME"),      # BigGAN G: image conv
+    (2, 75, 3, 32, 3, 2, "VALID"),     # Inception-v3 stem (299 -> 149 at full size): stride 2, VALID
+    (3, 16, 1, 64, 5, 1, "SAME"),      # one input channel, 25 taps
+    (2, 32, 64, 4, 3, 1, "SAME"),      # four output channels: 36 > 32 values per pixel -> stays on the streaming kernels
+]
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,stride,pad", THIN_TC_CASES)
+def test_thin_convolutions_on_tensor_cores(K, n, h, cin, cout, k, stride, pad):
+  """math_mode 1: convolutions with <= 4 input or output channels run as one 32-wide tcgen05 GEMM over a [pixels, 32] patch
+  tensor (csrc/thin_tc.cu) — forward, input gradient and filter gradient against the fp32 oracle at north_star's 1e-3, and
+  against the exact-fp32 streaming kernels they replace (CGAN_OPT_TC_THIN = 0)."""
+  from compare_gan_b200 import _lib
+  rng = np.random.RandomState(n + h + cin + cout)
+  x = rng.randn(n, h, h, cin).astype(np.float32)
+  w = (rng.randn(k, k, cin, cout) / np.sqrt(k * k * cin)).astype(np.float32)
+  b = rng.randn(cout).astype(np.float32)
+  xt, wt = torch.from_numpy(x).requires_grad_(True), torch.from_numpy(w).requires_grad_(True)
+  if pad == "SAME":
+    ref = T.conv2d_same(xt, wt, stride) + torch.from_numpy(b)
+  else:
+    ref = F.conv2d(xt.permute(0, 3, 1, 2), wt.permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1) + torch.from_numpy(b)
+  gy = rng.randn(*ref.shape).astype(np.float32)
+  ref.backward(torch.from_numpy(gy))
+  refs = [ref.detach().numpy(), xt.grad.numpy(), wt.grad.numpy()]
+  expect_tc = k * k * min(cin, cout) <= 32
+  lib = K.lib()
+  results = {}
+  K.set_math_mode(1)
+  try:
+    for thin in (1, 0):
+      lib.set_option(_lib.OPT_TC_THIN, thin)
+      xd, wd, bd = dev(K, x, True), dev(K, w, True), dev(K, b, True)
+      y = K.conv2d(xd, wd, bd, stride=stride, padding=pad)
+      path = _lib.PATH_NAMES[lib.get_option(_lib.OPT_LAST_PATH)]
+      gx, gw = tape_grads(K, y, gy, [xd, wd])
+      results[thin] = ([y.cpu(), gx.cpu(), gw.cpu()], path)
+  finally:
+    lib.set_option(_lib.OPT_TC_THIN, 1)
+    K.set_math_mode(0)
+  if not getattr(lib, "emulated", False):
+    assert results[1][1] == ("tcgen05_tf32" if expect_tc else results[0][1]), results[1][1]
+    assert results[0][1] != "tcgen05_tf32" or min(cin, cout) > 4 or cout <= 4, results[0][1]
+  for name, a, a0, r in zip(("fwd", "dgrad", "wgrad"), results[1][0], results[0][0], refs):
+    assert_close(a, r, 1e-3, "thin-tc %s vs fp32 oracle" % name)
+    assert_close(a, a0, 1e-3, "thin-tc %s vs streaming kernels" % name)
+
+
+def test_random_uniform_is_the_documented_counter_based_stream(K):
+  """cgan_random_uniform (the un-fed WGAN-GP interpolation coefficients, penalty_lib.py:72-73): SplitMix64(seed, offset + i),
+  top 24 bits -> [0, 1); stateless, so two launches over adjacent ranges continue one stream."""
+  n, seed = 4099, 0x5EEDA1FA
+  out = K.empty(n)
+  K._call("random_uniform", out.ptr, 1000, seed, 7)
+  K._call("random_uniform", out.ptr + 4 * 1000, n - 1000, seed, 1007)
+  got = out.cpu()
+  idx = np.arange(1, n + 1, dtype=np.uint64) + np.uint64(7)
+  with np.errstate(over="ignore"):
+    z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * idx
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+  ref = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+  np.testing.assert_array_equal(got, ref)
+  assert 0.0 <= got.min() and got.max() < 1.0 and abs(got.mean() - 0.5) < 0.02
