@@ -362,6 +362,8 @@ def run_ours(args):
       release(mf)
     if world > 1:
       dp = dp_equivalence(world, rank)
+  elif world > 1 and args.dp_check:
+    dp = dp_equivalence(world, rank)
 
   out = None
   if rank == 0:
@@ -535,6 +537,7 @@ def main():
   ap.add_argument("--eval-samples", type=int, default=0)
   ap.add_argument("--no-eval", action="store_true")
   ap.add_argument("--headline-only", action="store_true", help="skip the extra workload / fp32 / dp-equivalence legs")
+  ap.add_argument("--dp-check", action="store_true", help="with --headline-only at N > 1: still run the in-run dp_equivalence check")
   ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs only)")
   ap.add_argument("--eager", action="store_true", help="do not capture the cycle into a CUDA graph (profiling runs only)")
   args = ap.parse_args()

@@ -244,7 +244,48 @@ class ModularGAN(AbstractGAN):
       K._call("copy", self.losses.ptr + 4 * k, self.g_loss.ptr, 1)
       self.d_loss = self.g_loss = None
 
+  def _substep(self):
+    """One step of the NON-unrolled schedule (reference model_fn with unroll_graph False, :534-535, 566-575 — the
+    reference's default off TPU): ONE batch, one generator forward, one discriminator update, and a generator update only
+    when the discriminator step counter reaches a multiple of disc_iters (`tf.cond(disc_step % disc_iters == 0, ...)`,
+    evaluated after the D update).  Uses input slot 0; the device step counters advance exactly as in TF (global_step
+    counts G updates, global_step_disc D updates).  Returns True when the G update ran.  Eager only: the branch is taken
+    on the host from a mirror of the device counter (one 4-byte read), which is what makes it uncapturable."""
+    k = self._disc_iters
+    will_g = (int(self.d_opt.step.item()) + 1) % k == 0
+    with V.use(self.store):
+      f = dict(self.inputs[0])
+      sy = self._get_one_hot_labels(f["sampled_labels"]) if self.conditional else None
+      with tape.record(will_g):
+        gen = self.generator(f["z"], y=sy, is_training=True)          # _split_inputs_and_generate_samples, one sub-step
+      d_params = self.store.trainable_under("discriminator")
+      g_params = self.store.trainable_under("generator")
+      ones = K.fill_(K.empty(1), 1.0)
+      f["generated"] = tape.DT(gen.t)                                   # tf.stop_gradient (:476)
+      self.create_loss(f, f.get("labels"), for_discriminator=True)
+      grads = tape.backward([(self.d_loss, ones)], list(d_params.values()), K.add_grad,
+                            sinks=self._grad_sinks("discriminator", d_params))
+      scale = self._apply_grads("discriminator", self.flat_d, grads, list(d_params.keys()))
+      self.d_opt.apply(scale)
+      K._call("copy", self.losses.ptr, self.d_loss.ptr, 1)
+      self.d_loss = self.g_loss = None
+      if will_g:
+        f["generated"] = gen
+        self.create_loss(f, f.get("labels"), for_discriminator=False)
+        grads = tape.backward([(self.g_loss, ones)], list(g_params.values()), K.add_grad,
+                              sinks=self._grad_sinks("generator", g_params))
+        scale = self._apply_grads("generator", self.flat_g, grads, list(g_params.keys()))
+        self.g_opt.apply(scale, self.ema, self._ema_decay, self._ema_start_step)
+        K._call("copy", self.losses.ptr + 4 * k, self.g_loss.ptr, 1)
+        self.d_loss = self.g_loss = None
+    return will_g
+
   # ---- public step API -------------------------------------------------------------------------------------
+  def run_substep(self):
+    """One step of the reference's non-unrolled (CPU / GPU default) schedule on input slot 0, see _substep."""
+    K.sync_stream()
+    return self._substep()
+
   def set_inputs(self, images, z, labels=None, sampled_labels=None, alphas=None, non_blocking=True):
     """Host -> device copy of one cycle's inputs (lists of length disc_iters+1 of numpy / pinned torch arrays)."""
     def put(dst, src):

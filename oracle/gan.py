@@ -194,6 +194,37 @@ class GanOracle(object):
     return d_losses, float(g_loss.detach())
 
 
+  def substep(self, images, z, labels=None, sampled_labels=None, alpha=None):
+    """One step of the NON-unrolled schedule (modular_gan.py:534-535 num_sub_steps = 1, :566-575): one batch, one G forward
+    (its samples feed the D update detached and, when it runs, the G update with gradients), one D update, and the G
+    update iff global_step_disc % disc_iters == 0 after the D update.  Returns (d_loss, g_loss or None)."""
+    self._ensure_opts()
+    y = self.one_hot(labels) if self.conditional else None
+    sy = self.one_hot(sampled_labels) if self.conditional else None
+    will_g = (self.global_step_disc + 1) % self.disc_iters == 0
+    with torch.set_grad_enabled(will_g):
+      gen = nets.generator(self.store, self.cfg, torch.as_tensor(z).to(self.dtype), sy, True)
+    img = torch.as_tensor(images).to(self.dtype)
+    d_loss, _ = self.create_loss(img, gen.detach(), y, sy, None if alpha is None else torch.as_tensor(alpha).to(self.dtype))
+    params = self.store.trainable_under("discriminator")
+    grads = torch.autograd.grad(d_loss, list(params.values()), allow_unused=True)
+    self.d_opt.step({n: (g if g is not None else torch.zeros_like(p)) for (n, p), g in zip(params.items(), grads)})
+    self.global_step_disc += 1
+    if not will_g:
+      return float(d_loss.detach()), None
+    _, g_loss = self.create_loss(img, gen, y, sy, None, for_d=False)
+    params = self.store.trainable_under("generator")
+    grads = torch.autograd.grad(g_loss, list(params.values()), allow_unused=True)
+    self.g_opt.step({n: (g if g is not None else torch.zeros_like(p)) for (n, p), g in zip(params.items(), grads)})
+    if self.g_use_ema:
+      decay = self.ema_decay * float(self.global_step >= self.ema_start_step)
+      with torch.no_grad():
+        for n, p in params.items():
+          self.ema[n].sub_((self.ema[n] - p) * (1.0 - decay))
+    self.global_step += 1
+    return float(d_loss.detach()), float(g_loss.detach())
+
+
 # --------------------------------------------------------------------------- SSGAN (gans/ssgan.py)
 
 def rotate_images(images, rot90_scalars=(0, 1, 2, 3)):

@@ -116,3 +116,34 @@ def test_every_objective_through_a_full_cycle(loss):
     ref_d, ref_g = orc.cycle(*inputs)
     assert abs(d_losses[0] - ref_d[0]) <= 1e-4 * max(1.0, abs(ref_d[0])) and abs(g_loss - ref_g) <= 1e-4 * max(1.0, abs(ref_g))
     compare_grads(eng, orc, 2e-3, g_tol=5e-2)
+
+
+def test_non_unrolled_schedule_matches_the_reference_default():
+  """modular_gan.py:534-535, 566-575 (unroll_graph False — the reference's schedule off TPU, modular_gan_test.py:149-177):
+  every step is ONE discriminator update on one batch; the generator update runs only when global_step_disc reaches a
+  multiple of disc_iters.  Engine (ModularGAN.run_substep) vs oracle (oracle/gan.py substep) over 4 steps at disc_iters
+  = 3: losses, which steps updated G, the two step counters, and the state after the last step."""
+  import numpy as np
+  from tests.gpu_util import compare_states, make_inputs, make_pair
+  with emulated_library():
+    eng, orc = make_pair("resnet_cifar_arch", (32, 32, 3), 2, d_sn=True, disc_iters=3, g_use_ema=True, ema_start_step=0)
+    rng = np.random.RandomState(5)
+    g0 = eng.state_numpy()
+    ran_g = []
+    for step in range(4):
+      imgs, zs, _, _, _ = make_inputs(rng, 3, 2, (32, 32, 3), 128)
+      eng.set_inputs(imgs, zs)
+      did = eng.run_substep()
+      d_losses, g_loss = eng.read_losses()
+      ref_d, ref_g = orc.substep(imgs[0], zs[0])
+      assert did == (ref_g is not None)
+      ran_g.append(did)
+      assert abs(d_losses[0] - ref_d) <= 1e-4 * max(1.0, abs(ref_d)), (step, d_losses[0], ref_d)
+      if did:
+        assert abs(g_loss - ref_g) <= 1e-4 * max(1.0, abs(ref_g)), (step, g_loss, ref_g)
+      if step == 1:       # two D updates in, G untouched: its trainable weights are still the initial ones
+        s1 = eng.state_numpy()
+        assert all(np.array_equal(s1[k], g0[k]) for k in orc.store.trainable if k.startswith("generator/"))
+    assert ran_g == [False, False, True, False]
+    assert int(eng.d_opt.step.item()) == 4 == orc.global_step_disc and int(eng.g_opt.step.item()) == 1 == orc.global_step
+    compare_states(eng, orc, {"generator": 2e-4, "discriminator": 2e-4}, {"generator": 1, "discriminator": 4})
