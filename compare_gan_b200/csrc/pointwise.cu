@@ -306,6 +306,47 @@ __global__ void rotation_loss_kernel(float* loss, float* dlogits, const float* _
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) *loss = acc / rows;
 }
+// S3GAN heads (gans/s3gan.py:121-122, 149-150, 312-313); rows = examples of one sub-step, cols = classes
+__global__ void row_has_label_kernel(float* __restrict__ out, const float* __restrict__ y, int rows, int cols) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < cols; ++j) s += y[(long long)r * cols + j];
+    out[r] = s > 0.5f ? 1.f : 0.f;
+  }
+}
+__global__ void argmax_one_hot_kernel(float* __restrict__ out, const float* __restrict__ z, int rows, int cols) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float* row = z + (long long)r * cols;
+    int best = 0;
+    for (int j = 1; j < cols; ++j)
+      if (row[j] > row[best]) best = j;
+    for (int j = 0; j < cols; ++j) out[(long long)r * cols + j] = j == best ? 1.f : 0.f;
+  }
+}
+// one block: weighted soft-label cross entropy, SUM_BY_NONZERO_WEIGHTS
+__global__ void softmax_xent_kernel(float* loss, float* dlogits, const float* __restrict__ z, const float* __restrict__ lab,
+                                    const float* __restrict__ w, int rows, int cols) {
+  __shared__ float sh[32];
+  float acc = 0.f, present = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) present += (w ? w[r] : 1.f) != 0.f ? 1.f : 0.f;
+  present = block_sum(present, sh);
+  const float inv = present > 0.f ? 1.f / present : 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* zr = z + (long long)r * cols;
+    const float* lr = lab + (long long)r * cols;
+    float mx = zr[0];
+    for (int j = 1; j < cols; ++j) mx = fmaxf(mx, zr[j]);
+    float den = 0.f, lsum = 0.f, dot = 0.f;
+    for (int j = 0; j < cols; ++j) { den += expf(zr[j] - mx); lsum += lr[j]; dot += lr[j] * (zr[j] - mx); }
+    const float lden = logf(den);
+    const float wr = w ? w[r] : 1.f;
+    acc += wr * (lsum * lden - dot);                   // -sum_j l_j (z_j - mx - log den)
+    if (dlogits)
+      for (int j = 0; j < cols; ++j) dlogits[(long long)r * cols + j] = wr * inv * (lsum * expf(zr[j] - mx) / den - lr[j]);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *loss = acc * inv;
+}
 __global__ void add_kernel(float* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b, long long n, int rnd) {
   const long long n4 =
       ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) ? 0 : n >> 2;
@@ -801,6 +842,22 @@ int cgan_rotation_loss(cgan_ctx* ctx, float* loss_out, float* dlogits, const flo
   NONNULL(ctx);
   CGAN_REQUIRE(ctx, loss_out && logits && rows > 0 && num_rotations > 0 && rows % num_rotations == 0, "rows must be a multiple of num_rotations");
   rotation_loss_kernel<<<1, 256, 0, ctx->stream>>>(loss_out, dlogits, logits, rows, num_rotations);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_row_has_label(cgan_ctx* ctx, float* out, const float* y, int rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && y && rows > 0 && cols > 0, "bad argument");
+  row_has_label_kernel<<<ew_grid(ctx, rows), 256, 0, ctx->stream>>>(out, y, rows, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_argmax_one_hot(cgan_ctx* ctx, float* out, const float* logits, int rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, out && logits && rows > 0 && cols > 0, "bad argument");
+  argmax_one_hot_kernel<<<ew_grid(ctx, rows), 256, 0, ctx->stream>>>(out, logits, rows, cols);
+  CGAN_LAUNCHED(ctx); return CGAN_OK;
+}
+int cgan_softmax_xent(cgan_ctx* ctx, float* loss_out, float* dlogits, const float* logits, const float* labels,
+                      const float* weights, int rows, int cols) {
+  NONNULL(ctx); CGAN_REQUIRE(ctx, loss_out && logits && labels && rows > 0 && cols > 0, "bad argument");
+  softmax_xent_kernel<<<1, 256, 0, ctx->stream>>>(loss_out, dlogits, logits, labels, weights, rows, cols);
   CGAN_LAUNCHED(ctx); return CGAN_OK;
 }
 int cgan_add(cgan_ctx* ctx, float* y, const float* a, const float* b, int64_t n) { return cgan_add_tf32(ctx, y, a, b, n, 0); }

@@ -437,3 +437,4 @@ class ModularGAN(AbstractGAN):
 
 
 from . import ssgan  # noqa: E402,F401  (registers @SSGAN with gin wherever ModularGAN is importable)
+from . import s3gan  # noqa: E402,F401  (registers @S3GAN)

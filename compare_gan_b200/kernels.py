@@ -259,6 +259,34 @@ def rotation_loss(logits, num_rotations=4):
   return attach("rotation_loss", loss, [logits], lambda g, needs: [_scale_by(dl, g)])
 
 
+def row_has_label(y):
+  """[N, 1] indicator: 1 where the (one-hot or soft) label row sums to more than 0.5, i.e. a label was passed
+  (gans/s3gan.py:121-122).  A constant for differentiation."""
+  rows, cols = y.shape
+  out = empty(rows, 1)
+  _call("row_has_label", out.ptr, y.ptr, rows, cols)
+  return out
+
+
+def argmax_one_hot(logits):
+  """tf.one_hot(tf.arg_max(logits, 1), classes) (gans/s3gan.py:149-150); a constant for differentiation."""
+  rows, cols = logits.shape
+  out = empty(rows, cols)
+  _call("argmax_one_hot", out.ptr, logits.ptr, rows, cols)
+  return out
+
+
+def softmax_xent(logits, labels, weights=None):
+  """tf.losses.softmax_cross_entropy(labels, logits, weights=weights) (SUM_BY_NONZERO_WEIGHTS; gans/s3gan.py:312-313): a
+  one-element device tensor, differentiable w.r.t. the logits."""
+  rows, cols = logits.shape
+  if labels.shape != (rows, cols) or (weights is not None and weights.numel != rows):
+    raise ValueError("softmax_xent: labels %s / weights do not match logits %s" % (labels.shape, logits.shape))
+  loss, dl = empty(1), empty(rows, cols)
+  _call("softmax_xent", loss.ptr, dl.ptr, logits.ptr, labels.ptr, None if weights is None else weights.ptr, rows, cols)
+  return attach("softmax_xent", loss, [logits], lambda g, needs: [_scale_by(dl, g)])
+
+
 def concat_cols(a, b):
   """tf.concat([a, b], axis=1) for rank-2 tensors (resnet_biggan.py:254)."""
   n, ca, cb = a.shape[0], a.shape[1], b.shape[1]

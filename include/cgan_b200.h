@@ -261,6 +261,18 @@ int cgan_rot90(cgan_ctx*, float* y, const float* x, int n, int hw, int c, int k)
  * *loss_out = -mean log(softmax(logits)[label] + 1e-10) (ssgan.py:205-213); dlogits (nullable) = its gradient. */
 int cgan_rotation_loss(cgan_ctx*, float* loss_out, float* dlogits, const float* logits, int rows, int num_rotations);
 
+/* ---- S3GAN heads (gans/s3gan.py) --------------------------------------------------------------------------------------
+ * out[r] = 1 if sum_j y[r, j] > 0.5 else 0: "is a label available for this example" (s3gan.py:121-122). */
+int cgan_row_has_label(cgan_ctx*, float* out, const float* y, int rows, int cols);
+/* out[r, :] = one_hot(argmax_j logits[r, j]) (first maximum wins, like tf.argmax): the predictor's hard labels
+ * (s3gan.py:149-150). */
+int cgan_argmax_one_hot(cgan_ctx*, float* out, const float* logits, int rows, int cols);
+/* tf.losses.softmax_cross_entropy(onehot_labels = labels, logits, weights) with its default SUM_BY_NONZERO_WEIGHTS reduction
+ * (s3gan.py:312-313): *loss_out = sum_r w_r * (-sum_j labels[r,j] log softmax(logits_r)_j) / max(#{w_r != 0}, 1); labels may
+ * be soft; weights [rows] nullable (= 1).  dlogits (nullable) receives d loss / d logits. */
+int cgan_softmax_xent(cgan_ctx*, float* loss_out, float* dlogits, const float* logits, const float* labels,
+                      const float* weights, int rows, int cols);
+
 /* ---- optimizer (tf.train.AdamOptimizer + tf.train.ExponentialMovingAverage, gans/modular_gan.py:498-508) ---- */
 /* One fused multi-tensor step over a flat parameter buffer.  *step_dev (int32, device) is incremented first; then
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updated; p -= lr_t*m/(sqrt(v)+eps).  If ema != NULL:

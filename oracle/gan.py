@@ -297,3 +297,101 @@ class SsganOracle(GanOracle):
       d_loss = d_loss + c_real * self.w_d
       g_loss = g_loss + c_fake * self.w_g
     return (d_loss if for_d else None), g_loss
+
+
+# --------------------------------------------------------------------------- S3GAN (gans/s3gan.py)
+
+class S3ganOracle(SsganOracle):
+  """gans/s3gan.py:39-321 restated: rotation head (103-134), projection discriminator on real-or-predicted labels (136-158,
+  160-173), predictor trained with weighted cross entropy on the labelled real examples (305-318).  No penalty term."""
+
+  def __init__(self, cfg, rotated_batch_fraction=None, self_supervision="rotation", weight_rotation_loss_d=1.0,
+               weight_rotation_loss_g=0.2, project_y=False, use_predictor=False, use_soft_pred=False, weight_class_loss=1.0,
+               **kw):
+    GanOracle.__init__(self, cfg, **kw)
+    if use_predictor and not project_y:
+      raise ValueError("Using predictor requires projection.")
+    self.fraction, self.self_supervision = rotated_batch_fraction, self_supervision
+    self.w_d, self.w_g, self.w_class = weight_rotation_loss_d, weight_rotation_loss_g, weight_class_loss
+    self.project_y, self.use_predictor, self.use_soft_pred = project_y, use_predictor, use_soft_pred
+
+  def one_hot(self, labels):
+    """tf.one_hot: a label of -1 ("no label") gives a row of zeros."""
+    lab = torch.as_tensor(labels).long()
+    out = torch.zeros(lab.shape[0], self.cfg.num_classes, dtype=self.dtype)
+    ok = lab >= 0
+    out[ok, lab[ok]] = 1.0
+    return out
+
+  def _head(self, x, y):
+    d, logits, rep = nets.discriminator(self.store, self.cfg, x, y, True)
+    assert rep.dim() == 2
+    avail = (y.sum(1, keepdim=True) > 0.5).to(self.dtype) if y is not None else None
+    rot = None
+    if "rotation" in self.self_supervision:
+      with self.store.scope("discriminator_rotation"):
+        rot = nets.linear(self.store, self.cfg, rep, 4, "score_classify", use_sn=self.cfg.d_sn)
+    if not self.project_y:
+      return d, logits, rot, None, avail
+    aux = None
+    if self.use_predictor:
+      with self.store.scope("discriminator_predictor"):
+        aux = nets.linear(self.store, self.cfg, rep, y.shape[1], "predictor_linear", use_sn=self.cfg.d_sn, use_bias=True)
+      if self.use_soft_pred:
+        y_pred = torch.softmax(aux, -1)
+      else:
+        y_pred = torch.nn.functional.one_hot(aux.argmax(1), aux.shape[1]).to(self.dtype)
+      y = ((1.0 - avail) * y_pred + avail * y).detach()
+    with self.store.scope("discriminator_projection"):
+      k = self.store.get("kernel", (y.shape[1], rep.shape[1]), ("glorot_normal",))
+      if self.cfg.d_sn:
+        k = nets.spectral_norm(self.store, self.cfg, k)
+      emb = y @ k
+    logits = logits + (emb * rep).sum(1, keepdim=True)
+    return torch.sigmoid(logits), logits, rot, aux, avail
+
+  def build(self, batch):
+    GanOracle.build(self, batch)
+    h, w, c = self.cfg.image_shape
+    with torch.no_grad():
+      self._head(torch.zeros(2 * batch, h, w, c, dtype=self.dtype),
+                 None if not self.conditional else self.one_hot(np.zeros(2 * batch, np.int64)))
+      for k, v in self.store.vars.items():          # graph construction runs no ops (moving averages / u_var untouched)
+        if k.endswith("moving_mean"):
+          v.zero_()
+        elif k.endswith("moving_variance"):
+          v.fill_(1.0)
+    return self
+
+  def create_loss(self, images, generated, y, sampled_y, alpha=None, for_d=True):
+    bs = images.shape[0]
+    rotation = self.self_supervision == "rotation"
+    n = 0
+    if rotation:
+      assert bs % self.fraction == 0
+      n = (bs // self.fraction) // 4
+      assert n > 0
+      all_images = torch.cat([images, rotate_images(images[bs - n:], (1, 2, 3)), generated,
+                              rotate_images(generated[bs - n:], (1, 2, 3))], 0)
+      all_y = torch.cat([y, y[bs - n:].repeat(3, 1), sampled_y, sampled_y[bs - n:].repeat(3, 1)], 0) if self.conditional else None
+    else:
+      all_images = torch.cat([images, generated], 0)
+      all_y = torch.cat([y, sampled_y], 0) if self.conditional else None
+    d_all, d_logits, rot, aux, avail = self._head(all_images, all_y)
+    half = d_all.shape[0] // 2
+    assert d_all.shape[0] == 2 * bs + 6 * n
+    d_loss, _, _, g_loss = get_losses(self.loss, d_all[:bs], d_all[half:half + bs], d_logits[:bs], d_logits[half:half + bs])
+    if rotation:
+      rb = 4 * n
+      onehot = torch.nn.functional.one_hot(torch.arange(4).repeat_interleave(n), 4).to(self.dtype)
+      real_loss = -(onehot * torch.log(torch.softmax(rot[half - rb:half], -1) + 1e-10)).sum(1).mean()
+      fake_loss = -(onehot * torch.log(torch.softmax(rot[2 * half - rb:], -1) + 1e-10)).sum(1).mean()
+      d_loss = d_loss + real_loss * self.w_d
+      g_loss = g_loss + fake_loss * self.w_g
+    if self.use_predictor:
+      w = avail[:bs, 0]
+      ce = -(y * torch.log_softmax(aux[:bs], -1)).sum(1)
+      present = (w != 0).sum()
+      class_loss = (w * ce).sum() / present if int(present) > 0 else (w * ce).sum() * 0.0     # SUM_BY_NONZERO_WEIGHTS
+      d_loss = d_loss + self.w_class * class_loss
+    return (d_loss if for_d else None), g_loss

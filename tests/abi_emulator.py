@@ -146,7 +146,9 @@ class EmulatedLib(object):
   def cgan_one_hot(self, out, labels, n, classes):
     o = f32(out, n * classes).reshape(n, classes)
     o[:] = 0
-    o[np.arange(n), i32(labels, n)] = 1
+    lab = i32(labels, n)
+    ok = (lab >= 0) & (lab < classes)          # tf.one_hot: an out-of-range index (S3GAN's -1 = "no label") is a zero row
+    o[np.arange(n)[ok], lab[ok]] = 1
 
   # ---- contractions -------------------------------------------------------------------------
   def _conv_tensors(self, d, x_ptr, w_ptr):
@@ -429,6 +431,27 @@ class EmulatedLib(object):
     f32(loss_out, 1)[0] = float(loss.detach())
     if dlogits is not None:
       f32(dlogits, rows * nrot)[:] = z.grad.numpy().astype(np.float32).ravel()
+
+  def cgan_row_has_label(self, out, y, rows, cols):
+    f32(out, rows)[:] = (f32(y, rows * cols).reshape(rows, cols).sum(1) > 0.5).astype(np.float32)
+
+  def cgan_argmax_one_hot(self, out, logits, rows, cols):
+    z = f32(logits, rows * cols).reshape(rows, cols)
+    o = f32(out, rows * cols).reshape(rows, cols)
+    o[:] = 0
+    o[np.arange(rows), z.argmax(1)] = 1
+
+  def cgan_softmax_xent(self, loss_out, dlogits, logits, labels, weights, rows, cols):
+    z = torch.from_numpy(f32(logits, rows * cols).reshape(rows, cols).copy()).double().requires_grad_(True)
+    lab = torch.from_numpy(f32(labels, rows * cols).reshape(rows, cols).copy()).double()
+    w = torch.ones(rows, dtype=torch.float64) if weights is None else torch.from_numpy(f32(weights, rows).copy()).double()
+    ce = -(lab * torch.log_softmax(z, -1)).sum(1)
+    present = float((w != 0).sum())
+    loss = (w * ce).sum() / present if present > 0 else (w * ce).sum() * 0.0
+    loss.backward()
+    f32(loss_out, 1)[0] = float(loss.detach())
+    if dlogits is not None:
+      f32(dlogits, rows * cols)[:] = z.grad.numpy().astype(np.float32).ravel()
 
   def cgan_add(self, y, a, b, n):
     f32(y, n)[:] = f32(a, n) + f32(b, n)
