@@ -4,8 +4,9 @@
 //
 // The reference materialises the [Lq, Lk] score matrix (tf.matmul -> tf.nn.softmax -> tf.matmul); at BigGAN-128 that is
 // 4096 x 1024 floats per image, 4.3 GB per batch of 256, crossing HBM three times per direction.  Here the scores never
-// leave the SM: S tiles are produced by tcgen05.mma into TMEM, read by the softmax warps with tcgen05.ld, exponentiated,
-// written as TF32 into a 128B-swizzled K-major shared-memory tile and consumed from there by the second tcgen05.mma.
+// leave the SM — not even the tensor memory: S tiles are produced by tcgen05.mma into TMEM, read by the softmax warps with
+// tcgen05.ld, exponentiated, rounded to TF32 and written back IN PLACE with tcgen05.st, and the second tcgen05.mma takes them
+// as its A operand straight from TMEM (no shared-memory tile, no generic -> async proxy fence on the per-tile chain).
 //
 // Operand tiles stream through multi-stage shared-memory rings filled by ONE polling TMA thread (the first version refilled
 // a single buffer after its last reader retired: every tile then paid a full TMA round trip, ~5000 clk per tile in all three
@@ -45,7 +46,6 @@ constexpr size_t AT_SMEM_MAX = 227 * 1024;
 
 struct AtParams {
   int lq, lk, dk, dv;
-  int np;               // fwd: P buffers (1: two CTAs per SM, 2: one CTA per SM with deeper rings)
   int ns_a, ns_b;       // ring depths: fwd K / V tiles; dq: key-tile ring (both operand groups); dkv: K-major / MN-major query groups
   int kq;               // MMA k-steps of the score contraction: ceil(dk / 8)
   int kv;               // MMA k-steps of a contraction over dv: ceil(dv / 8)
@@ -128,14 +128,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// one 128-byte row (32 floats) of a K-major 128B-swizzled [rows x 32] chunk: 16-byte unit u of row r lives at unit u ^ (r & 7)
-__device__ __forceinline__ void store_row32(uint32_t chunk_base, int row, const float (&v)[32]) {
-  const uint32_t ra = chunk_base + (uint32_t)row * 128u;
-  const int x = row & 7;
-#pragma unroll
-  for (int u = 0; u < 8; ++u) sts128(ra + (uint32_t)((u ^ x) << 4), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
-}
-
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -145,8 +137,30 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// tcgen05.st 32 lanes x 32 columns: every thread writes 32 consecutive fp32 columns of ITS TMEM lane (the probabilities /
+// dS go back where the scores came from: the next tcgen05.mma reads them as its A operand straight from TMEM)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+        "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+        "f"(v[30]), "f"(v[31]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem: 128 lanes x 8 fp32 columns per K step] * B[smem descriptor]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 // one row of `dst` from the accumulator columns [0, ncols) at `taddr`, scaled; this thread takes the 32-column chunks
 // c_begin, c_begin + c_step, ...
@@ -163,8 +177,8 @@ __device__ __forceinline__ void store_acc_row(float* dst, uint32_t taddr, int nc
 }
 
 // ------------------------------------------------------------------------------------------------------------ forward
-// shared memory: Q 16 KB | P 2 x 32 KB | K ring ns_a x 8 KB | V ring ns_b x (vg x 8 KB) | barriers | row max / sum exchange.
-// TMEM: S0 @0, S1 @64, O @128 (256 columns).
+// shared memory: Q 16 KB | K ring ns_a x 8 KB | V ring ns_b x (vg x 8 KB) | barriers | row max / sum exchange.
+// TMEM (256 columns): S0 / P0 @0, S1 / P1 @64, O @128.
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AtParams p) {
@@ -172,8 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int v_bytes = p.vg * 2 * 4096;
   uint8_t* sQ = smem;
-  uint8_t* sP = smem + 16384;
-  uint8_t* sK = sP + p.np * 32768;
+  uint8_t* sK = smem + 16384;
   uint8_t* sV = sK + p.ns_a * 8192;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.ns_b * v_bytes);
   uint64_t* q_full = bars;                          // 1
@@ -181,17 +194,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* k_empty = k_full + AT_MAX_STAGES;
   uint64_t* v_full = k_empty + AT_MAX_STAGES;
   uint64_t* v_empty = v_full + AT_MAX_STAGES;
-  uint64_t* s_full = v_empty + AT_MAX_STAGES;       // 2
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;                   // 2
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* o_full = p_empty + 2;                   // 26 barriers
+  uint64_t* s_full = v_empty + AT_MAX_STAGES;       // 2: scores of a tile are in TMEM
+  uint64_t* s_empty = s_full + 2;                   // 2: pass 1 — the softmax warps have read them
+  uint64_t* p_ready = s_empty + 2;                  // 2: pass 2 — the probabilities are back in TMEM
+  uint64_t* pv_done = p_ready + 2;                  // 2: pass 2 — P V retired: the buffer may take new scores
+  uint64_t* o_full = pv_done + 2;                   // 26 barriers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
   float* sX = reinterpret_cast<float*>(bars + 32);       // [2][128]: row maxima / row sums of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_TQ, img = blockIdx.y;
-  const int nkt = p.lk / AT_TK;
+  const int nkt = p.lk / AT_TK;                     // even (lk is a multiple of 128): tile parity == buffer in both passes
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
@@ -205,7 +218,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], AT_SWARPS); mbar_init(&p_full[s], AT_SWARPS); mbar_init(&p_empty[s], 1);
+        mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], AT_SWARPS); mbar_init(&p_ready[s], AT_SWARPS); mbar_init(&pv_done[s], 1);
       }
       mbar_init(o_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -251,12 +264,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 1) {
     const uint32_t id_s = idesc(AT_TK, 0), id_pv = idesc(p.nv, 1);
-    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
     bwait(q_full, 0);
+    // scores of tile `it` (0 .. 2 nkt - 1) into buffer it & 1.  The buffer's previous tenant is tile it - 2: in pass 1 it is
+    // free once the softmax warps have read it (s_empty), in pass 2 once the P V product that reads it has retired (pv_done)
     auto issue_s = [&](int it) {
       const int ks = it % p.ns_a, sb = it & 1;
       bwait(&k_full[ks], (it / p.ns_a) & 1);
-      bwait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
+      if (it >= 2) {
+        if (it - 2 < nkt) bwait(&s_empty[sb], ((it - 2) >> 1) & 1);
+        else bwait(&pv_done[sb], ((it - 2 - nkt) >> 1) & 1);
+      }
       fence_after();
       if (lane == 0) {
         for (int k = 0; k < p.kq; ++k)
@@ -270,15 +288,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     issue_s(nkt);
     for (int j = 0; j < nkt; ++j) {
       if (j + 1 < nkt) issue_s(nkt + j + 1);
-      const int vs = j % p.ns_b, pb = j % p.np;
-      bwait(&p_full[pb], (j / p.np) & 1);
+      const int vs = j % p.ns_b, sb = j & 1;
+      bwait(&p_ready[sb], (j >> 1) & 1);
       bwait(&v_full[vs], (j / p.ns_b) & 1);
       fence_after();
       if (lane == 0) {
-        for (int kk = 0; kk < AT_TK / 8; ++kk)
-          umma_tf32(tmem + 128, desc_k(aP + pb * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32),
-                    desc_mn(aV + vs * v_bytes + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_pv, (j | kk) ? 1u : 0u);
-        umma_commit(&p_empty[pb]);
+        for (int kk = 0; kk < AT_TK / 8; ++kk)           // A = P from TMEM: 8 fp32 columns per K step
+          umma_tf32_ts(tmem + 128, tmem + (uint32_t)(sb * AT_TK + kk * 8),
+                       desc_mn(aV + vs * v_bytes + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_pv, (j | kk) ? 1u : 0u);
+        umma_commit(&pv_done[sb]);
         umma_commit(&v_empty[vs]);
         if (j == nkt - 1) umma_commit(o_full);
       }
@@ -287,7 +305,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   } else {
     const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
-    const uint32_t aP = smem_u32(sP) + (uint32_t)(half * 16384);
     float m = -INFINITY;
     for (int it = 0; it < nkt; ++it) {
       const int s = it & 1;
@@ -308,22 +325,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float m2 = m * AT_LOG2E;
     float l = 0.f;
     for (int j = 0; j < nkt; ++j) {
-      const int it = nkt + j, s = it & 1, pb = j % p.np;
+      const int it = nkt + j, s = it & 1;
       bwait(&s_full[s], (it >> 1) & 1);
       fence_after();
       uint32_t r[32];
       tmem_ld32(tl + (uint32_t)(s * AT_TK), r);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
       float pv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) { pv[i] = rnd_tf32(ex2(fmaf(__uint_as_float(r[i]), AT_LOG2E, -m2))); l += pv[i]; }
-      bwait(&p_empty[pb], ((j / p.np) & 1) ^ 1);
-      store_row32(aP + (uint32_t)(pb * 32768), row, pv);
-      fence_async_smem();
+      tmem_st32(tl + (uint32_t)(s * AT_TK), pv);           // in place: the probabilities replace the scores
+      fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[pb]);
+      if (lane == 0) mbar_arrive(&p_ready[s]);
     }
     sX[half * 128 + row] = l;
     softmax_bar();
@@ -343,8 +356,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // -------------------------------------------------------------------------------------------------------- backward: dQ
-// shared memory: Q 16 KB | dO vg x 16 KB | dS 32 KB | key-tile ring ns_a x [K (K-major) 8 KB | V (K-major) vg x 8 KB |
-// K (MN-major) 8 KB] | barriers.  TMEM (512 columns): buffer b @ b*128: S @+0, dP @+64; dQ @256.
+// shared memory: Q 16 KB | dO vg x 16 KB | key-tile ring ns_a x [K (K-major) 8 KB | V (K-major) vg x 8 KB | K (MN-major) 8 KB] |
+// barriers.  TMEM (512 columns): buffer b @ b*128: S -> dS @+0, dP @+64; dQ @256.
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
@@ -354,19 +367,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int stage_bytes = 16384 + p.vg * 8192;     // [K K-major 8 KB | V K-major vg x 8 KB | K MN-major 8 KB]
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + 16384;
-  uint8_t* sdS = sdO + p.vg * 16384;
-  uint8_t* ring = sdS + 32768;
+  uint8_t* ring = sdO + p.vg * 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.ns_a * stage_bytes);
   uint64_t* q_full = bars;
   uint64_t* km_full = bars + 1;                     // AT_MAX_STAGES each
   uint64_t* km_empty = km_full + AT_MAX_STAGES;
   uint64_t* mn_full = km_empty + AT_MAX_STAGES;
   uint64_t* mn_empty = mn_full + AT_MAX_STAGES;
-  uint64_t* sd_full = mn_empty + AT_MAX_STAGES;     // 2
-  uint64_t* sd_empty = sd_full + 2;
-  uint64_t* ds_full = sd_empty + 2;
-  uint64_t* ds_empty = ds_full + 1;
-  uint64_t* dq_full = ds_empty + 1;                 // 24 barriers
+  uint64_t* sd_full = mn_empty + AT_MAX_STAGES;     // 2: S and dP of a tile are in TMEM
+  uint64_t* ds_ready = sd_full + 2;                 // 2: dS is back in TMEM
+  uint64_t* dq_done = ds_ready + 2;                 // 2: dQ += dS K retired: the buffer may take the next tile
+  uint64_t* dq_full = dq_done + 2;                  // 24 barriers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dq_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,8 +390,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int s = 0; s < AT_MAX_STAGES; ++s) {
         mbar_init(&km_full[s], 1); mbar_init(&km_empty[s], 1); mbar_init(&mn_full[s], 1); mbar_init(&mn_empty[s], 1);
       }
-      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
-      mbar_init(ds_full, AT_SWARPS); mbar_init(ds_empty, 1); mbar_init(dq_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&ds_ready[s], AT_SWARPS); mbar_init(&dq_done[s], 1); }
+      mbar_init(dq_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -426,13 +437,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     const uint32_t id_s = idesc(AT_TK, 0), id_dq = idesc(32, 1);
-    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aR = smem_u32(ring), adS = smem_u32(sdS);
+    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aR = smem_u32(ring);
     bwait(q_full, 0);
     auto issue_sd = [&](int j) {
       const int b = j & 1, s = j % p.ns_a;
       const uint32_t aKk = aR + s * stage_bytes, aVk = aKk + 8192;
       bwait(&km_full[s], (j / p.ns_a) & 1);
-      bwait(&sd_empty[b], ((j >> 1) & 1) ^ 1);
+      if (j >= 2) bwait(&dq_done[b], ((j - 2) >> 1) & 1);        // the buffer's previous tile has been consumed by its dQ product
       fence_after();
       if (lane == 0) {
         for (int k = 0; k < p.kq; ++k)
@@ -448,16 +459,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     issue_sd(0);
     for (int j = 0; j < nkt; ++j) {
       if (j + 1 < nkt) issue_sd(j + 1);
-      const int s = j % p.ns_a;
+      const int s = j % p.ns_a, b = j & 1;
       const uint32_t aKm = aR + s * stage_bytes + 8192 + p.vg * 8192;
-      bwait(ds_full, j & 1);
+      bwait(&ds_ready[b], (j >> 1) & 1);
       bwait(&mn_full[s], (j / p.ns_a) & 1);
       fence_after();
       if (lane == 0) {
-        for (int kk = 0; kk < AT_TK / 8; ++kk)
-          umma_tf32(tmem + 256, desc_k(adS + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aKm + (kk >> 2) * 4096 + (kk & 3) * 1024),
-                    id_dq, (j | kk) ? 1u : 0u);
-        umma_commit(ds_empty);
+        for (int kk = 0; kk < AT_TK / 8; ++kk)           // A = dS from TMEM (it replaced S)
+          umma_tf32_ts(tmem + 256, tmem + (uint32_t)(b * 128 + kk * 8), desc_mn(aKm + (kk >> 2) * 4096 + (kk & 3) * 1024), id_dq,
+                       (j | kk) ? 1u : 0u);
+        umma_commit(&dq_done[b]);
         umma_commit(&mn_empty[s]);
         if (j == nkt - 1) umma_commit(dq_full);
       }
@@ -466,7 +477,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   } else {
     const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
-    const uint32_t adS = smem_u32(sdS) + (uint32_t)(half * 16384);
     const long long grow = (long long)img * p.lq + q0 + row;
     const float lse2 = p.lse[grow] * AT_LOG2E, dsum = p.dsum[grow];
     for (int j = 0; j < nkt; ++j) {
@@ -476,18 +486,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       uint32_t rs[32], rd[32];
       tmem_ld32(tl + (uint32_t)(b * 128), rs);
       tmem_ld32(tl + (uint32_t)(b * 128 + 64), rd);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sd_empty[b]);
       float ds[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         ds[i] = rnd_tf32(ex2(fmaf(__uint_as_float(rs[i]), AT_LOG2E, -lse2)) * (__uint_as_float(rd[i]) - dsum));
-      bwait(ds_empty, (j & 1) ^ 1);
-      store_row32(adS, row, ds);
-      fence_async_smem();
+      tmem_st32(tl + (uint32_t)(b * 128), ds);
+      fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&ds_ready[b]);
     }
     bwait(dq_full, 0);
     fence_after();
@@ -503,25 +509,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------------- backward: dK, dV
 // One CTA per 128 keys; query tiles of 64.  S^T = K Q^T and dP^T = V dO^T (M = keys, N = queries) so that P^T and dS^T come out
-// in the A-operand orientation of dV += P^T dO and dK += dS^T Q.
-// shared memory: K 16 KB | V vg x 16 KB | P^T 32 KB | dS^T 32 KB | ring ns_a x [Q (K-major, 64 q) 8 KB | dO (K-major) vg x 8 KB] |
-// ring ns_b x [Q (MN-major) 8 KB | dO (MN-major) vg x 8 KB] | lse, D of the query tile 2 x 2 x 64 floats | barriers.  The whole
-// 227 KB are in use at dv = 96, so the buffer is NOT re-aligned in the kernel: the 1024-byte alignment the swizzled layouts
-// need is asserted (extern __shared__ __align__(1024)).
-// TMEM (512 columns): buffer b @ b*128: S^T @+0, dP^T @+64; dK @256; dV @320.
+// in the A-operand orientation of dV += P^T dO and dK += dS^T Q — and stay in TMEM, where they replace S^T and dP^T.
+// shared memory: K 16 KB | V vg x 16 KB | ring ns_a x [Q (K-major, 64 q) 8 KB | dO (K-major) vg x 8 KB] |
+// ring ns_b x [Q (MN-major) 8 KB | dO (MN-major) vg x 8 KB] | lse, D of the query tile 2 x 2 x 64 floats | barriers.
+// TMEM (512 columns): buffer b @ b*128: S^T -> P^T @+0, dP^T -> dS^T @+64; dK @256; dV @320.
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_vk,
                     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_qm, const __grid_constant__ CUtensorMap tm_dom, const AtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if (smem_u32(smem) & 1023u) __trap();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = 8192 + p.vg * 8192;
   uint8_t* sK = smem;
   uint8_t* sV = sK + 16384;
-  uint8_t* sPt = sV + p.vg * 16384;
-  uint8_t* sdSt = sPt + 32768;
-  uint8_t* ringk = sdSt + 32768;                             // K-major Q / dO tiles
+  uint8_t* ringk = sV + p.vg * 16384;                        // K-major Q / dO tiles
   uint8_t* ringm = ringk + p.ns_a * stage_bytes;             // MN-major Q / dO tiles
   float* sL = reinterpret_cast<float*>(ringm + p.ns_b * stage_bytes);        // [2][64] lse * log2(e)
   float* sD = sL + 128;                                      // [2][64]
@@ -532,10 +533,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   uint64_t* qm_full = qk_empty + AT_MAX_STAGES;
   uint64_t* qm_empty = qm_full + AT_MAX_STAGES;
   uint64_t* sd_full = qm_empty + AT_MAX_STAGES;     // 2
-  uint64_t* sd_empty = sd_full + 2;
-  uint64_t* pt_full = sd_empty + 2;
-  uint64_t* pt_empty = pt_full + 1;
-  uint64_t* acc_full = pt_empty + 1;                // 24 barriers
+  uint64_t* pt_ready = sd_full + 2;                 // 2: P^T and dS^T are back in TMEM
+  uint64_t* acc_done = pt_ready + 2;                // 2: dV / dK products of the buffer retired
+  uint64_t* acc_full = acc_done + 2;                // 24 barriers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -548,8 +548,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       for (int s = 0; s < AT_MAX_STAGES; ++s) {
         mbar_init(&qk_full[s], 1); mbar_init(&qk_empty[s], 1); mbar_init(&qm_full[s], 1); mbar_init(&qm_empty[s], 1);
       }
-      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&sd_empty[s], AT_SWARPS); }
-      mbar_init(pt_full, AT_SWARPS); mbar_init(pt_empty, 1); mbar_init(acc_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&sd_full[s], 1); mbar_init(&pt_ready[s], AT_SWARPS); mbar_init(&acc_done[s], 1); }
+      mbar_init(acc_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -597,14 +597,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     }
   } else if (warp == 1) {
     const uint32_t id_s = idesc(AT_TK, 0), id_dk = idesc(32, 1), id_dv = idesc(p.nv, 1);
-    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aRk = smem_u32(ringk), aRm = smem_u32(ringm), aPt = smem_u32(sPt),
-                   adSt = smem_u32(sdSt);
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aRk = smem_u32(ringk), aRm = smem_u32(ringm);
     bwait(kv_full, 0);
     auto issue_sd = [&](int i) {
       const int b = i & 1, s = i % p.ns_a;
       const uint32_t aQk = aRk + s * stage_bytes, adOk = aQk + 8192;
       bwait(&qk_full[s], (i / p.ns_a) & 1);
-      bwait(&sd_empty[b], ((i >> 1) & 1) ^ 1);
+      if (i >= 2) bwait(&acc_done[b], ((i - 2) >> 1) & 1);
       fence_after();
       if (lane == 0) {
         for (int k = 0; k < p.kq; ++k)
@@ -620,19 +619,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     issue_sd(0);
     for (int i = 0; i < nqt; ++i) {
       if (i + 1 < nqt) issue_sd(i + 1);
-      const int s = i % p.ns_b;
+      const int s = i % p.ns_b, b = i & 1;
       const uint32_t aQm = aRm + s * stage_bytes, adOm = aQm + 8192;
-      bwait(pt_full, i & 1);
+      bwait(&pt_ready[b], (i >> 1) & 1);
       bwait(&qm_full[s], (i / p.ns_b) & 1);
       fence_after();
       if (lane == 0) {
-        for (int kk = 0; kk < AT_TK / 8; ++kk)
-          umma_tf32(tmem + 320, desc_k(aPt + (kk >> 2) * 16384 + (kk & 3) * 32),
-                    desc_mn(adOm + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024), id_dv, (i | kk) ? 1u : 0u);
-        for (int kk = 0; kk < AT_TK / 8; ++kk)
-          umma_tf32(tmem + 256, desc_k(adSt + (kk >> 2) * 16384 + (kk & 3) * 32), desc_mn(aQm + (kk >> 2) * 4096 + (kk & 3) * 1024),
-                    id_dk, (i | kk) ? 1u : 0u);
-        umma_commit(pt_empty);
+        for (int kk = 0; kk < AT_TK / 8; ++kk)           // dV += P^T dO,  A = P^T from TMEM
+          umma_tf32_ts(tmem + 320, tmem + (uint32_t)(b * 128 + kk * 8), desc_mn(adOm + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024),
+                       id_dv, (i | kk) ? 1u : 0u);
+        for (int kk = 0; kk < AT_TK / 8; ++kk)           // dK += dS^T Q, A = dS^T from TMEM
+          umma_tf32_ts(tmem + 256, tmem + (uint32_t)(b * 128 + 64 + kk * 8), desc_mn(aQm + (kk >> 2) * 4096 + (kk & 3) * 1024), id_dk,
+                       (i | kk) ? 1u : 0u);
+        umma_commit(&acc_done[b]);
         umma_commit(&qm_empty[s]);
         if (i == nqt - 1) umma_commit(acc_full);
       }
@@ -642,7 +641,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
     const int quarter = warp & 3, half = (warp - 2) >> 2, row = quarter * 32 + lane;
     const int st = threadIdx.x - 64;             // 0..255 among the softmax threads
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32);
-    const uint32_t aPt = smem_u32(sPt) + (uint32_t)(half * 16384), adSt = smem_u32(sdSt) + (uint32_t)(half * 16384);
     // per-query lse and D of a tile (columns here) are staged in shared memory and read as broadcasts; the global loads for
     // tile i + 1 are issued at the top of tile i so that their latency is off the per-tile critical path
     const long long gq0 = (long long)img * p.lq + (st < AT_TK ? st : 0);
@@ -662,9 +660,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       uint32_t rs[32], rd[32];
       tmem_ld32(tl + (uint32_t)(b * 128), rs);
       tmem_ld32(tl + (uint32_t)(b * 128 + 64), rd);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sd_empty[b]);
       float pt[32], ds[32];
       const float* lrow = sL + b * AT_TK + half * 32;
       const float* drow = sD + b * AT_TK + half * 32;
@@ -674,12 +669,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
         pt[c] = rnd_tf32(pe);
         ds[c] = rnd_tf32(pe * (__uint_as_float(rd[c]) - drow[c]));
       }
-      bwait(pt_empty, (i & 1) ^ 1);
-      store_row32(aPt, row, pt);
-      store_row32(adSt, row, ds);
-      fence_async_smem();
+      tmem_st32(tl + (uint32_t)(b * 128), pt);
+      tmem_st32(tl + (uint32_t)(b * 128 + 64), ds);
+      fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pt_full);
+      if (lane == 0) mbar_arrive(&pt_ready[b]);
     }
     bwait(acc_full, 0);
     fence_after();
@@ -758,18 +752,13 @@ int cgan_attention_fwd(cgan_ctx* ctx, const float* q, const float* k, const floa
   if (!make_rows_map(&tq, q, dk, lq, batch, 128, false) || !make_rows_map(&tk, k, dk, lk, batch, 64, false) ||
       !make_rows_map(&tv, v, dv, lk, batch, 32, true))
     return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_fwd");
-  // Two CTAs per SM (default: one P buffer, rings as deep as half an SM's shared memory allows) or one CTA per SM with two P
-  // buffers and deeper rings (env CGAN_ATTN_CTAS=1).  Measured (profiles/r2_attention_*.txt): the softmax warps are bound
-  // by TMEM reads and the exponentials, which two resident CTAs overlap better than deeper prefetch in one.
+  // Two CTAs per SM (default; 256 TMEM columns each) with rings as deep as half an SM's shared memory allows, or one CTA
+  // per SM with deeper rings (env CGAN_ATTN_CTAS=1).  Measured (profiles/r2_attention_*.txt): two resident CTAs overlap
+  // each other's per-tile dependency chains better than deeper prefetch in one.
   static const int ctas = []() { const char* e = getenv("CGAN_ATTN_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
-  const size_t v_stage = (size_t)p.vg * 8192;
-  size_t budget = ctas == 2 ? (AT_SMEM_MAX - 2048) / 2 : AT_SMEM_MAX;
-  p.np = ctas == 2 ? 1 : 2;
-  size_t fixed = 16384 + (size_t)p.np * 32768 + 1280 + 1024;
-  if (ctas == 2 && fixed + 2 * 8192 + v_stage > budget) {       // dv = 128: one CTA per SM
-    budget = AT_SMEM_MAX; p.np = 2; fixed = 16384 + 65536 + 1280 + 1024;
-  }
-  p.ns_a = budget == AT_SMEM_MAX ? AT_MAX_STAGES : 2;
+  const size_t v_stage = (size_t)p.vg * 8192, fixed = 16384 + 1280 + 1024;
+  const size_t budget = ctas == 2 ? (AT_SMEM_MAX - 2048) / 2 : AT_SMEM_MAX;
+  p.ns_a = AT_MAX_STAGES;
   p.ns_b = (int)((budget - fixed - (size_t)p.ns_a * 8192) / v_stage);
   if (p.ns_b > AT_MAX_STAGES) p.ns_b = AT_MAX_STAGES;
   if (p.ns_b > lk / AT_TK) p.ns_b = lk / AT_TK;
@@ -808,7 +797,7 @@ int cgan_attention_bwd(cgan_ctx* ctx, const float* q, const float* k, const floa
     return cgan_fail(ctx, CGAN_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", "cgan_attention_bwd");
   {
     p.out = dq; p.out2 = nullptr;
-    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 32768 + 256 + 1024, stage = 16384 + (size_t)p.vg * 8192;
+    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 256 + 1024, stage = 16384 + (size_t)p.vg * 8192;
     p.ns_a = (int)((AT_SMEM_MAX - fixed) / stage);
     if (p.ns_a > AT_MAX_STAGES) p.ns_a = AT_MAX_STAGES;
     if (p.ns_a > lk / AT_TK) p.ns_a = lk / AT_TK;
@@ -821,8 +810,7 @@ int cgan_attention_bwd(cgan_ctx* ctx, const float* q, const float* k, const floa
   }
   {
     p.out = dk_out; p.out2 = dv_out;
-    // no alignment slack here (the kernel asserts the 1024-byte alignment of its buffer): at dv = 96 that is the third stage
-    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 65536 + 1024 + 256, stage = 8192 + (size_t)p.vg * 8192;
+    const size_t fixed = 16384 + (size_t)p.vg * 16384 + 1024 + 256 + 1024, stage = 8192 + (size_t)p.vg * 8192;
     int total = (int)((AT_SMEM_MAX - fixed) / stage);
     if (total > 2 * AT_MAX_STAGES) total = 2 * AT_MAX_STAGES;
     p.ns_a = (total + 1) / 2;           // K-major group: needed first (S^T, dP^T)
