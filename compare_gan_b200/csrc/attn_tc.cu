@@ -446,11 +446,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (j >= 2) bwait(&dq_done[b], ((j - 2) >> 1) & 1);        // the buffer's previous tile has been consumed by its dQ product
       fence_after();
       if (lane == 0) {
-        for (int k = 0; k < p.kq; ++k)
-          umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aQ + k * 32), desc_k(aKk + k * 32), id_s, k ? 1u : 0u);
-        for (int kk = 0; kk < p.kv; ++kk)
+        // the two products accumulate into different TMEM columns: their MMAs are issued alternately so that consecutive
+        // instructions in the tensor pipe do not depend on each other (a K step of N = 64 is 32 clk of math, far less than
+        // the latency of a dependent accumulation)
+        for (int kk = 0; kk < p.kv; ++kk) {
           umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(adO + (kk >> 2) * 16384 + (kk & 3) * 32),
                     desc_k(aVk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
+          if (kk < p.kq)
+            umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aQ + kk * 32), desc_k(aKk + kk * 32), id_s, kk ? 1u : 0u);
+        }
         umma_commit(&km_empty[s]);
         umma_commit(&sd_full[b]);
       }
@@ -606,11 +610,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       if (i >= 2) bwait(&acc_done[b], ((i - 2) >> 1) & 1);
       fence_after();
       if (lane == 0) {
-        for (int k = 0; k < p.kq; ++k)
-          umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aK + k * 32), desc_k(aQk + k * 32), id_s, k ? 1u : 0u);
-        for (int kk = 0; kk < p.kv; ++kk)
+        for (int kk = 0; kk < p.kv; ++kk) {              // alternate the two independent accumulations (see the dQ kernel)
           umma_tf32(tmem + (uint32_t)(b * 128 + 64), desc_k(aV + (kk >> 2) * 16384 + (kk & 3) * 32),
                     desc_k(adOk + (kk >> 2) * 8192 + (kk & 3) * 32), id_s, kk ? 1u : 0u);
+          if (kk < p.kq)
+            umma_tf32(tmem + (uint32_t)(b * 128), desc_k(aK + kk * 32), desc_k(aQk + kk * 32), id_s, kk ? 1u : 0u);
+        }
         umma_commit(&qk_empty[s]);
         umma_commit(&sd_full[b]);
       }
@@ -625,12 +630,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       bwait(&qm_full[s], (i / p.ns_b) & 1);
       fence_after();
       if (lane == 0) {
-        for (int kk = 0; kk < AT_TK / 8; ++kk)           // dV += P^T dO,  A = P^T from TMEM
+        for (int kk = 0; kk < AT_TK / 8; ++kk) {         // alternately: dV += P^T dO (A = P^T from TMEM), dK += dS^T Q (A = dS^T)
           umma_tf32_ts(tmem + 320, tmem + (uint32_t)(b * 128 + kk * 8), desc_mn(adOm + (kk >> 2) * p.vg * 4096 + (kk & 3) * 1024),
                        id_dv, (i | kk) ? 1u : 0u);
-        for (int kk = 0; kk < AT_TK / 8; ++kk)           // dK += dS^T Q, A = dS^T from TMEM
           umma_tf32_ts(tmem + 256, tmem + (uint32_t)(b * 128 + 64 + kk * 8), desc_mn(aQm + (kk >> 2) * 4096 + (kk & 3) * 1024), id_dk,
                        (i | kk) ? 1u : 0u);
+        }
         umma_commit(&acc_done[b]);
         umma_commit(&qm_empty[s]);
         if (i == nqt - 1) umma_commit(acc_full);
