@@ -89,7 +89,7 @@ def _grad_feeds_tc(t):
   """Will the gradient w.r.t. `t` be the dy operand of a tensor-core contraction?  (Then its producer stores it
   TF32-rounded and the contraction skips its rounding pass; a wrong guess only costs that pass.)"""
   if not tf32_on() or (t is not None and len(t.shape) == 4 and t.shape[-1] <= 4):
-    return False          # (3-channel image-side contractions run in the exact-fp32 streaming kernels)
+    return False          # (3-channel image-side contractions round their thin operand while gathering the patch tensor)
   for _ in range(4):
     if t is None or t.node is None:
       return False
