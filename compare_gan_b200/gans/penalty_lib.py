@@ -21,8 +21,10 @@ def wgangp_penalty(discriminator, x, x_fake, y, is_training, alpha=None):
   if alpha is None:
     # tf.random.uniform (penalty_lib.py:72-73) through the library's counter-based generator (cgan_random_uniform): no
     # torch op on the product path; successive draws advance the offset
+    from ..tpu import tpu_ops
     alpha = K.empty(x.shape[0], 1, 1, 1)
-    K._call("random_uniform", alpha.ptr, alpha.numel, _ALPHA_RNG["seed"], _ALPHA_RNG["offset"])
+    # every replica draws its own coefficients (the reference's per-replica tf.random.uniform): the rank selects the stream
+    K._call("random_uniform", alpha.ptr, alpha.numel, _ALPHA_RNG["seed"] + tpu_ops.replica_id(), _ALPHA_RNG["offset"])
     _ALPHA_RNG["offset"] += alpha.numel
   interpolates = K.interpolate(x, x_fake, alpha)
   interpolates.req = True                      # differentiate the logits wrt this leaf

@@ -21,6 +21,13 @@ def num_replicas():
   return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
+def replica_id():
+  """Rank of this process among the replicas (0 when single-replica)."""
+  if _FORCE_LOCAL[0] or not (dist.is_available() and dist.is_initialized()):
+    return 0
+  return dist.get_rank()
+
+
 _P2P = {"state": None, "max": 0}       # None: not tried yet; True: peer buffers connected; False: unavailable (NCCL only)
 
 

@@ -560,7 +560,7 @@ class EmulatedLib(object):
     gt = torch.from_numpy(f32(g, n * per).reshape(n, per).copy()).requires_grad_(True)
     slopes = torch.sqrt(1e-4 + (gt * gt).sum(1))
     pen = ((slopes - 1.0) ** 2).mean()
-    f32(penalty_out, 1)[0] = float(pen)
+    f32(penalty_out, 1)[0] = float(pen.detach())
     if dg is not None:
       (weight * pen).backward()
       f32(dg, n * per)[:] = gt.grad.numpy().ravel()

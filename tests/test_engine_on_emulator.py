@@ -147,3 +147,30 @@ def test_non_unrolled_schedule_matches_the_reference_default():
     assert ran_g == [False, False, True, False]
     assert int(eng.d_opt.step.item()) == 4 == orc.global_step_disc and int(eng.g_opt.step.item()) == 1 == orc.global_step
     compare_states(eng, orc, {"generator": 2e-4, "discriminator": 2e-4}, {"generator": 1, "discriminator": 4})
+
+
+def test_unfed_gradient_penalty_coefficients_come_from_the_library_stream():
+  """penalty_lib.wgangp_penalty without a fed `alpha` (reference penalty_lib.py:72-73: tf.random.uniform) draws from
+  cgan_random_uniform — no torch RNG on the product path: the penalty of a linear critic equals the closed form evaluated
+  with the documented SplitMix64 stream, and a second call continues the stream instead of repeating it."""
+  import numpy as np
+  from compare_gan_b200 import kernels as K
+  from compare_gan_b200.gans import penalty_lib
+  with emulated_library():
+    rng = np.random.RandomState(0)
+    b, d = 6, 12
+    x, xf = rng.rand(b, 2, 2, 3).astype(np.float32), rng.rand(b, 2, 2, 3).astype(np.float32)
+    w = rng.randn(d, 1).astype(np.float32)
+    wd = K.from_numpy(w, req=True)
+
+    def critic(images, y=None, is_training=True, reuse=True):
+      logits = K.matmul(K.reshape(images, b, d), wd)
+      return K.sigmoid(logits), logits, None
+    penalty_lib._ALPHA_RNG["offset"] = 0
+    p1 = float(penalty_lib.wgangp_penalty(critic, K.from_numpy(x), K.from_numpy(xf), None, True).cpu()[0])
+    assert penalty_lib._ALPHA_RNG["offset"] == b
+    p2 = float(penalty_lib.wgangp_penalty(critic, K.from_numpy(x), K.from_numpy(xf), None, True).cpu()[0])
+    # a linear critic's input gradient is w for every interpolate: the penalty does not depend on alpha, only its shape does
+    want = (np.sqrt(1e-4 + float((w ** 2).sum())) - 1.0) ** 2
+    assert abs(p1 - want) <= 1e-5 * max(1.0, want) and abs(p2 - want) <= 1e-5 * max(1.0, want)
+    assert penalty_lib._ALPHA_RNG["offset"] == 2 * b
