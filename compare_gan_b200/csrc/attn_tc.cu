@@ -8,13 +8,12 @@
 // tcgen05.ld, exponentiated, rounded to TF32 and written back IN PLACE with tcgen05.st, and the second tcgen05.mma takes them
 // as its A operand straight from TMEM (no shared-memory tile, no generic -> async proxy fence on the per-tile chain).
 //
-// Operand tiles stream through multi-stage shared-memory rings filled by ONE polling TMA thread (the first version refilled
-// a single buffer after its last reader retired: every tile then paid a full TMA round trip, ~5000 clk per tile in all three
-// kernels whatever their arithmetic — profiles/r2_attention_*.txt).
+// Operand tiles stream through multi-stage shared-memory rings filled by ONE polling TMA thread, which never blocks on one
+// ring while another could be refilled (measured history of the variants: DESIGN.md section 7, profiles/r2_attention_*.txt).
 // Forward (attn_fwd_kernel): one CTA per 128 queries of one image, key tiles of 64.
 //   pass 1: S_j = Q K_j^T (M=128, N=64, K=8 per MMA, dk <= 32 zero-padded by TMA) -> row maxima m.
 //   pass 2: S_j again (K has 4x fewer channels than V: recomputing costs 1/4 of the P V MMAs and avoids rescaling O in
-//           TMEM), p = exp(s - m), l += p, P -> smem, O += P V_j (V is MN-major as it lies in HBM: the filter-gradient
+//           TMEM), p = exp(s - m), l += p, P -> TMEM (in place), O += P V_j (V is MN-major as it lies in HBM: the filter-gradient
 //           kernel's SWIZZLE_128B_BASE32B operand form).  Epilogue: O / l, lse = m + log l (kept for the backward).
 // Backward: P is recomputed from Q, K and lse (no [Lq, Lk] tensor is ever stored); with D = rowsum(dO * O),
 //   dS = P * (dO V^T - D),  dQ = dS K,  dK = dS^T Q,  dV = P^T dO.
@@ -22,8 +21,7 @@
 //   attn_bwd_dkv_kernel: one CTA per 128 keys, loops over query tiles of 64 (accumulates dK, dV in TMEM) — S^T and dP^T
 //   are produced directly (M = keys), so no transposition pass exists and the summation order is fixed (deterministic).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = softmax / epilogue:
-// TMEM lane quarter = warp % 4, two warps per quarter, each owning one 32-column half of every 64-column score tile (one
-// warp per SM sub-partition could not hide the tcgen05.ld / MUFU latencies of its own dependent chain).
+// TMEM lane quarter = warp % 4, two warps per quarter, each owning one 32-column half of every 64-column score tile.
 //
 // Operands are consumed as TF32: callers pass tensors already rounded to the nearest TF32 value (cgan_round_tf32 or a
 // producer's ROUND_OUT epilogue); P and dS are rounded to nearest by the softmax warps.  Accumulation is fp32 in TMEM.
