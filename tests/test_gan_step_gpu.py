@@ -62,9 +62,12 @@ def _cycles_both(eng, orc, batch, image_shape, z_dim, k, n_cycles=2, num_classes
       compare_grads(eng, orc, grad_tol, g_tol=5e-2, flips=flips)
   assert eng.global_step == n_cycles and eng.global_step_disc == n_cycles * k     # modular_gan_test.py:175-177
   # a flipped (leaky-)ReLU mask sends the two Adam trajectories apart by a fraction of the step size, which the BN
-  # moving statistics then see: the tight bound on the non-trainable state only holds when the masks agreed
+  # moving statistics then see: the tight bound on the non-trainable state holds when the masks agreed and widens with the
+  # NUMBER of flipped elements (2e-3 per flip), saturating at 2e-2
+  state_tol = min(2e-2, 2e-3 * (1 + total_flips))
+  print("[%s] %d ReLU mask flips over %d cycles -> non-trainable state bound %.1e" % (eng._architecture, total_flips, n_cycles, state_tol))
   return compare_states(eng, orc, {"generator": g_lr, "discriminator": d_lr},
-                        {"generator": n_cycles, "discriminator": n_cycles * k}, state_tol=2e-3 if total_flips == 0 else 2e-2)
+                        {"generator": n_cycles, "discriminator": n_cycles * k}, state_tol=state_tol)
 
 
 def _frozen_d_gradients(batch, image_shape, z_dim, k, num_classes=0, gp=False, z_normal=False, tol=1e-3, **pair_kw):
